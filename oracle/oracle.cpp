@@ -1,0 +1,712 @@
+// TEST INFRASTRUCTURE — CPU oracle for the integrator2 hot path.  NOT part of the product:
+// only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+// load this library.  The product (integrator2_b200/csrc) never calls into it.
+//
+// Plain C++17 + OpenMP restatement (FP64, libm) of the reference's algorithm for the path
+// EvaluatorJ3DK::integrateOver{Simple,Attached,Not}Neighbors.  Every function cites the
+// reference file:line it follows (paths relative to /root/reference).  The order of the
+// floating-point operations follows the reference so that differences against the reference's
+// CUDA build are limited to libm-vs-libdevice and FMA contraction (expected 1e-13..1e-15).
+//
+// Parity status: the reference ships no golden vectors.  This oracle is pinned
+// against binary dumps of the reference's own CUDA build run on a B200 (oracle/ref_dump.cu,
+// fixtures under tests/golden/, see tests/test_oracle_vs_reference_golden.py).
+//
+// Documented deviations from the reference:
+//  * q_thetaPsi_zero leaves its .x (q_Theta) uninitialised (src/evaluators/evaluatorJ3DK.cu:474-481);
+//    the doc comment there says q_Theta = 0 (:471) — the oracle returns 0.
+//  * refined-task sums are accumulated in a fixed (lexicographic child) order; the reference
+//    uses FP64 atomicAdd in arbitrary order (src/NumericalIntegrator3d.cu:160-173).
+//  * fixed refinement level N >= 2: the reference maps tasks through a stale index table
+//    (SURVEY.md D6); the oracle integrates over the 4^N children of the task's own cell i.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+// ---- constants: src/common/constants.h:11-65 -------------------------------------------------
+constexpr double kDoubleMin = 2e-6;
+constexpr double kEpsZero = 1e-6;
+constexpr double kEpsZero2 = 1e-10;
+constexpr double kEpsPsiTheta2 = kEpsZero * kEpsZero;
+constexpr double kEpsIntegration = 1e-5;
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kTwoPi = 6.28318530717958647692;
+constexpr double kRecipFourPi = 0.079577471545947667884;
+constexpr int kMaxRefineLevel = 5;
+constexpr int kMaxGauss = 13;
+
+struct V3 { double x, y, z; };
+struct V4 { double x, y, z, w; };
+struct Tri { int a, b, c; };
+
+// ---- vector helpers: src/common/cuda_math.cuh:80-230 -----------------------------------------
+inline V3 add(V3 p, V3 q) { return {p.x + q.x, p.y + q.y, p.z + q.z}; }
+inline V3 sub(V3 p, V3 q) { return {p.x - q.x, p.y - q.y, p.z - q.z}; }
+inline V3 neg(V3 p) { return {-p.x, -p.y, -p.z}; }
+inline V3 mul(double s, V3 p) { return {p.x * s, p.y * s, p.z * s}; }
+inline double dot(V3 p, V3 q) { return p.x * q.x + p.y * q.y + p.z * q.z; }
+inline V3 cross(V3 p, V3 q) { return {p.y * q.z - p.z * q.y, p.z * q.x - p.x * q.z, p.x * q.y - p.y * q.x}; }
+inline double len2(V3 p) { return dot(p, p); }
+inline double len(V3 p) { return std::sqrt(dot(p, p)); }
+inline V3 divs(V3 p, double s) { return {p.x / s, p.y / s, p.z / s}; }
+inline V3 unit(V3 p) { const double inv = 1.0 / len(p); return {p.x * inv, p.y * inv, p.z * inv}; }  // cuda_math.cuh:232-241
+inline double sqr(double x) { return x * x; }
+inline V4 add4(V4 p, V4 q) { return {p.x + q.x, p.y + q.y, p.z + q.z, p.w + q.w}; }
+inline V4 sub4(V4 p, V4 q) { return {p.x - q.x, p.y - q.y, p.z - q.z, p.w - q.w}; }
+inline V4 mul4(double s, V4 p) { return {p.x * s, p.y * s, p.z * s, p.w * s}; }
+inline V4 vec4(V3 p) { return {p.x, p.y, p.z, 0.0}; }
+inline double norm1(V3 p) { return std::fabs(p.x) + std::fabs(p.y) + std::fabs(p.z); }
+inline double norm1(V4 p) { return std::fabs(p.x) + std::fabs(p.y) + std::fabs(p.z) + std::fabs(p.w); }
+
+// src/common/cuda_math.cuh:31-49
+inline double sgn(double x) {
+    if (std::fabs(x) < kDoubleMin) return 0.0;
+    return (x > kDoubleMin) ? 1.0 : -1.0;
+}
+inline double argf(double x) { return (x > kDoubleMin) ? 0.0 : kPi; }
+
+// src/common/cuda_math.cu:14-27
+inline double angle(V3 p, V3 q) {
+    const double den = std::sqrt(len2(p) * len2(q));
+    if (den < kEpsZero) return 0;
+    const double c = dot(p, q) / den;
+    if (c >= 1.0) return 0;
+    if (c <= -1.0) return kPi;
+    return std::acos(c);
+}
+
+// src/common/cuda_math.cuh:270-280
+inline V4 divide(V4 n, V4 d) {
+    V4 r;
+    r.x = (std::fabs(n.x) < kDoubleMin && std::fabs(d.x) < kDoubleMin) ? 0.0 : n.x / d.x;
+    r.y = (std::fabs(n.y) < kDoubleMin && std::fabs(d.y) < kDoubleMin) ? 0.0 : n.y / d.y;
+    r.z = (std::fabs(n.z) < kDoubleMin && std::fabs(d.z) < kDoubleMin) ? 0.0 : n.z / d.z;
+    r.w = (std::fabs(n.w) < kEpsZero2 && std::fabs(d.w) < kEpsZero2) ? 0.0 : n.w / d.w;
+    return r;
+}
+
+// ---- quadrature rule (process-global like the reference's __constant__ symbols,
+//      src/NumericalIntegrator3d.cu:9-11,197-211) ----------------------------------------------
+struct Quadrature {
+    int n = 0;
+    int order = 0;
+    V3 L[kMaxGauss];
+    double w[kMaxGauss];
+} g_qf;
+
+struct Mesh {
+    std::vector<V3> verts;
+    std::vector<Tri> cells;
+    std::vector<V3> normals;
+    std::vector<double> measures;
+    std::vector<int> pairs[3];  // i, j, k triples, i<j, lexicographic
+};
+
+inline V3 vert(const Mesh &m, int v) { return m.verts[v]; }
+inline int triAt(const Tri &t, int k) { return k == 0 ? t.a : (k == 1 ? t.b : t.c); }
+
+// src/evaluators/evaluatorJ3DK.cu:827-847
+inline Tri rotateLeft(const Tri &t, int shift) {
+    if (shift > 3) return {0, 0, 0};
+    if (shift == 3) return t;
+    Tri r;
+    int *out[3] = {&r.a, &r.b, &r.c};
+    for (int k = 0; k < 3; ++k) {
+        int from = k + shift;
+        if (from >= 3) from -= 3;
+        *out[k] = triAt(t, from);
+    }
+    return r;
+}
+
+// src/evaluators/evaluatorJ3DK.cu:782-795 (the break leaves only the inner loop)
+inline void shiftsSimple(const Tri &t1, const Tri &t2, int &s1, int &s2) {
+    s1 = 0; s2 = 0;
+    for (int p = 0; p < 3; ++p)
+        for (int q = 0; q < 3; ++q)
+            if (triAt(t1, p) == triAt(t2, q)) { s1 = p; s2 = q; break; }
+}
+
+// src/evaluators/evaluatorJ3DK.cu:797-825: positions of the vertices OPPOSITE the shared edge
+inline void shiftsAttached(const Tri &t1, const Tri &t2, int &s1, int &s2) {
+    int mp[2] = {-1, -1}, mq[2] = {-1, -1}, cnt = 0;
+    for (int p = 0; p < 3; ++p)
+        for (int q = 0; q < 3; ++q)
+            if (triAt(t1, p) == triAt(t2, q) && cnt < 2) { mp[cnt] = p; mq[cnt] = q; ++cnt; }
+    s1 = 0; s2 = 0;
+    for (int p = 0; p < 3; ++p) if (mp[0] != p && mp[1] != p) { s1 = p; break; }
+    for (int q = 0; q < 3; ++q) if (mq[0] != q && mq[1] != q) { s2 = q; break; }
+}
+
+// ---- thetaPsi: src/evaluators/evaluatorJ3DK.cu:266-313 ---------------------------------------
+V4 thetaPsi(V3 pt, V3 A, V3 B, V3 C) {
+    V3 ova = sub(pt, A), ovb = sub(pt, B), ovc = sub(pt, C);
+    const double lva = len(ova), lvb = len(ovb), lvc = len(ovc);
+    ova = divs(ova, lva); ovb = divs(ovb, lvb); ovc = divs(ovc, lvc);
+
+    const V3 taua = unit(sub(C, B)), taub = unit(sub(A, C)), tauc = unit(sub(B, A));
+    const double rac = dot(ova, tauc), rbc = dot(ovb, tauc), rba = dot(ovb, taua);
+    const double rca = dot(ovc, taua), rcb = dot(ovc, taub), rab = dot(ova, taub);
+
+    double t1, t2, t3;
+    if (std::fabs(rbc + 1.0) < 0.5 * kEpsPsiTheta2) t1 = std::log(lvb / lva);
+    else t1 = std::log((lva * (1.0 + rac)) / (lvb * (1.0 + rbc)));
+    if (std::fabs(rca + 1.0) < 0.5 * kEpsPsiTheta2) t2 = std::log(lvc / lvb);
+    else t2 = std::log((lvb * (1.0 + rba)) / (lvc * (1.0 + rca)));
+    if (std::fabs(rab + 1.0) < 0.5 * kEpsPsiTheta2) t3 = std::log(lva / lvc);
+    else t3 = std::log((lvc * (1.0 + rcb)) / (lva * (1.0 + rab)));
+
+    V4 r = vec4(add(add(mul(t1, tauc), mul(t2, taua)), mul(t3, taub)));
+    r.w = 2.0 * std::atan2(dot(cross(ova, ovb), ovc), 1.0 + dot(ova, ovb) + dot(ovb, ovc) + dot(ovc, ova));
+    return r;
+}
+
+// ---- singular part at a point, edge-adjacent: src/evaluators/evaluatorJ3DK.cu:315-350 --------
+V4 singularPartAttached(const Mesh &m, V3 pt, int i, int j) {
+    int si, sj;
+    shiftsAttached(m.cells[i], m.cells[j], si, sj);
+    const Tri tj = rotateLeft(m.cells[j], sj);
+    const V3 JA = vert(m, tj.a), JB = vert(m, tj.b), JC = vert(m, tj.c);
+
+    V3 va = sub(pt, JB), vb = sub(pt, JC);
+    const double lva = len(va), lvb = len(vb);
+    va = divs(va, lva); vb = divs(vb, lvb);
+
+    const V3 taua = unit(sub(JA, JC)), taub = unit(sub(JB, JA));
+    V3 tauc = sub(JC, JB);
+    const double ilvc = 1.0 / len(tauc);
+    tauc = mul(ilvc, tauc);
+
+    const double l1 = std::log((lvb * dot(tauc, sub(tauc, vb))) / (lva * dot(tauc, sub(tauc, va))));
+    const double l2 = std::log(lva * dot(taub, add(taub, va)) * ilvc);
+    const double l3 = std::log(lvb * dot(taua, sub(taua, vb)) * ilvc);
+    V4 r = vec4(sub(sub(mul(l1, tauc), mul(l2, taub)), mul(l3, taua)));
+    r.w = 2.0 * (std::atan2(dot(cross(va, taub), tauc), dot(sub(taub, tauc), add(taub, va))) -
+                 std::atan2(dot(cross(vb, taua), tauc), dot(sub(taua, tauc), sub(taua, vb))));
+    return r;
+}
+
+// direction e and angles (delta_a, delta_b) shared by the point-wise and the integrated
+// vertex-adjacent singular parts: src/evaluators/evaluatorJ3DK.cu:376-399 and :698-723
+struct SimpleFrame { V3 e; double da, db; };
+SimpleFrame simpleFrame(V3 normalI, V3 normalJ, V3 taua, V3 taub) {
+    V3 e = cross(normalI, normalJ);
+    if (len2(e) < kEpsZero2) e = taub;
+    else e = unit(e);
+    auto deltas = [&](V3 d, double &da, double &db) {
+        da = std::atan2(dot(cross(taua, d), normalJ), -dot(d, taua));
+        db = std::atan2(dot(cross(d, taub), normalJ), dot(d, taub));
+    };
+    double da, db;
+    deltas(e, da, db);
+    if ((kPi - std::fabs(da) < kEpsZero) || (kPi - std::fabs(db) < kEpsZero)) {
+        e = mul(-1, e);
+        deltas(e, da, db);
+    }
+    if ((da * db < 0) && (std::fabs(da - db) > kPi)) {
+        e = mul(-1, e);
+        deltas(e, da, db);
+    }
+    return {e, da, db};
+}
+
+// ---- singular part at a point, vertex-adjacent: src/evaluators/evaluatorJ3DK.cu:352-407 ------
+V4 singularPartSimple(const Mesh &m, V3 pt, int i, int j) {
+    int si, sj;
+    shiftsSimple(m.cells[i], m.cells[j], si, sj);
+    const Tri tj = rotateLeft(m.cells[j], sj);
+    const V3 JA = vert(m, tj.a), JB = vert(m, tj.b), JC = vert(m, tj.c);
+
+    V3 ovc = sub(pt, JA);
+    const double lvc = len(ovc);
+    ovc = divs(ovc, lvc);
+
+    const V3 taua = unit(sub(JA, JC)), taub = unit(sub(JB, JA));
+    const SimpleFrame fr = simpleFrame(m.normals[i], m.normals[j], taua, taub);
+    const V3 e = fr.e;
+
+    const double invAri = 1.0 / std::sqrt(m.measures[i]);  // rsqrt on the device (:401)
+
+    const double la = std::log((lvc * (1 + dot(taua, ovc))) * invAri);
+    const double lb = std::log((lvc * (1 - dot(taub, ovc))) * invAri);
+    V4 r = vec4(neg(add(mul(la, taua), mul(lb, taub))));
+    r.w = 2.0 * (std::atan2(dot(cross(ovc, taua), e), dot(sub(e, ovc), sub(e, taua))) +
+                 std::atan2(dot(cross(ovc, taub), e), dot(sub(e, ovc), add(e, taub))));
+    return r;
+}
+
+struct SC { double s, c; };
+inline SC sincosOf(double a) { return {std::sin(a), std::cos(a)}; }
+
+// src/evaluators/evaluatorJ3DK.cu:418-421
+inline double phi(SC alpha, SC gamma, double sinXi, double cosLambda) {
+    return 2.0 * std::atan2(sinXi * alpha.s * gamma.s, 1.0 - alpha.c + gamma.c + cosLambda);
+}
+
+struct Q2 { double theta, psi; };
+
+// src/evaluators/evaluatorJ3DK.cu:438-461
+Q2 qThetaPsi(SC al, SC be, SC ga, SC nu, SC xi, double cosMu, double cosLambda) {
+    const double phi1 = phi(al, ga, xi.s, cosLambda);
+    const double phi2 = phi({al.s, -al.c}, {ga.s, -ga.c}, xi.s, cosLambda);
+    const double k = 1.0 / (al.s * (1.0 - cosMu * cosMu));
+    Q2 r;
+    r.theta = phi1 + ga.s * nu.s * k * (
+                  (be.c * ga.s - xi.c * be.s * ga.c) * phi2 +
+                  xi.s * be.s * (0.5 * (1.0 + cosMu) * std::log((1.0 + be.c) / (1.0 - nu.c)) +
+                                 0.5 * (1.0 - cosMu) * std::log((1.0 - be.c) / (1.0 + nu.c)) +
+                                 std::log((1.0 + cosLambda) / (1.0 - ga.c))));
+    r.psi = 1.5 - k * (
+                be.s * (nu.c + cosMu * cosLambda) * std::log(1.0 + cosLambda) +
+                nu.s * (be.c + cosMu * ga.c) * std::log(1.0 - ga.c) +
+                be.s * (1.0 - cosMu) * (nu.c - cosLambda) * std::log(be.s / nu.s) +
+                nu.s * be.s * (be.s * ga.c - xi.c * ga.s * be.c) * std::log((1.0 - nu.c) / (1.0 + be.c)) +
+                phi2 * xi.s * ga.s * nu.s * be.s);
+    return r;
+}
+
+// src/evaluators/evaluatorJ3DK.cu:474-481 (.theta defined as 0, see header)
+Q2 qThetaPsiZero(SC be, SC nu, double sinAlpha) {
+    Q2 r;
+    r.theta = 0.0;
+    r.psi = 1.5 - (nu.c * be.s * std::log(1.0 + nu.c) + nu.s * be.c * std::log(1.0 - be.c) + sinAlpha
+                   - be.s + nu.s + be.s * nu.c * std::log(be.s / nu.s)) / sinAlpha;
+    return r;
+}
+
+// src/evaluators/evaluatorJ3DK.cu:511-601
+Q2 qThetaPsiCont(SC xi, double mu, SC scMu, double logSinMu, double logSinNu, double psi, SC scPsi, double nu, SC scNu,
+                 double kappa, double sinKappa, double sinNuPsi, double sinMuPsi, double delta, SC scDelta,
+                 double cosLambda, double cosTheta, double cosEta, double cosSigma, double cosChi) {
+    Q2 r;
+    const double logOneCosTheta = std::log(1.0 + cosTheta);
+    const double logOneCosLambda = std::log(1.0 + cosLambda);
+    const double Lambda1 = logOneCosLambda - logOneCosTheta + logSinNu - logSinMu;
+    const double Lambda2 = std::log(std::tan(0.5 * nu) * std::tan(0.5 * mu));
+
+    const SC hd = sincosOf(0.5 * delta);
+    const double tanHalfDelta = hd.s / hd.c;
+    const SC hmp = sincosOf(0.5 * (mu - psi)), hnp = sincosOf(0.5 * (nu + psi));
+    const double Amu = std::atan2(tanHalfDelta * hmp.c * xi.s, tanHalfDelta * hmp.c * xi.c + hmp.s);
+    const double Anu = std::atan2(tanHalfDelta * hnp.s * xi.s, tanHalfDelta * hnp.s * xi.c + hnp.c);
+
+    SC t1 = sincosOf(0.5 * (mu - psi) - 0.5 * (nu + psi));
+    const SC t2 = sincosOf(0.5 * kappa);
+    const double W = std::atan2(scDelta.s * t2.s * xi.s, t2.c + scDelta.s * t1.c * xi.c + scDelta.c * t1.s);
+
+    t1 = sincosOf(delta - psi);
+    const double D = 1.0 / (sqr(t1.s) + scDelta.s * scPsi.s * (1.0 - xi.c) * (t1.c + cosSigma));
+    const double G = scPsi.c * (scDelta.s * cosSigma * xi.c + scDelta.c * cosChi - sqr(scDelta.s) / scPsi.s);
+
+    const double gent = 2.0 * (Anu * scMu.s * sinNuPsi - Amu * scNu.s * sinMuPsi -
+                               D * scMu.s * scNu.s * scDelta.s * (W * cosEta + 0.5 * scPsi.s * xi.s * (Lambda1 - Lambda2 * cosSigma))) /
+                        (scPsi.s * sinKappa);
+    const double gens = 0.5 * (3.0 - std::log(2.0)) +
+                        (scMu.s * scNu.s / sinKappa) * ((logOneCosLambda - logOneCosTheta) * scPsi.c / scPsi.s +
+                                                        D * (Lambda1 * scDelta.s * cosEta / scPsi.s + Lambda2 * cosChi -
+                                                             2.0 * W * scDelta.s * xi.s - G * (logSinNu - logSinMu))) -
+                        (scMu.c * scNu.s * (logOneCosLambda - logSinMu) + scMu.s * scNu.c * (logOneCosTheta - logSinNu)) / sinKappa -
+                        0.5 * (logSinMu + logSinNu - std::log(sinKappa));
+
+    const double mulPsi = sgn(xi.s * scPsi.s);
+    const double mulDelta = sgn(xi.s * scDelta.s);
+
+    if ((std::fabs(xi.s) < kEpsZero) && (1.0 - std::fabs(cosSigma) < 0.5 * kEpsZero2) && (std::fabs(scPsi.s) > kEpsZero)) {
+        const double ara = argf(std::sin(0.5 * (nu + psi)) * cosSigma);
+        const double arb = argf(std::cos(0.5 * (mu - psi)) * cosSigma);
+        r.theta = 2.0 * mulPsi * cosSigma * xi.c / (sinKappa * scPsi.s) * (scMu.s * sinNuPsi * ara - scNu.s * sinMuPsi * arb);
+        r.psi = 0.5 * (1.0 - std::log(2.0)) - 0.5 * std::log((1.0 - cosSigma * scMu.c) * (1.0 + cosSigma * scNu.c) / sinKappa) +
+                cosSigma * (scMu.s - scNu.s + 0.5 * std::sin(mu - nu) * Lambda2) / sinKappa;
+        return r;
+    }
+    if ((std::fabs(xi.s) < kEpsZero) && (std::fabs(scPsi.s) > kEpsZero)) {
+        const double are = argf(std::sin(0.5 * (nu + mu)) + std::sin(0.5 * (mu - nu) - psi + delta * xi.c));
+        const double arc = argf(1.0 / std::tan(0.5 * (nu + psi)) + std::tan(0.5 * delta) * xi.c);
+        const double ard = argf(std::tan(0.5 * (mu - psi)) + std::tan(0.5 * delta) * xi.c);
+        r.theta = 2.0 * mulDelta * (scDelta.s * scMu.s * scNu.s / cosChi * xi.c * are +
+                                    scMu.s * sinNuPsi * arc - scNu.s * sinMuPsi * ard) / (sinKappa * scPsi.s);
+        r.psi = gens;
+        return r;
+    }
+    if (std::fabs(std::sin(psi)) < kEpsZero) {
+        if (std::fabs(delta) > kEpsZero) {
+            r.theta = 2.0 * (scMu.s * scNu.s * (W * scDelta.c * xi.c - 0.5 * (Lambda1 - Lambda2 * cosSigma) * xi.s) / scDelta.s +
+                             (Anu + mulDelta * argf(std::sin(0.5 * (nu + psi)))) * scMu.s * scNu.c +
+                             (Amu + mulDelta * argf(std::cos(0.5 * (mu - psi)))) * scMu.c * scNu.s) / sinKappa;
+            r.psi = 0.5 * (3.0 - std::log(2.0)) -
+                    0.5 * (std::log((1.0 + cosLambda) * (1.0 + cosTheta) / sinKappa) - std::sin(mu - nu) / sinKappa * Lambda1) -
+                    scMu.s * scNu.s * ((Lambda1 * scDelta.c - Lambda2 * scPsi.c) * xi.c + 2.0 * W * xi.s) / (sinKappa * scDelta.s);
+            return r;
+        } else {
+            r.theta = 2.0 * argf(scPsi.c);
+            r.psi = 0.5 * (1.0 - std::log(2.0)) - 0.5 * std::log((1.0 - scPsi.c * scMu.c) * (1.0 + scPsi.c * scNu.c) / sinKappa) +
+                    (0.5 * std::sin(mu - nu) * Lambda1 + scPsi.c * (scMu.s - scNu.s)) / sinKappa;
+            return r;
+        }
+    }
+    r.theta = gent;
+    r.psi = gens;
+    return r;
+}
+
+// ---- analytic integral of the singular part, edge-adjacent: evaluatorJ3DK.cu:603-672 ---------
+V4 integrateSingularAttached(const Mesh &m, int i, int j) {
+    int si, sj;
+    shiftsAttached(m.cells[i], m.cells[j], si, sj);
+    const Tri ti = rotateLeft(m.cells[i], si), tj = rotateLeft(m.cells[j], sj);
+    const V3 IA = vert(m, ti.a), IB = vert(m, ti.b), IC = vert(m, ti.c);
+    const V3 JA = vert(m, tj.a), JB = vert(m, tj.b), JC = vert(m, tj.c);
+
+    const V3 taua = unit(sub(JA, JC)), taub = unit(sub(JB, JA)), tauc = unit(sub(JC, JB));
+
+    const double alpha = angle(sub(IA, IC), sub(IB, IC));
+    const double beta = angle(sub(IC, IB), sub(IA, IB));
+    const double gamma = angle(sub(JC, JB), sub(JA, JB));
+    const double delta = angle(sub(JB, JC), sub(JA, JC));
+    const double nu = kPi - alpha - beta;
+
+    const V3 nI = m.normals[i], nJ = m.normals[j];
+    const double xi = std::atan2(dot(cross(nI, nJ), tauc), dot(nI, nJ));
+
+    const SC al = sincosOf(alpha), be = sincosOf(beta), ga = sincosOf(gamma), de = sincosOf(delta), sx = sincosOf(xi);
+    SC sn;
+    sn.s = al.s * be.c + al.c * be.s;
+    sn.c = al.s * be.s - al.c * be.c;
+
+    const double cosSigma = -(al.c * de.c + sx.c * al.s * de.s);
+    const double cosMu = -(be.c * ga.c + sx.c * be.s * ga.s);
+    const double cosLambda = -(al.c * ga.c - sx.c * al.s * ga.s);
+    const double cosTheta = -(be.c * de.c - sx.c * be.s * de.s);
+
+    const double qab = sn.s * std::log(std::tan(0.5 * alpha) * std::tan(0.5 * nu)) / be.s +
+                       sn.s * std::log(std::tan(0.5 * beta) * std::tan(0.5 * nu)) / al.s +
+                       std::log(std::tan(0.5 * alpha) * std::tan(0.5 * beta));
+
+    Q2 qa, qb;
+    if ((std::fabs(xi) < kEpsZero) && (std::fabs(beta - gamma) < kEpsZero)) qa = qThetaPsiZero(be, sn, al.s);
+    else qa = qThetaPsi(al, be, ga, sn, sx, cosMu, cosLambda);
+    if ((std::fabs(xi) < kEpsZero) && (std::fabs(alpha - delta) < kEpsZero)) qb = qThetaPsiZero(al, sn, be.s);
+    else qb = qThetaPsi(be, al, de, sn, sx, cosSigma, cosTheta);
+
+    const double S = m.measures[i];
+    V4 r = vec4(mul(S, sub(add(mul(qa.psi, taub), mul(qb.psi, taua)), mul(qab, tauc))));
+    r.w = S * (qa.theta + qb.theta);
+    return r;
+}
+
+// ---- analytic integral of the singular part, vertex-adjacent: evaluatorJ3DK.cu:674-780 -------
+V4 integrateSingularSimple(const Mesh &m, int i, int j, int *orientationWarning) {
+    int si, sj;
+    shiftsSimple(m.cells[i], m.cells[j], si, sj);
+    const Tri ti = rotateLeft(m.cells[i], si), tj = rotateLeft(m.cells[j], sj);
+    const V3 IA = vert(m, ti.a), IB = vert(m, ti.b), IC = vert(m, ti.c);
+    const V3 JA = vert(m, tj.a), JB = vert(m, tj.b), JC = vert(m, tj.c);
+
+    const V3 taua = unit(sub(JA, JC)), taub = unit(sub(JB, JA));
+    const V3 nI = m.normals[i], nJ = m.normals[j];
+
+    if (orientationWarning && len2(cross(nI, nJ)) < kEpsZero2 && dot(nI, nJ) < 0) *orientationWarning = 1;  // :699-702
+    const SimpleFrame fr = simpleFrame(nI, nJ, taua, taub);
+    const V3 e = fr.e;
+
+    const double xi = std::atan2(dot(cross(nI, nJ), e), dot(nI, nJ));
+    const SC dA = sincosOf(fr.da), dB = sincosOf(fr.db), sx = sincosOf(xi);
+
+    const V3 s = sub(IC, IB);
+    const double nu = angle(sub(IA, IB), sub(IC, IB));
+    const double mu = angle(sub(IB, IC), sub(IA, IC));
+    const double kappa = angle(sub(IB, IA), sub(IC, IA));
+    const SC scMu = sincosOf(mu), scNu = sincosOf(nu);
+    const double logSinNu = std::log(scNu.s), logSinMu = std::log(scMu.s);
+    const double sinKappa = std::sin(kappa);
+
+    const double psi = std::atan2(dot(cross(e, s), nI), dot(e, s));
+    const SC scPsi = sincosOf(psi);
+    const SC np = sincosOf(nu + psi), mp = sincosOf(mu - psi);
+
+    auto pack = [&](SC d, double &cSigma, double &cChi, double &cEta, double &cTheta, double &cLambda) {
+        cSigma = d.s * scPsi.s * sx.c + d.c * scPsi.c;
+        cChi = d.s * scPsi.c * sx.c - d.c * scPsi.s;
+        cEta = d.c * scPsi.s * sx.c - d.s * scPsi.c;
+        cTheta = d.s * np.s * sx.c + d.c * np.c;
+        cLambda = d.s * mp.s * sx.c - d.c * mp.c;
+    };
+    double sgA, chA, etA, thA, laA, sgB, chB, etB, thB, laB;
+    pack(dA, sgA, chA, etA, thA, laA);
+    pack(dB, sgB, chB, etB, thB, laB);
+
+    const Q2 qa = qThetaPsiCont(sx, mu, scMu, logSinMu, logSinNu, psi, scPsi, nu, scNu, kappa, sinKappa, np.s, mp.s,
+                                fr.da, dA, laA, thA, etA, sgA, chA);
+    const Q2 qb = qThetaPsiCont(sx, mu, scMu, logSinMu, logSinNu, psi, scPsi, nu, scNu, kappa, sinKappa, np.s, mp.s,
+                                fr.db, dB, laB, thB, etB, sgB, chB);
+
+    const double S = m.measures[i];
+    V4 r = vec4(mul(S, add(mul(qa.psi, taua), mul(qb.psi, taub))));
+    r.w = (std::fabs(xi) < kEpsZero) ? 0.0 : (S * (qa.theta - qb.theta));
+    return r;
+}
+
+// ---- numerical quadrature over one (sub)triangle -------------------------------------------
+// points: src/NumericalIntegrator3d.cu:569-585 ; weighted sum: :560-567 ; kernels :87-205
+V4 quadOverTriangle(const Mesh &m, int cls, V3 A, V3 B, V3 C, double measure, int iOrig, int j) {
+    const Tri tj = m.cells[j];
+    const V3 JA = vert(m, tj.a), JB = vert(m, tj.b), JC = vert(m, tj.c);
+    V4 acc = {0, 0, 0, 0};
+    for (int g = 0; g < g_qf.n; ++g) {
+        V3 p = {0, 0, 0};
+        p = add(p, mul(g_qf.L[g].x, A));
+        p = add(p, mul(g_qf.L[g].y, B));
+        p = add(p, mul(g_qf.L[g].z, C));
+        V4 f = thetaPsi(p, JA, JB, JC);
+        if (cls == 0) f = sub4(f, singularPartSimple(m, p, iOrig, j));
+        else if (cls == 1) f = sub4(f, singularPartAttached(m, p, iOrig, j));
+        acc = add4(acc, mul4(g_qf.w[g], f));
+    }
+    return mul4(measure, acc);
+}
+
+// uniform midpoint refinement, children in kSplitCell's order (src/NumericalIntegrator3d.cu:55-72);
+// the sum over the 4^level leaves follows the lexicographic child order.
+void sumOverChildren(const Mesh &m, int cls, V3 A, V3 B, V3 C, double measure, int level, int iOrig, int j, V4 &acc) {
+    if (level == 0) {
+        acc = add4(acc, quadOverTriangle(m, cls, A, B, C, measure, iOrig, j));
+        return;
+    }
+    const V3 ma = mul(0.5, add(B, C)), mb = mul(0.5, add(C, A)), mc = mul(0.5, add(A, B));
+    const double q = 0.25 * measure;
+    sumOverChildren(m, cls, mc, B, ma, q, level - 1, iOrig, j, acc);
+    sumOverChildren(m, cls, ma, C, mb, q, level - 1, iOrig, j, acc);
+    sumOverChildren(m, cls, mb, A, mc, q, level - 1, iOrig, j, acc);
+    sumOverChildren(m, cls, ma, mb, mc, q, level - 1, iOrig, j, acc);
+}
+
+V4 regularIntegral(const Mesh &m, int cls, int i, int j, int level) {
+    const Tri ti = m.cells[i];
+    V4 acc = {0, 0, 0, 0};
+    sumOverChildren(m, cls, vert(m, ti.a), vert(m, ti.b), vert(m, ti.c), m.measures[i], level, i, j, acc);
+    return acc;
+}
+
+// src/evaluators/evaluatorJ3DK.cu:224-264
+V3 finalize(const Mesh &m, int cls, int i, int j, V4 I) {
+    const V3 n = m.normals[j];
+    double theta = I.w;
+    if (cls == 0) {
+        int p = 0;
+        const double ref = kTwoPi * m.measures[i];
+        if (theta > ref) p = -((int)std::trunc((theta - ref) / (2.0 * ref)) + 1);
+        else if (theta < -ref) p = ((int)std::trunc((-ref - theta) / (2.0 * ref)) + 1);
+        theta = theta + 2.0 * p * ref;
+    }
+    const V3 psi = {I.x, I.y, I.z};
+    return mul(kRecipFourPi, add(mul(theta, n), cross(psi, n)));
+}
+
+// Runge criterion: src/evaluators/evaluator3d.cu:76-99 (2^p multiplies the COARSER value)
+bool rungeUnconverged(V4 cur, V4 prev) {
+    const double pow2p = (double)(1 << g_qf.order);
+    const V4 num = sub4(cur, prev);
+    const V4 den = sub4(mul4(pow2p, prev), cur);
+    return norm1(divide(num, den)) > kEpsIntegration;
+}
+
+}  // namespace
+
+extern "C" {
+
+// quadrature rule: xy = n pairs (L_x, L_y); L_z = 1 - L_x - L_y (src/NumericalIntegrator3d.cu:202-206)
+int orc_set_quadrature(const double *xy, const double *w, int n, int order) {
+    if (n < 1 || n > kMaxGauss) return -1;
+    g_qf.n = n;
+    g_qf.order = order;
+    for (int g = 0; g < n; ++g) {
+        g_qf.L[g] = {xy[2 * g], xy[2 * g + 1], 1.0 - xy[2 * g] - xy[2 * g + 1]};
+        g_qf.w[g] = w[g];
+    }
+    return 0;
+}
+
+// mesh: vertices (already scaled), cells 0-based; normals/measures as src/Mesh3d.cu:23-71
+void *orc_mesh_create(const double *verts, int nv, const int *cells, int nc) {
+    Mesh *m = new Mesh;
+    m->verts.resize(nv);
+    m->cells.resize(nc);
+    for (int v = 0; v < nv; ++v) m->verts[v] = {verts[3 * v], verts[3 * v + 1], verts[3 * v + 2]};
+    for (int c = 0; c < nc; ++c) m->cells[c] = {cells[3 * c], cells[3 * c + 1], cells[3 * c + 2]};
+    m->normals.resize(nc);
+    m->measures.resize(nc);
+    for (int c = 0; c < nc; ++c) {
+        const Tri t = m->cells[c];
+        const V3 v12 = sub(m->verts[t.b], m->verts[t.a]), v13 = sub(m->verts[t.c], m->verts[t.a]);
+        m->normals[c] = unit(cross(v12, v13));
+        m->measures[c] = len(cross(v12, v13)) * 0.5;
+    }
+    return m;
+}
+
+void orc_mesh_free(void *h) { delete (Mesh *)h; }
+
+void orc_mesh_get(const void *h, double *normals, double *measures) {
+    const Mesh *m = (const Mesh *)h;
+    for (size_t c = 0; c < m->cells.size(); ++c) {
+        if (normals) { normals[3 * c] = m->normals[c].x; normals[3 * c + 1] = m->normals[c].y; normals[3 * c + 2] = m->normals[c].z; }
+        if (measures) measures[c] = m->measures[c];
+    }
+}
+
+// neighbour classification: src/Mesh3d.cu:93-142 (pairs i<j, by number of shared vertex ids;
+// 3 shared ids are dropped like in the reference).  Lists come out lexicographically sorted,
+// k = slot in the list (the reference's slot order is atomicAdd order, i.e. arbitrary).
+void orc_classify(void *h, long long *counts) {
+    Mesh *m = (Mesh *)h;
+    for (int c = 0; c < 3; ++c) m->pairs[c].clear();
+    const int n = (int)m->cells.size();
+    for (int i = 0; i < n; ++i) {
+        const Tri a = m->cells[i];
+        for (int j = i + 1; j < n; ++j) {
+            const Tri b = m->cells[j];
+            int common = 0;
+            if (a.a == b.a || a.a == b.b || a.a == b.c) ++common;
+            if (a.b == b.a || a.b == b.b || a.b == b.c) ++common;
+            if (a.c == b.a || a.c == b.b || a.c == b.c) ++common;
+            int cls = common == 0 ? 2 : (common == 1 ? 0 : (common == 2 ? 1 : -1));
+            if (cls < 0) continue;
+            std::vector<int> &L = m->pairs[cls];
+            const int k = (int)(L.size() / 3);
+            L.push_back(i); L.push_back(j); L.push_back(k);
+        }
+    }
+    for (int c = 0; c < 3; ++c) counts[c] = (long long)(m->pairs[c].size() / 3);
+}
+
+void orc_get_pairs(const void *h, int cls, int *out) {
+    const Mesh *m = (const Mesh *)h;
+    std::memcpy(out, m->pairs[cls].data(), m->pairs[cls].size() * sizeof(int));
+}
+
+void orc_theta_psi(const double *pt, const double *A, const double *B, const double *C, double *out) {
+    const V4 r = thetaPsi({pt[0], pt[1], pt[2]}, {A[0], A[1], A[2]}, {B[0], B[1], B[2]}, {C[0], C[1], C[2]});
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+void orc_singular_part(const void *h, int cls, const double *pt, int i, int j, double *out) {
+    const Mesh *m = (const Mesh *)h;
+    const V3 p = {pt[0], pt[1], pt[2]};
+    const V4 r = cls == 0 ? singularPartSimple(*m, p, i, j) : singularPartAttached(*m, p, i, j);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+void orc_integrate_singular(const void *h, int cls, int i, int j, double *out) {
+    const Mesh *m = (const Mesh *)h;
+    const V4 r = cls == 0 ? integrateSingularSimple(*m, i, j, nullptr) : integrateSingularAttached(*m, i, j);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+// regular part of n tasks (i,j,k) at a uniform refinement level: out[t] = double4
+void orc_regular_integrals(const void *h, int cls, const int *tasks, long long n, int level, double *out) {
+    const Mesh *m = (const Mesh *)h;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long long t = 0; t < n; ++t) {
+        const V4 r = regularIntegral(*m, cls, tasks[3 * t], tasks[3 * t + 1], level);
+        out[4 * t] = r.x; out[4 * t + 1] = r.y; out[4 * t + 2] = r.z; out[4 * t + 3] = r.w;
+    }
+}
+
+// Full path for one class, as EvaluatorJ3DK::integrateOver* (src/evaluators/evaluatorJ3DK.cu:849-1012).
+//   level >= 0 : fixed refinement level; level < 0 : adaptive error control (Runge rule), including
+//   the result-buffer ping-pong of :976 and the per-cell refinement counters
+//   (src/NumericalIntegrator3d.cu:461-499).
+//   integrals[n*4] : (Psi, Theta) incl. the analytic singular part ; results[n*3] : J
+//   refinements[nc] (adaptive only, may be NULL) ; stats[0] = L (last round executed),
+//   stats[1+2r] = tasks integrated in round r (refined-task count), stats[2+2r] = unconverged after round r.
+int orc_run_class(const void *h, int cls, const int *tasks, long long n, int level,
+                  double *integrals, double *results, unsigned char *refinements, long long *stats) {
+    const Mesh *m = (const Mesh *)h;
+    const int nc = (int)m->cells.size();
+    std::vector<V4> bufA(n), bufB(n);
+    std::vector<V4> *cur = &bufA, *tmp = &bufB;
+    if (stats) std::memset(stats, 0, sizeof(long long) * (3 + 2 * kMaxRefineLevel));
+    if (refinements) std::memset(refinements, 0, nc);
+
+    if (level >= 0) {
+#pragma omp parallel for schedule(dynamic, 64)
+        for (long long t = 0; t < n; ++t) (*cur)[t] = regularIntegral(*m, cls, tasks[3 * t], tasks[3 * t + 1], level);
+    } else {
+        std::vector<long long> rest(n), next;
+        for (long long t = 0; t < n; ++t) rest[t] = t;
+        auto bumpCells = [&](const std::vector<long long> &list) {
+            if (!refinements) return;
+            std::vector<unsigned char> flag(nc, 0);
+            for (long long t : list) flag[tasks[3 * t]] = 1;
+            for (int c = 0; c < nc; ++c) if (flag[c]) refinements[c] += 1;
+        };
+#pragma omp parallel for schedule(dynamic, 64)
+        for (long long t = 0; t < n; ++t) (*cur)[t] = regularIntegral(*m, cls, tasks[3 * t], tasks[3 * t + 1], 0);
+        if (stats) stats[1] = n;
+        bumpCells(rest);
+        long long remaining = n;
+        int iter = 0;
+        while (remaining && iter < kMaxRefineLevel) {
+            ++iter;
+            std::swap(cur, tmp);
+            const long long cnt = (long long)rest.size();
+#pragma omp parallel for schedule(dynamic, 16)
+            for (long long r = 0; r < cnt; ++r) {
+                const long long t = rest[r];
+                (*cur)[t] = regularIntegral(*m, cls, tasks[3 * t], tasks[3 * t + 1], iter);
+            }
+            if (stats) stats[1 + 2 * iter] = cnt << (2 * iter);
+            next.clear();
+            for (long long r = 0; r < cnt; ++r) {
+                const long long t = rest[r];
+                if (rungeUnconverged((*cur)[t], (*tmp)[t])) next.push_back(t);
+            }
+            rest.swap(next);
+            remaining = (long long)rest.size();
+            if (stats) { stats[2 + 2 * iter] = remaining; stats[0] = iter; }
+            if (remaining) bumpCells(rest);
+        }
+    }
+
+    int warn = 0;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long long t = 0; t < n; ++t) {
+        const int i = tasks[3 * t], j = tasks[3 * t + 1];
+        V4 I = (*cur)[t];
+        if (cls == 0) I = add4(I, integrateSingularSimple(*m, i, j, &warn));
+        else if (cls == 1) I = add4(I, integrateSingularAttached(*m, i, j));
+        const V3 J = finalize(*m, cls, i, j, I);
+        if (integrals) { integrals[4 * t] = I.x; integrals[4 * t + 1] = I.y; integrals[4 * t + 2] = I.z; integrals[4 * t + 3] = I.w; }
+        if (results) { results[3 * t] = J.x; results[3 * t + 1] = J.y; results[3 * t + 2] = J.z; }
+    }
+    return warn;
+}
+
+// delta for (i,j)/(j,i): src/evaluators/evaluator3d.cu:45-57 ; results has 2n entries
+void orc_symmetry_error(const double *results, long long n, double *errors) {
+    for (long long t = 0; t < n; ++t) {
+        const V3 a = {results[3 * t], results[3 * t + 1], results[3 * t + 2]};
+        const V3 b = {results[3 * (n + t)], results[3 * (n + t) + 1], results[3 * (n + t) + 2]};
+        const double d = norm1(add(a, b)) / std::max(norm1(a), norm1(b));
+        errors[t] = d;
+        errors[n + t] = d;
+    }
+}
+
+int orc_num_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+}  // extern "C"
