@@ -1,0 +1,136 @@
+/*
+ * i2_abi.h — C ABI of the B200-native integrator2 hot path (libintegrator2_b200.so).
+ *
+ * The reference (andreyypopov/integrator2) has no C ABI: its hot path sits behind the C++ abstract class
+ * Evaluator3D (src/evaluators/evaluator3d.cuh:51-53, pure virtuals integrateOverSimpleNeighbors /
+ * integrateOverAttachedNeighbors / integrateOverNotNeighbors) implemented by EvaluatorJ3DK
+ * (src/evaluators/evaluatorJ3DK.cu:849-1012).  The functions below are what a C/FFI binding of that path binds;
+ * the drop-in C++ classes in include/integrator2/ are thin callers of exactly these entry points
+ * (see INTEGRATION.md for the mapping and for a ctypes / cgo style stub).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; `d_` = device pointer on the context's device, `h_` = host pointer;
+ *   - Point3 arrays are double[n][3], double4 arrays are double[n][4] (32-byte aligned), int3 arrays int[n][3]:
+ *     the same memory layouts as the reference's Point3/double4/int3 device vectors;
+ *   - neighbour classes use the reference's enum values (src/Mesh3d.cuh:18-23):
+ *     0 = simple (vertex-adjacent), 1 = attached (edge-adjacent), 2 = not neighbours (regular);
+ *   - every function returns 0 on success, a positive cudaError_t, or a negative I2_E_* code;
+ *   - all work of a context is enqueued on one CUDA stream; functions taking h_ outputs synchronise it;
+ *   - there is no CPU fallback: without a CUDA device every call fails with a CUDA error code.
+ */
+#ifndef I2_ABI_H
+#define I2_ABI_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct i2_context i2_context;
+
+#define I2_E_BADARG (-1)     /* null pointer / negative size / class out of range                      */
+#define I2_E_NOMESH (-2)     /* i2_set_mesh was not called                                            */
+#define I2_E_NOQUAD (-3)     /* i2_set_quadrature was not called                                      */
+#define I2_E_LEVEL (-4)      /* fixed refinement level outside 0..12                                  */
+#define I2_E_TOOBIG (-5)     /* a count does not fit the 32-bit slots of the reference's int3 tasks   */
+
+#define I2_CLASS_SIMPLE 0
+#define I2_CLASS_ATTACHED 1
+#define I2_CLASS_NOT 2
+
+#define I2_LEVEL_ADAPTIVE (-1) /* automatic error control (Runge rule), NumericalIntegrator3D default     */
+
+#define I2_MATH_STRICT 0 /* regular pairs evaluated in the reference's operation order                    */
+#define I2_MATH_FAST 1   /* hoisted / un-normalised formulation (default)                                 */
+
+/* per-class statistics of one i2_integrate_class call (printed by the drop-in classes exactly like the
+ * reference prints them: src/evaluators/evaluatorJ3DK.cu:956,980 and src/evaluators/evaluator3d.cu:338) */
+typedef struct i2_stats {
+    int last_round;              /* L: number of refinement rounds executed (0 in fixed mode)                */
+    long long integrated[6];     /* refined tasks integrated in round r = unconverged(r-1) * 4^r             */
+    long long unconverged[6];    /* original tasks still unconverged after round r (r >= 1)                  */
+    int orientation_warnings;    /* coplanar vertex-adjacent pairs with opposite normals                     */
+} i2_stats;
+
+/* ---- context ---------------------------------------------------------------------------------------- */
+int i2_create(i2_context **ctx, int device);
+int i2_destroy(i2_context *ctx);
+int i2_set_stream(i2_context *ctx, void *cuda_stream);   /* optional: run on the caller's stream            */
+int i2_synchronize(i2_context *ctx);
+int i2_set_math_mode(i2_context *ctx, int mode);
+const char *i2_error_string(int code);
+
+/* ---- quadrature: replaces NumericalIntegrator3D's constant-memory upload
+ *      (src/NumericalIntegrator3d.cu:197-211).  xy = n pairs (L_x, L_y), L_z = 1 - L_x - L_y;
+ *      order = p of the Runge rule (2^p).  Process-global constant memory, like the reference.            */
+int i2_set_quadrature(i2_context *ctx, const double *h_xy, const double *h_w, int n, int order);
+
+/* ---- mesh: replaces kCalculateCellNormal/Center/Measure (src/Mesh3d.cu:23-71); any output may be NULL   */
+int i2_mesh_geometry(i2_context *ctx, const double *d_vertices, int nv, const int *d_cells, int nc,
+                     double *d_normals, double *d_centers, double *d_measures);
+/* packs vertices/tangents/normals/areas of all triangles into the SoA the kernels read (context-owned);
+ * the four input arrays are borrowed and must stay alive while the context uses the mesh                  */
+int i2_set_mesh(i2_context *ctx, const double *d_vertices, int nv, const int *d_cells, int nc,
+                const double *d_normals, const double *d_measures);
+
+/* one uniform midpoint refinement of a whole mesh, materialised (only the refined-mesh EXPORT needs it; the
+ * integrate kernels rebuild children on the fly).  Replaces kSplitCell for the fixed-level case
+ * (src/NumericalIntegrator3d.cu:37-87) with deterministic slots: the 3 new vertices of cell c go to
+ * nv_in + 3c.., its 4 children to 4c..4c+3.  Outputs: vertices[nv_in + 3 nc_in], cells[4 nc_in], measures[4 nc_in] */
+int i2_refine_mesh_once(i2_context *ctx, const double *d_vertices_in, int nv_in, const int *d_cells_in, int nc_in,
+                        const double *d_measures_in, double *d_vertices_out, int *d_cells_out, double *d_measures_out);
+
+/* ---- neighbour classification: replaces kDetermineNeighborType (src/Mesh3d.cu:93-142, 243-262).
+ *      Two passes so that the lists come out deterministic (lexicographic in (i,j), i<j, k = slot).       */
+int i2_classify_count(i2_context *ctx, const int *d_cells, int nc, long long h_counts[3]);
+int i2_classify_fill(i2_context *ctx, const int *d_cells, int nc, int *d_simple, int *d_attached, int *d_not);
+/* tasks[n..2n) = (j, i, n+idx): replaces kAddReversedPairs (src/evaluators/evaluator3d.cu:22-31)            */
+int i2_add_reversed_pairs(i2_context *ctx, int *d_tasks, long long n);
+
+/* ---- THE HOT PATH: replaces EvaluatorJ3DK::integrateOver{Simple,Attached,Not}Neighbors
+ *      (src/evaluators/evaluatorJ3DK.cu:849-1012) including numericalIntegration, the refinement loop of
+ *      NumericalIntegrator3D (src/NumericalIntegrator3d.cu:369-558) and compareIntegrationResults
+ *      (src/evaluators/evaluator3d.cu:297-341).
+ *   d_tasks      int3[n]  (i, j, k); the result of task t is stored at slot t
+ *   level        >= 0 fixed uniform refinement of the control panel i, I2_LEVEL_ADAPTIVE for error control
+ *   d_integrals  double4[n] out: (Psi, Theta) including the closed-form singular part
+ *   d_results    Point3[n]  out: J(K_i, K_j)
+ *   d_refinements unsigned char[nc] in/out, adaptive only, may be NULL: += 1 per round in which cell i still
+ *                has an unconverged task (NumericalIntegrator3D::getRefinementsRequired)
+ *   d_converged  unsigned char[n] out, adaptive only, may be NULL (getIntegralsConverged)
+ *   h_stats      may be NULL; when given the call synchronises the stream before returning                 */
+int i2_integrate_class(i2_context *ctx, int cls, const int *d_tasks, long long n, int level,
+                       double *d_integrals, double *d_results, unsigned char *d_refinements,
+                       unsigned char *d_converged, i2_stats *h_stats);
+
+/* delta = |J_ij + J_ji|_1 / max(|J_ij|_1, |J_ji|_1) for slots t and n_half+t: replaces
+ * kCalculateIntegrationError (src/evaluators/evaluator3d.cu:45-57)                                         */
+int i2_symmetry_error(i2_context *ctx, const double *d_results, long long n_half, double *d_errors);
+
+/* ---- host-buffer entry points (the end-to-end path: host mesh in, host results out) --------------------
+ * i2_host_prepare uploads the mesh (already scaled), computes geometry, classifies and builds the three
+ * ordered task lists exactly like Evaluator3D::runAllPairs (src/evaluators/evaluator3d.cu:120-169);
+ * h_task_counts[c] = 2 * pairs of class c.  i2_host_run integrates all three classes and copies tasks,
+ * results (and deltas when h_errors[c] != NULL) back; copies of finished chunks overlap the computation
+ * of the next ones when the host buffers are pinned.  Any h_tasks[c]/h_results[c] may be NULL (skipped).   */
+int i2_host_prepare(i2_context *ctx, const double *h_vertices, int nv, const int *h_cells, int nc,
+                    long long h_task_counts[3]);
+int i2_host_run(i2_context *ctx, int level, int *const h_tasks[3], double *const h_results[3],
+                double *const h_errors[3], unsigned char *const h_refinements[3], i2_stats h_stats[3]);
+/* device views of what i2_host_prepare built (valid until the next prepare/destroy)                        */
+int i2_host_device_views(i2_context *ctx, const int *d_tasks[3], const double *d_results[3]);
+
+/* ---- instrumentation for bench.py -------------------------------------------------------------------------
+ * launch counter: kernels launched by this library since process start (all contexts).
+ * profiling: when enabled, i2_integrate_class brackets its integrate kernel(s) and its finalize kernel with CUDA
+ * events on the context's stream; i2_profile_last returns the device times of the last fixed-level call.      */
+int i2_launch_count(long long *h_count);
+int i2_set_profiling(i2_context *ctx, int enabled);
+int i2_profile_last(i2_context *ctx, float *ms_integrate, float *ms_finalize);
+
+/* ---- measured roofline denominators: FP64-pipe DFMA rate and XU-pipe MUFU rate of this device ---------- */
+int i2_peak_rates(i2_context *ctx, double *dfma_tflops, double *mufu_gops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* I2_ABI_H */

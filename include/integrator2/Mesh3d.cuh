@@ -1,0 +1,52 @@
+// Mesh3D — drop-in for the reference class of the same name (/root/reference/src/Mesh3d.cuh:37-177):
+// .dat loader, per-cell normals/centres/areas, neighbour-classified pair lists.  All device work goes through
+// the C ABI (include/i2_abi.h: i2_mesh_geometry, i2_classify_count, i2_classify_fill).
+// Difference a user can observe: the three pair lists come out sorted by (i, j) and are sized exactly
+// (the reference's order is atomicAdd order and its capacities are heuristic, src/Mesh3d.cu:243-262).
+#ifndef MESH3D_CUH
+#define MESH3D_CUH
+
+#include "common/cuda_math.cuh"
+#include "common/device_vector.cuh"
+
+#include <array>
+#include <string>
+#include <vector>
+
+enum class neighbour_type_enum {
+    simple_neighbors = 0,    // exactly one shared vertex
+    attached_neighbors = 1,  // a shared edge
+    not_neighbors = 2,       // nothing shared
+    undefined = -1
+};
+
+class Mesh3D {
+public:
+    virtual ~Mesh3D() = default;
+
+    bool loadMeshFromFile(const std::string &filename, double scale = 1.0);
+    void prepareMesh();
+
+    const auto &getSimpleNeighbors() const { return pairLists[0]; }
+    const auto &getAttachedNeighbors() const { return pairLists[1]; }
+    const auto &getNotNeighbors() const { return pairLists[2]; }
+    const auto &getVertices() const { return vertices; }
+    const auto &getCells() const { return cells; }
+    const auto &getCellNormals() const { return cellNormals; }
+    const auto &getCellMeasures() const { return cellMeasures; }
+
+private:
+    deviceVector<Point3> vertices;
+    deviceVector<int3> cells;
+    deviceVector<Point3> cellNormals;
+    deviceVector<Point3> cellCenters;
+    deviceVector<double> cellMeasures;
+    deviceVector<int3> pairLists[3];  // indexed by neighbour_type_enum
+};
+
+void exportMeshToObj(const std::string &filename, const std::vector<Point3> &vertices, const std::vector<int3> &cells);
+void exportMeshToVtk(const std::string &filename, const std::vector<Point3> &vertices, const std::vector<int3> &cells,
+                     const std::array<std::vector<unsigned char>, 3> &refinementsRequired);
+std::string neighborTypeString(neighbour_type_enum neighborType);
+
+#endif  // MESH3D_CUH

@@ -1,0 +1,262 @@
+"""ctypes binding of libintegrator2_b200.so (the C ABI in include/i2_abi.h).
+
+This is plumbing for tests/ and bench.py: device memory comes from torch tensors (data_ptr()), streams from
+torch.cuda.  The product is the shared library; there is no Python or CPU implementation of the path, and
+every call fails loudly if the library is missing or no CUDA device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libintegrator2_b200.so")
+
+SIMPLE, ATTACHED, NOT = 0, 1, 2
+LEVEL_ADAPTIVE = -1
+MATH_STRICT, MATH_FAST = 0, 1
+CLASS_NAMES = ("simple", "attached", "not")
+
+# Cowper rules as shipped by the reference (/root/reference/src/QuadratureFormula3d.cuh:181-213): 13 points, order 7
+QF13_XY = np.array([
+    [0.333333333333333, 0.333333333333333], [0.479308067841923, 0.260345966079038],
+    [0.260345966079038, 0.479308067841923], [0.260345966079038, 0.260345966079038],
+    [0.869739794195598, 0.065130102902216], [0.065130102902216, 0.869739794195598],
+    [0.065130102902216, 0.065130102902216], [0.638444188569809, 0.312865496004875],
+    [0.312865496004875, 0.638444188569809], [0.638444188569809, 0.048690315425316],
+    [0.048690315425316, 0.638444188569809], [0.312865496004875, 0.048690315425316],
+    [0.048690315425316, 0.312865496004875]], dtype=np.float64)
+QF13_W = np.array([-0.149570044467670, 0.175615257433204, 0.175615257433204, 0.175615257433204,
+                   0.053347235608839, 0.053347235608839, 0.053347235608839, 0.077113760890257,
+                   0.077113760890257, 0.077113760890257, 0.077113760890257, 0.077113760890257,
+                   0.077113760890257], dtype=np.float64)
+QF13_ORDER = 7
+
+
+class Stats(C.Structure):
+    _fields_ = [("last_round", C.c_int), ("integrated", C.c_longlong * 6), ("unconverged", C.c_longlong * 6),
+                ("orientation_warnings", C.c_int)]
+
+    def as_dict(self):
+        return dict(last_round=int(self.last_round), integrated=[int(x) for x in self.integrated],
+                    unconverged=[int(x) for x in self.unconverged], orientation_warnings=int(self.orientation_warnings))
+
+
+EXPORTS = [
+    "i2_create", "i2_destroy", "i2_set_stream", "i2_synchronize", "i2_set_math_mode", "i2_error_string",
+    "i2_set_quadrature", "i2_mesh_geometry", "i2_set_mesh", "i2_classify_count", "i2_classify_fill",
+    "i2_add_reversed_pairs", "i2_integrate_class", "i2_symmetry_error", "i2_host_prepare", "i2_host_run",
+    "i2_host_device_views", "i2_peak_rates", "i2_refine_mesh_once", "i2_launch_count", "i2_set_profiling", "i2_profile_last",
+]
+
+_lib = None
+
+
+class I2Error(RuntimeError):
+    pass
+
+
+def load_library():
+    """Load the CUDA extension; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise I2Error(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "(make -C integrator2_b200/csrc). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, ll, i32 = C.c_void_p, C.c_longlong, C.c_int
+    L.i2_create.argtypes = [C.POINTER(vp), i32]
+    L.i2_destroy.argtypes = [vp]
+    L.i2_set_stream.argtypes = [vp, vp]
+    L.i2_synchronize.argtypes = [vp]
+    L.i2_set_math_mode.argtypes = [vp, i32]
+    L.i2_error_string.argtypes = [i32]
+    L.i2_error_string.restype = C.c_char_p
+    L.i2_set_quadrature.argtypes = [vp, vp, vp, i32, i32]
+    L.i2_mesh_geometry.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp]
+    L.i2_set_mesh.argtypes = [vp, vp, i32, vp, i32, vp, vp]
+    L.i2_classify_count.argtypes = [vp, vp, i32, C.POINTER(ll)]
+    L.i2_classify_fill.argtypes = [vp, vp, i32, vp, vp, vp]
+    L.i2_add_reversed_pairs.argtypes = [vp, vp, ll]
+    L.i2_integrate_class.argtypes = [vp, i32, vp, ll, i32, vp, vp, vp, vp, C.POINTER(Stats)]
+    L.i2_symmetry_error.argtypes = [vp, vp, ll, vp]
+    L.i2_host_prepare.argtypes = [vp, vp, i32, vp, i32, C.POINTER(ll)]
+    L.i2_host_run.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(Stats)]
+    L.i2_host_device_views.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.i2_refine_mesh_once.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, vp]
+    L.i2_launch_count.argtypes = [C.POINTER(ll)]
+    L.i2_set_profiling.argtypes = [vp, i32]
+    L.i2_profile_last.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.i2_peak_rates.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    for name in EXPORTS:
+        if name != "i2_error_string":
+            getattr(L, name).restype = i32
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise I2Error(f"i2 call failed ({rc}): {load_library().i2_error_string(rc).decode()}")
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def launch_count() -> int:
+    n = C.c_longlong()
+    _check(load_library().i2_launch_count(C.byref(n)))
+    return int(n.value)
+
+
+class Context:
+    """One integrator context on one CUDA device (mirrors the lifetime of the reference's
+    Mesh3D + NumericalIntegrator3D + EvaluatorJ3DK trio)."""
+
+    def __init__(self, device: int = 0, math_mode: int = MATH_FAST):
+        import torch
+        self.torch = torch
+        self.L = load_library()
+        self.device = device
+        h = C.c_void_p()
+        _check(self.L.i2_create(C.byref(h), device))
+        self.h = h
+        _check(self.L.i2_set_math_mode(self.h, math_mode))
+        self.set_quadrature(QF13_XY, QF13_W, QF13_ORDER)
+        self._keep = []
+        self.nc = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.i2_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def set_math_mode(self, mode):
+        _check(self.L.i2_set_math_mode(self.h, mode))
+
+    def set_quadrature(self, xy, w, order):
+        xy = np.ascontiguousarray(xy, dtype=np.float64)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        _check(self.L.i2_set_quadrature(self.h, xy.ctypes.data, w.ctypes.data, int(w.size), int(order)))
+
+    def synchronize(self):
+        _check(self.L.i2_synchronize(self.h))
+
+    # ---- device-pointer API ------------------------------------------------------------------------
+    def set_mesh(self, vertices, cells):
+        """vertices float64[nv,3] (scaled), cells int32[nc,3]; returns (normals, measures) device tensors."""
+        torch = self.torch
+        dev = f"cuda:{self.device}"
+        v = torch.as_tensor(np.ascontiguousarray(vertices, dtype=np.float64)).to(dev)
+        c = torch.as_tensor(np.ascontiguousarray(cells, dtype=np.int32)).to(dev)
+        nv, nc = v.shape[0], c.shape[0]
+        normals = torch.empty((nc, 3), dtype=torch.float64, device=dev)
+        centers = torch.empty((nc, 3), dtype=torch.float64, device=dev)
+        measures = torch.empty((nc,), dtype=torch.float64, device=dev)
+        _check(self.L.i2_mesh_geometry(self.h, _ptr(v), nv, _ptr(c), nc, _ptr(normals), _ptr(centers), _ptr(measures)))
+        _check(self.L.i2_set_mesh(self.h, _ptr(v), nv, _ptr(c), nc, _ptr(normals), _ptr(measures)))
+        self._keep = [v, c, normals, measures, centers]
+        self.d_vertices, self.d_cells, self.d_normals, self.d_measures, self.d_centers = v, c, normals, measures, centers
+        self.nc = nc
+        return normals, measures
+
+    def classify(self):
+        """-> list of 3 int32[n,3] device tensors (i<j pairs, lexicographic, k = slot)."""
+        torch = self.torch
+        cnt = (C.c_longlong * 3)()
+        _check(self.L.i2_classify_count(self.h, _ptr(self.d_cells), self.nc, cnt))
+        dev = f"cuda:{self.device}"
+        lists = [torch.empty((int(cnt[k]), 3), dtype=torch.int32, device=dev) for k in range(3)]
+        _check(self.L.i2_classify_fill(self.h, _ptr(self.d_cells), self.nc, _ptr(lists[0]), _ptr(lists[1]), _ptr(lists[2])))
+        return lists
+
+    def tasks_from_pairs(self, pairs):
+        """pairs int32[n,3] device tensor -> ordered tasks int32[2n,3] (pairs + reversed pairs at n+idx)."""
+        torch = self.torch
+        n = pairs.shape[0]
+        t = torch.empty((2 * n, 3), dtype=torch.int32, device=pairs.device)
+        t[:n] = pairs
+        _check(self.L.i2_add_reversed_pairs(self.h, _ptr(t), n))
+        return t
+
+    def integrate_class(self, cls, tasks, level=0, want_stats=True, refinements=None, out=None):
+        """tasks: int32[n,3] device tensor. -> dict(integrals[n,4], results[n,3], refinements, converged, stats)"""
+        torch = self.torch
+        n = tasks.shape[0]
+        dev = tasks.device
+        if out is None:
+            integrals = torch.empty((n, 4), dtype=torch.float64, device=dev)
+            results = torch.empty((n, 3), dtype=torch.float64, device=dev)
+        else:
+            integrals, results = out
+        conv = None
+        if level < 0:
+            if refinements is None:
+                refinements = torch.zeros((self.nc,), dtype=torch.uint8, device=dev)
+            conv = torch.zeros((n,), dtype=torch.uint8, device=dev)
+        st = Stats()
+        _check(self.L.i2_integrate_class(self.h, cls, _ptr(tasks), n, level, _ptr(integrals), _ptr(results),
+                                         _ptr(refinements) if level < 0 else C.c_void_p(0), _ptr(conv),
+                                         C.byref(st) if want_stats else None))
+        return dict(integrals=integrals, results=results, refinements=refinements, converged=conv,
+                    stats=st.as_dict() if want_stats else None)
+
+    def symmetry_error(self, results):
+        torch = self.torch
+        n = results.shape[0]
+        err = torch.empty((n,), dtype=torch.float64, device=results.device)
+        _check(self.L.i2_symmetry_error(self.h, _ptr(results), n // 2, _ptr(err)))
+        return err
+
+    def set_profiling(self, on=True):
+        _check(self.L.i2_set_profiling(self.h, 1 if on else 0))
+
+    def profile_last(self):
+        a, b = C.c_float(), C.c_float()
+        _check(self.L.i2_profile_last(self.h, C.byref(a), C.byref(b)))
+        return float(a.value), float(b.value)
+
+    def set_stream(self, cuda_stream_ptr):
+        _check(self.L.i2_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def peak_rates(self):
+        a, b = C.c_double(), C.c_double()
+        _check(self.L.i2_peak_rates(self.h, C.byref(a), C.byref(b)))
+        return float(a.value), float(b.value)
+
+    # ---- host-buffer API (end-to-end) ------------------------------------------------------------------
+    def host_prepare(self, vertices, cells):
+        v = np.ascontiguousarray(vertices, dtype=np.float64)
+        c = np.ascontiguousarray(cells, dtype=np.int32)
+        cnt = (C.c_longlong * 3)()
+        _check(self.L.i2_host_prepare(self.h, v.ctypes.data, v.shape[0], c.ctypes.data, c.shape[0], cnt))
+        self.nc = c.shape[0]
+        return [int(x) for x in cnt]
+
+    def host_run(self, level, h_tasks, h_results, h_errors=None, h_refinements=None):
+        """h_* : lists of 3 pinned CPU torch tensors (or None entries). Returns list of 3 stats dicts."""
+        def arr(lst):
+            a = (C.c_void_p * 3)()
+            for k in range(3):
+                t = lst[k] if lst is not None else None
+                a[k] = t.data_ptr() if t is not None and t.numel() else None
+            return a
+        st = (Stats * 3)()
+        _check(self.L.i2_host_run(self.h, level, arr(h_tasks), arr(h_results), arr(h_errors), arr(h_refinements), st))
+        return [s.as_dict() for s in st]
+
+    def host_device_views(self):
+        t = (C.c_void_p * 3)()
+        r = (C.c_void_p * 3)()
+        _check(self.L.i2_host_device_views(self.h, t, r))
+        return list(t), list(r)

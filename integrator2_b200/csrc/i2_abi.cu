@@ -1,0 +1,494 @@
+// C-ABI entry points of libintegrator2_b200.so (declared in include/i2_abi.h).
+// Host-side orchestration only: every numerical step is a kernel in i2_kernels.cu; there is no CPU fallback.
+#include "../../include/i2_abi.h"
+#include "i2_kernels.cuh"
+
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+using namespace i2;
+
+#define I2_CUDA(call)                                   \
+    do {                                                \
+        cudaError_t e__ = (call);                       \
+        if (e__ != cudaSuccess) return (int)e__;        \
+    } while (0)
+
+struct i2_context {
+    int device = 0;
+    int numSMs = 148;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copyStream = nullptr;
+    bool ownStream = false;
+    int mathMode = I2_MATH_FAST;
+    bool haveQuad = false;
+
+    // borrowed mesh arrays + owned SoA pack
+    const double *verts = nullptr;
+    const int *cells = nullptr;
+    int nv = 0, nc = 0;
+    double *tri = nullptr;
+    int stride = 0;
+    size_t triCap = 0;
+
+    // adaptive work queue scratch (owned, grown on demand)
+    double *bufB = nullptr;
+    size_t bufBCap = 0;
+    int *rest[2] = {nullptr, nullptr};
+    size_t restCap = 0;
+    unsigned char *cellFlag = nullptr;
+    size_t cellFlagCap = 0;
+    QueueState *qs = nullptr;
+
+    // classification scratch
+    unsigned long long *rowCounts = nullptr;
+    size_t rowCap = 0;
+
+    // host-entry state (i2_host_prepare / i2_host_run)
+    double *hVerts = nullptr, *hNormals = nullptr, *hMeasures = nullptr;
+    int *hCells = nullptr;
+    int *hTasks[3] = {nullptr, nullptr, nullptr};
+    double *hIntegrals[3] = {nullptr, nullptr, nullptr};
+    double *hResults[3] = {nullptr, nullptr, nullptr};
+    double *hErrors[3] = {nullptr, nullptr, nullptr};
+    unsigned char *hRefinements[3] = {nullptr, nullptr, nullptr};
+    long long hCount[3] = {0, 0, 0};
+    cudaEvent_t chunkDone[2] = {nullptr, nullptr};
+    bool profiling = false;
+    cudaEvent_t prof[3] = {nullptr, nullptr, nullptr};
+};
+
+namespace {
+
+template <class T>
+int ensure(T **p, size_t *cap, size_t need) {
+    if (need <= *cap && *p) return 0;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    if (need == 0) return 0;
+    I2_CUDA(cudaMalloc((void **)p, need * sizeof(T)));
+    *cap = need;
+    return 0;
+}
+
+void freeHostState(i2_context *c) {
+    auto fr = [](auto *&p) { if (p) cudaFree(p); p = nullptr; };
+    fr(c->hVerts); fr(c->hNormals); fr(c->hMeasures); fr(c->hCells);
+    for (int k = 0; k < 3; ++k) { fr(c->hTasks[k]); fr(c->hIntegrals[k]); fr(c->hResults[k]); fr(c->hErrors[k]); fr(c->hRefinements[k]); c->hCount[k] = 0; }
+}
+
+PackedMesh packed(const i2_context *c) {
+    PackedMesh pm;
+    pm.tri = c->tri;
+    pm.cells = c->cells;
+    pm.nc = c->nc;
+    pm.stride = c->stride;
+    return pm;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *i2_error_string(int code) {
+    switch (code) {
+    case 0: return "success";
+    case I2_E_BADARG: return "i2: bad argument";
+    case I2_E_NOMESH: return "i2: no mesh set (i2_set_mesh)";
+    case I2_E_NOQUAD: return "i2: no quadrature rule set (i2_set_quadrature)";
+    case I2_E_LEVEL: return "i2: refinement level out of range";
+    case I2_E_TOOBIG: return "i2: count exceeds 32-bit task slots";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "i2: unknown error";
+    }
+}
+
+int i2_create(i2_context **out, int device) {
+    if (!out) return I2_E_BADARG;
+    *out = nullptr;
+    I2_CUDA(cudaSetDevice(device));
+    i2_context *c = new i2_context;
+    c->device = device;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { delete c; return (int)e; }
+    c->numSMs = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return (int)e; }
+    c->ownStream = true;
+    e = cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; return (int)e; }
+    for (int k = 0; k < 2; ++k) cudaEventCreateWithFlags(&c->chunkDone[k], cudaEventDisableTiming);
+    e = cudaMalloc((void **)&c->qs, sizeof(QueueState));
+    if (e != cudaSuccess) { delete c; return (int)e; }
+    *out = c;
+    return 0;
+}
+
+int i2_destroy(i2_context *c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    freeHostState(c);
+    if (c->tri) cudaFree(c->tri);
+    if (c->bufB) cudaFree(c->bufB);
+    for (int k = 0; k < 2; ++k) { if (c->rest[k]) cudaFree(c->rest[k]); if (c->chunkDone[k]) cudaEventDestroy(c->chunkDone[k]); }
+    if (c->cellFlag) cudaFree(c->cellFlag);
+    if (c->qs) cudaFree(c->qs);
+    for (int k = 0; k < 3; ++k) if (c->prof[k]) cudaEventDestroy(c->prof[k]);
+    if (c->rowCounts) cudaFree(c->rowCounts);
+    if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
+    if (c->copyStream) cudaStreamDestroy(c->copyStream);
+    delete c;
+    return 0;
+}
+
+int i2_set_stream(i2_context *c, void *s) {
+    if (!c) return I2_E_BADARG;
+    if (c->ownStream && c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    c->stream = (cudaStream_t)s;
+    c->ownStream = false;
+    return 0;
+}
+
+int i2_synchronize(i2_context *c) {
+    if (!c) return I2_E_BADARG;
+    I2_CUDA(cudaStreamSynchronize(c->stream));
+    I2_CUDA(cudaStreamSynchronize(c->copyStream));
+    return 0;
+}
+
+int i2_set_math_mode(i2_context *c, int mode) {
+    if (!c || (mode != I2_MATH_STRICT && mode != I2_MATH_FAST)) return I2_E_BADARG;
+    c->mathMode = mode;
+    return 0;
+}
+
+int i2_set_quadrature(i2_context *c, const double *xy, const double *w, int n, int order) {
+    if (!c || !xy || !w || n < 1 || n > MAX_GAUSS_POINTS || order < 0 || order > 30) return I2_E_BADARG;
+    I2_CUDA(cudaSetDevice(c->device));
+    double packed4[MAX_GAUSS_POINTS * 4];
+    for (int g = 0; g < n; ++g) {
+        packed4[4 * g] = xy[2 * g];
+        packed4[4 * g + 1] = xy[2 * g + 1];
+        packed4[4 * g + 2] = 1.0 - xy[2 * g] - xy[2 * g + 1];  // as NumericalIntegrator3D's ctor (src/NumericalIntegrator3d.cu:202-206)
+        packed4[4 * g + 3] = w[g];
+    }
+    I2_CUDA(upload_quadrature(packed4, n, (double)(1 << order), c->stream));
+    I2_CUDA(cudaStreamSynchronize(c->stream));  // packed4 lives on this stack frame
+    c->haveQuad = true;
+    return 0;
+}
+
+int i2_mesh_geometry(i2_context *c, const double *verts, int nv, const int *cells, int nc, double *normals, double *centers, double *measures) {
+    if (!c || nv < 0 || nc < 0 || (nc > 0 && (!verts || !cells))) return I2_E_BADARG;
+    I2_CUDA(cudaSetDevice(c->device));
+    launch_geometry(verts, cells, nc, normals, centers, measures, c->stream);
+    I2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int i2_set_mesh(i2_context *c, const double *verts, int nv, const int *cells, int nc, const double *normals, const double *measures) {
+    if (!c || nv < 0 || nc < 0 || (nc > 0 && (!verts || !cells || !normals || !measures))) return I2_E_BADARG;
+    I2_CUDA(cudaSetDevice(c->device));
+    c->verts = verts; c->cells = cells; c->nv = nv; c->nc = nc;
+    c->stride = (nc + 31) & ~31;  // keep every component row 256-byte aligned
+    int rc = ensure(&c->tri, &c->triCap, (size_t)PK_COUNT * (size_t)c->stride);
+    if (rc) return rc;
+    launch_pack(verts, cells, normals, measures, nc, c->stride, c->tri, c->stream);
+    I2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int i2_refine_mesh_once(i2_context *c, const double *vin, int nvIn, const int *cin, int ncIn, const double *min, double *vout, int *cout,
+                        double *mout) {
+    if (!c || nvIn < 0 || ncIn < 0 || (ncIn > 0 && (!vin || !cin || !min || !vout || !cout || !mout))) return I2_E_BADARG;
+    I2_CUDA(cudaSetDevice(c->device));
+    if (nvIn > 0) I2_CUDA(cudaMemcpyAsync(vout, vin, sizeof(double) * 3 * nvIn, cudaMemcpyDeviceToDevice, c->stream));
+    launch_split_uniform(vin, nvIn, cin, ncIn, min, vout, cout, mout, c->stream);
+    I2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int i2_classify_count(i2_context *c, const int *cells, int nc, long long counts[3]) {
+    if (!c || !counts || nc < 0 || (nc > 0 && !cells)) return I2_E_BADARG;
+    I2_CUDA(cudaSetDevice(c->device));
+    counts[0] = counts[1] = counts[2] = 0;
+    if (nc == 0) return 0;
+    int rc = ensure(&c->rowCounts, &c->rowCap, (size_t)3 * nc);
+    if (rc) return rc;
+    launch_classify_count(cells, nc, c->rowCounts, c->stream);
+    I2_CUDA(cudaGetLastError());
+    std::vector<unsigned long long> h((size_t)3 * nc);
+    I2_CUDA(cudaMemcpyAsync(h.data(), c->rowCounts, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    I2_CUDA(cudaStreamSynchronize(c->stream));
+    unsigned long long run[3] = {0, 0, 0};
+    for (int i = 0; i < nc; ++i)
+        for (int k = 0; k < 3; ++k) {
+            const unsigned long long v = h[(size_t)3 * i + k];
+            h[(size_t)3 * i + k] = run[k];  // exclusive prefix = first slot of row i
+            run[k] += v;
+        }
+    I2_CUDA(cudaMemcpyAsync(c->rowCounts, h.data(), h.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+    I2_CUDA(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 3; ++k) counts[k] = (long long)run[k];
+    return 0;
+}
+
+int i2_classify_fill(i2_context *c, const int *cells, int nc, int *simple, int *attached, int *notn) {
+    if (!c || nc < 0 || (nc > 0 && (!cells || !c->rowCounts))) return I2_E_BADARG;
+    I2_CUDA(cudaSetDevice(c->device));
+    launch_classify_fill(cells, nc, c->rowCounts, simple, attached, notn, c->stream);
+    I2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int i2_add_reversed_pairs(i2_context *c, int *tasks, long long n) {
+    if (!c || n < 0 || (n > 0 && !tasks)) return I2_E_BADARG;
+    if (2 * n > INT_MAX) return I2_E_TOOBIG;
+    I2_CUDA(cudaSetDevice(c->device));
+    launch_add_reversed(tasks, n, c->stream);
+    I2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int i2_integrate_class(i2_context *c, int cls, const int *tasks, long long n, int level, double *integrals, double *results,
+                       unsigned char *refinements, unsigned char *converged, i2_stats *stats) {
+    if (!c || cls < 0 || cls > 2 || n < 0) return I2_E_BADARG;
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (n == 0) return 0;
+    if (!tasks || !integrals || !results) return I2_E_BADARG;
+    if (!c->tri) return I2_E_NOMESH;
+    if (!c->haveQuad) return I2_E_NOQUAD;
+    if (level > 12) return I2_E_LEVEL;
+    if (n > INT_MAX) return I2_E_TOOBIG;
+    I2_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const PackedMesh pm = packed(c);
+    I2_CUDA(cudaMemsetAsync(c->qs, 0, sizeof(QueueState), s));
+
+    if (level >= 0) {
+        if (c->profiling) I2_CUDA(cudaEventRecord(c->prof[0], s));
+        launch_integrate(cls, c->mathMode, pm, tasks, nullptr, nullptr, n, level, integrals, c->numSMs, s);
+        if (c->profiling) I2_CUDA(cudaEventRecord(c->prof[1], s));
+    } else {
+        int rc = ensure(&c->bufB, &c->bufBCap, (size_t)4 * n);
+        if (rc) return rc;
+        if ((size_t)n > c->restCap) {
+            size_t cap0 = c->restCap, cap1 = c->restCap;
+            rc = ensure(&c->rest[0], &cap0, (size_t)n);
+            if (rc) return rc;
+            rc = ensure(&c->rest[1], &cap1, (size_t)n);
+            if (rc) return rc;
+            c->restCap = (size_t)n;
+        }
+        rc = ensure(&c->cellFlag, &c->cellFlagCap, (size_t)c->nc);
+        if (rc) return rc;
+        I2_CUDA(cudaMemsetAsync(c->cellFlag, 0, c->nc, s));
+
+        // round 0: every task on the original control panel; every control panel present in the list is marked
+        launch_integrate(cls, c->mathMode, pm, tasks, nullptr, nullptr, n, 0, integrals, c->numSMs, s);
+        launch_flag_cells(tasks, n, c->cellFlag, s);
+        launch_bump(c->cellFlag, refinements, c->nc, s);
+        // rounds 1..5 are enqueued unconditionally; a round whose device-side task count is 0 does nothing.
+        for (int m = 1; m <= MAX_REFINE_LEVEL; ++m) {
+            double *cur = (m & 1) ? c->bufB : integrals;
+            const double *prev = (m & 1) ? integrals : c->bufB;
+            const int *listIn = m == 1 ? nullptr : c->rest[(m - 1) & 1];
+            const int *countIn = m == 1 ? nullptr : &c->qs->count[m - 1];
+            launch_integrate(cls, c->mathMode, pm, tasks, listIn, countIn, n, m, cur, c->numSMs, s);
+            launch_compare(cur, prev, tasks, listIn, countIn, n, c->rest[m & 1], &c->qs->count[m], c->cellFlag, converged, c->qs, m,
+                           c->numSMs, s);
+            launch_bump(c->cellFlag, refinements, c->nc, s);
+        }
+    }
+    launch_finalize(cls, pm, c->verts, tasks, n, integrals, c->bufB, c->qs, results, c->qs, s);
+    I2_CUDA(cudaGetLastError());
+    if (c->profiling && level >= 0) I2_CUDA(cudaEventRecord(c->prof[2], s));
+
+    if (stats) {
+        QueueState h;
+        I2_CUDA(cudaMemcpyAsync(&h, c->qs, sizeof(h), cudaMemcpyDeviceToHost, s));
+        I2_CUDA(cudaStreamSynchronize(s));
+        stats->last_round = h.lastRound;
+        stats->orientation_warnings = h.orientationWarnings;
+        stats->integrated[0] = n << (level > 0 ? 2 * level : 0);
+        long long before = n;
+        for (int m = 1; m <= h.lastRound && m <= MAX_REFINE_LEVEL; ++m) {
+            stats->integrated[m] = before << (2 * m);
+            stats->unconverged[m] = h.count[m];
+            before = h.count[m];
+        }
+    }
+    return 0;
+}
+
+int i2_symmetry_error(i2_context *c, const double *results, long long nHalf, double *errors) {
+    if (!c || nHalf < 0 || (nHalf > 0 && (!results || !errors))) return I2_E_BADARG;
+    I2_CUDA(cudaSetDevice(c->device));
+    launch_symmetry_error(results, nHalf, errors, c->stream);
+    I2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host-buffer entry points
+// ---------------------------------------------------------------------------------------------------------
+int i2_host_prepare(i2_context *c, const double *hv, int nv, const int *hc, int nc, long long taskCounts[3]) {
+    if (!c || !hv || !hc || nv <= 0 || nc <= 0 || !taskCounts) return I2_E_BADARG;
+    I2_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    freeHostState(c);
+    I2_CUDA(cudaMalloc((void **)&c->hVerts, sizeof(double) * 3 * nv));
+    I2_CUDA(cudaMalloc((void **)&c->hCells, sizeof(int) * 3 * nc));
+    I2_CUDA(cudaMalloc((void **)&c->hNormals, sizeof(double) * 3 * nc));
+    I2_CUDA(cudaMalloc((void **)&c->hMeasures, sizeof(double) * nc));
+    I2_CUDA(cudaMemcpyAsync(c->hVerts, hv, sizeof(double) * 3 * nv, cudaMemcpyHostToDevice, s));
+    I2_CUDA(cudaMemcpyAsync(c->hCells, hc, sizeof(int) * 3 * nc, cudaMemcpyHostToDevice, s));
+    int rc = i2_mesh_geometry(c, c->hVerts, nv, c->hCells, nc, c->hNormals, nullptr, c->hMeasures);
+    if (rc) return rc;
+    rc = i2_set_mesh(c, c->hVerts, nv, c->hCells, nc, c->hNormals, c->hMeasures);
+    if (rc) return rc;
+    long long pairs[3];
+    rc = i2_classify_count(c, c->hCells, nc, pairs);
+    if (rc) return rc;
+    for (int k = 0; k < 3; ++k) {
+        if (2 * pairs[k] > INT_MAX) return I2_E_TOOBIG;
+        c->hCount[k] = 2 * pairs[k];
+        taskCounts[k] = c->hCount[k];
+        if (c->hCount[k]) {
+            I2_CUDA(cudaMalloc((void **)&c->hTasks[k], sizeof(int) * 3 * c->hCount[k]));
+            I2_CUDA(cudaMalloc((void **)&c->hIntegrals[k], sizeof(double) * 4 * c->hCount[k]));
+            I2_CUDA(cudaMalloc((void **)&c->hResults[k], sizeof(double) * 3 * c->hCount[k]));
+        }
+        I2_CUDA(cudaMalloc((void **)&c->hRefinements[k], nc));
+    }
+    rc = i2_classify_fill(c, c->hCells, nc, c->hTasks[0], c->hTasks[1], c->hTasks[2]);
+    if (rc) return rc;
+    for (int k = 0; k < 3; ++k) {
+        rc = i2_add_reversed_pairs(c, c->hTasks[k], pairs[k]);
+        if (rc) return rc;
+    }
+    I2_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int i2_host_device_views(i2_context *c, const int *tasks[3], const double *results[3]) {
+    if (!c) return I2_E_BADARG;
+    for (int k = 0; k < 3; ++k) {
+        if (tasks) tasks[k] = c->hTasks[k];
+        if (results) results[k] = c->hResults[k];
+    }
+    return 0;
+}
+
+int i2_host_run(i2_context *c, int level, int *const hTasks[3], double *const hResults[3], double *const hErrors[3],
+                unsigned char *const hRefinements[3], i2_stats hStats[3]) {
+    if (!c) return I2_E_BADARG;
+    if (!c->hVerts) return I2_E_NOMESH;
+    I2_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream, cs = c->copyStream;
+    const long long chunkTasks = 1LL << 24;  // 16 Mi tasks: 384 MiB of Point3 per chunk
+    int turn = 0;
+    for (int k = 0; k < 3; ++k) {
+        const long long n = c->hCount[k];
+        if (level < 0) I2_CUDA(cudaMemsetAsync(c->hRefinements[k], 0, c->nc, s));
+        if (n == 0) { if (hStats) std::memset(&hStats[k], 0, sizeof(i2_stats)); continue; }
+        const bool wantErr = hErrors && hErrors[k];
+        if (level >= 0 && !wantErr) {
+            // fixed level: tasks are independent -> integrate chunk by chunk, copy each finished chunk on the copy stream
+            for (long long off = 0; off < n; off += chunkTasks) {
+                const long long m = (n - off < chunkTasks) ? (n - off) : chunkTasks;
+                int rc = i2_integrate_class(c, k, c->hTasks[k] + 3 * off, m, level, c->hIntegrals[k] + 4 * off, c->hResults[k] + 3 * off,
+                                            nullptr, nullptr, nullptr);
+                if (rc) return rc;
+                I2_CUDA(cudaEventRecord(c->chunkDone[turn], s));
+                I2_CUDA(cudaStreamWaitEvent(cs, c->chunkDone[turn], 0));
+                turn ^= 1;
+                if (hResults && hResults[k])
+                    I2_CUDA(cudaMemcpyAsync(hResults[k] + 3 * off, c->hResults[k] + 3 * off, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost, cs));
+                if (hTasks && hTasks[k])
+                    I2_CUDA(cudaMemcpyAsync(hTasks[k] + 3 * off, c->hTasks[k] + 3 * off, sizeof(int) * 3 * m, cudaMemcpyDeviceToHost, cs));
+            }
+            if (hStats) { std::memset(&hStats[k], 0, sizeof(i2_stats)); hStats[k].integrated[0] = n << (2 * level); }
+        } else {
+            int rc = i2_integrate_class(c, k, c->hTasks[k], n, level, c->hIntegrals[k], c->hResults[k],
+                                        level < 0 ? c->hRefinements[k] : nullptr, nullptr, hStats ? &hStats[k] : nullptr);
+            if (rc) return rc;
+            if (wantErr) {
+                if (!c->hErrors[k]) I2_CUDA(cudaMalloc((void **)&c->hErrors[k], sizeof(double) * n));
+                rc = i2_symmetry_error(c, c->hResults[k], n / 2, c->hErrors[k]);
+                if (rc) return rc;
+                I2_CUDA(cudaMemcpyAsync(hErrors[k], c->hErrors[k], sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+            }
+            if (hResults && hResults[k])
+                I2_CUDA(cudaMemcpyAsync(hResults[k], c->hResults[k], sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, s));
+            if (hTasks && hTasks[k])
+                I2_CUDA(cudaMemcpyAsync(hTasks[k], c->hTasks[k], sizeof(int) * 3 * n, cudaMemcpyDeviceToHost, s));
+            if (level < 0 && hRefinements && hRefinements[k])
+                I2_CUDA(cudaMemcpyAsync(hRefinements[k], c->hRefinements[k], c->nc, cudaMemcpyDeviceToHost, s));
+        }
+    }
+    I2_CUDA(cudaStreamSynchronize(s));
+    I2_CUDA(cudaStreamSynchronize(cs));
+    return 0;
+}
+
+int i2_launch_count(long long *count) {
+    if (!count) return I2_E_BADARG;
+    *count = g_launchCount;
+    return 0;
+}
+
+int i2_set_profiling(i2_context *c, int enabled) {
+    if (!c) return I2_E_BADARG;
+    I2_CUDA(cudaSetDevice(c->device));
+    c->profiling = enabled != 0;
+    if (c->profiling && !c->prof[0])
+        for (int k = 0; k < 3; ++k) I2_CUDA(cudaEventCreate(&c->prof[k]));
+    return 0;
+}
+
+int i2_profile_last(i2_context *c, float *msIntegrate, float *msFinalize) {
+    if (!c || !c->prof[0]) return I2_E_BADARG;
+    I2_CUDA(cudaEventSynchronize(c->prof[2]));
+    if (msIntegrate) I2_CUDA(cudaEventElapsedTime(msIntegrate, c->prof[0], c->prof[1]));
+    if (msFinalize) I2_CUDA(cudaEventElapsedTime(msFinalize, c->prof[1], c->prof[2]));
+    return 0;
+}
+
+int i2_peak_rates(i2_context *c, double *dfmaTflops, double *mufuGops) {
+    if (!c) return I2_E_BADARG;
+    I2_CUDA(cudaSetDevice(c->device));
+    double *sink = nullptr;
+    I2_CUDA(cudaMalloc((void **)&sink, sizeof(double)));
+    cudaEvent_t e0, e1;
+    I2_CUDA(cudaEventCreate(&e0));
+    I2_CUDA(cudaEventCreate(&e1));
+    const int blocks = c->numSMs * 8, iters = 20000;
+    float ms = 0.f;
+    for (int rep = 0; rep < 3; ++rep) {  // last repetition is reported (first ones warm up clocks)
+        I2_CUDA(cudaEventRecord(e0, c->stream));
+        launch_peak_dfma(sink, iters, blocks, c->stream);
+        I2_CUDA(cudaEventRecord(e1, c->stream));
+        I2_CUDA(cudaEventSynchronize(e1));
+        I2_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    }
+    if (dfmaTflops) *dfmaTflops = (double)blocks * 256.0 * iters * 8.0 * 2.0 / (ms * 1e-3) / 1e12;
+    for (int rep = 0; rep < 3; ++rep) {
+        I2_CUDA(cudaEventRecord(e0, c->stream));
+        launch_peak_mufu(sink, iters / 4, blocks, c->stream);
+        I2_CUDA(cudaEventRecord(e1, c->stream));
+        I2_CUDA(cudaEventSynchronize(e1));
+        I2_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    }
+    if (mufuGops) *mufuGops = (double)blocks * 256.0 * (iters / 4) * 4.0 / (ms * 1e-3) / 1e9;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,72 @@
+// Kernel-side declarations shared by i2_kernels.cu (device code) and i2_abi.cu (C-ABI entry points).
+#pragma once
+#include <cuda_runtime.h>
+#include "i2_vec.cuh"
+
+namespace i2 {
+
+// Packed triangle data in HBM: structure of arrays, component-major with a padded stride so that
+// consecutive triangles are consecutive in memory (coalesced when consecutive lanes hold consecutive j).
+// See DESIGN.md "Data layout in HBM".
+enum PackComp {
+    PK_A = 0,    // 0..2   vertex A
+    PK_B = 3,    // 3..5   vertex B
+    PK_C = 6,    // 6..8   vertex C
+    PK_TA = 9,   // 9..11  unit tangent (C-B)^
+    PK_TB = 12,  // 12..14 unit tangent (A-C)^
+    PK_TC = 15,  // 15..17 unit tangent (B-A)^
+    PK_NU = 18,  // 18..20 (B-A)x(C-A), not normalised
+    PK_N = 21,   // 21..23 unit normal n_j (as Mesh3D computes it)
+    PK_S = 24,   // 24     area S
+    PK_COUNT = 25
+};
+
+struct PackedMesh {
+    const double *tri;   // [PK_COUNT][stride]
+    const int *cells;    // int3[nc] (vertex ids, needed to locate shared vertices/edges)
+    int nc;
+    int stride;
+};
+
+// device-resident bookkeeping of the adaptive work queue (one per context)
+struct QueueState {
+    int count[MAX_REFINE_LEVEL + 2];   // count[m] = tasks still unconverged after round m (count[0] = all)
+    int lastRound;                     // L = last refinement round that was executed
+    int orientationWarnings;
+};
+
+extern long long g_launchCount;       // kernels launched by the launch_* wrappers (bench.py's gpu_launches)
+constexpr int kThreads = 128;          // CTA size of the integrate kernels
+
+// math mode of the regular-pair point function
+enum MathMode { MATH_STRICT = 0, MATH_FAST = 1 };
+
+void launch_pack(const double *verts, const int *cells, const double *normals, const double *measures, int nc, int stride,
+                 double *tri, cudaStream_t s);
+void launch_geometry(const double *verts, const int *cells, int nc, double *normals, double *centers, double *measures,
+                     cudaStream_t s);
+// regular part of `count` tasks at uniform refinement `level`; list==nullptr -> task slots 0..count-1,
+// otherwise slots list[0..*countDev-1] (device-side count, persistent grid)
+void launch_integrate(int cls, int mathMode, const PackedMesh &pm, const int *tasks, const int *list, const int *countDev,
+                      long long countHost, int level, double *out4, int numSMs, cudaStream_t s);
+void launch_compare(const double *cur4, const double *prev4, const int *tasks, const int *listIn, const int *countIn,
+                    long long countHost, int *listOut, int *countOut, unsigned char *cellFlag, unsigned char *converged,
+                    QueueState *qs, int round, int numSMs, cudaStream_t s);
+void launch_flag_cells(const int *tasks, long long n, unsigned char *cellFlag, cudaStream_t s);
+void launch_bump(unsigned char *cellFlag, unsigned char *refinements, int nc, cudaStream_t s);
+// adds the closed-form singular integral (adjacent classes), assembles J; bufA/bufB selected by QueueState::lastRound
+void launch_finalize(int cls, const PackedMesh &pm, const double *verts, const int *tasks, long long n, double *bufA4,
+                     const double *bufB4, const QueueState *qs, double *results3, QueueState *qsMut, cudaStream_t s);
+void launch_symmetry_error(const double *results3, long long nHalf, double *errors, cudaStream_t s);
+void launch_add_reversed(int *tasks3, long long n, cudaStream_t s);
+void launch_classify_count(const int *cells, int nc, unsigned long long *rowCounts3, cudaStream_t s);
+void launch_classify_fill(const int *cells, int nc, const unsigned long long *rowOffsets3, int *simple3, int *attached3,
+                          int *not3, cudaStream_t s);
+void launch_split_uniform(const double *vin, int nvIn, const int *cin, int ncIn, const double *min, double *vout, int *cout,
+                          double *mout, cudaStream_t s);
+cudaError_t upload_quadrature(const double *Lxyzw, int n, double pow2p, cudaStream_t s);
+// FP64-pipe / MUFU peak micro-benchmarks: returns elapsed ms for `iters` dependent-chain iterations
+void launch_peak_dfma(double *sink, int iters, int blocks, cudaStream_t s);
+void launch_peak_mufu(double *sink, int iters, int blocks, cudaStream_t s);
+
+}  // namespace i2

@@ -1,0 +1,166 @@
+// Evaluator3D host class: task lists, result buffers, the per-class driver and the exports.
+#include "../../include/integrator2/evaluators/evaluator3d.cuh"
+#include "host_context.h"
+
+#include <fstream>
+
+Evaluator3D::Evaluator3D(const Mesh3D &mesh_, NumericalIntegrator3D &numIntegrator_) : mesh(mesh_), numIntegrator(numIntegrator_) {}
+
+namespace {
+struct ClassBuffers {
+    deviceVector<int3> *tasks;
+    deviceVector<double4> *integrals;
+    deviceVector<Point3> *results;
+    deviceVector<double> *errors;
+};
+}  // namespace
+
+#define I2_CLASS_BUFFERS(self)                                                                                             \
+    ClassBuffers cb[3] = {{&(self)->simpleNeighborsTasks, &(self)->d_simpleNeighborsIntegrals, &(self)->d_simpleNeighborsResults, &(self)->simpleNeighborsErrors},     \
+                          {&(self)->attachedNeighborsTasks, &(self)->d_attachedNeighborsIntegrals, &(self)->d_attachedNeighborsResults, &(self)->attachedNeighborsErrors}, \
+                          {&(self)->notNeighborsTasks, &(self)->d_notNeighborsIntegrals, &(self)->d_notNeighborsResults, &(self)->notNeighborsErrors}}
+
+const deviceVector<Point3> *Evaluator3D::getResultsVector(neighbour_type_enum t) const {
+    auto *self = const_cast<Evaluator3D *>(this);
+    I2_CLASS_BUFFERS(self);
+    return ((int)t >= 0 && (int)t < 3) ? cb[(int)t].results : nullptr;
+}
+const deviceVector<double4> *Evaluator3D::getIntegralsVector(neighbour_type_enum t) const {
+    auto *self = const_cast<Evaluator3D *>(this);
+    I2_CLASS_BUFFERS(self);
+    return ((int)t >= 0 && (int)t < 3) ? cb[(int)t].integrals : nullptr;
+}
+const deviceVector<double> *Evaluator3D::getErrorsVector(neighbour_type_enum t) const {
+    auto *self = const_cast<Evaluator3D *>(this);
+    I2_CLASS_BUFFERS(self);
+    return ((int)t >= 0 && (int)t < 3) ? cb[(int)t].errors : nullptr;
+}
+
+void Evaluator3D::allocateClass(int cls, int taskCount) {
+    I2_CLASS_BUFFERS(this);
+    cb[cls].tasks->allocate(taskCount);
+    cb[cls].results->allocate(taskCount);
+    cb[cls].integrals->allocate(taskCount);
+}
+
+// Same sequence as the reference's runAllPairs (src/evaluators/evaluator3d.cu:120-204): ordered tasks = pairs followed by
+// the reversed pairs, preparation, the three timed per-class integrations, optional (i,j)/(j,i) defect.
+void Evaluator3D::runAllPairs(bool checkCorrectness) {
+    i2_context *ctx = i2host::context();
+    I2_CLASS_BUFFERS(this);
+    const deviceVector<int3> *pairs[3] = {&mesh.getSimpleNeighbors(), &mesh.getAttachedNeighbors(), &mesh.getNotNeighbors()};
+    for (int k = 0; k < 3; ++k) {
+        allocateClass(k, 2 * pairs[k]->size);
+        copy_d2d(pairs[k]->data, cb[k].tasks->data, pairs[k]->size);
+        checkI2Errors(i2_add_reversed_pairs(ctx, (int *)cb[k].tasks->data, pairs[k]->size));
+    }
+    numIntegrator.prepareTasksAndMesh(simpleNeighborsTasks, attachedNeighborsTasks, notNeighborsTasks);
+
+    timer.start();
+    integrateOverSimpleNeighbors();
+    timer.stop("Simple neighbors integration");
+    requestFreeDeviceMemoryAmount();
+
+    timer.start();
+    integrateOverAttachedNeighbors();
+    timer.stop("Attached neighbors integration");
+    requestFreeDeviceMemoryAmount();
+
+    timer.start();
+    integrateOverNotNeighbors();
+    timer.stop("Non-neighbors integration");
+    requestFreeDeviceMemoryAmount();
+
+    if (checkCorrectness) {
+        for (int k = 0; k < 3; ++k) {
+            cb[k].errors->allocate(2 * pairs[k]->size);
+            checkI2Errors(i2_symmetry_error(ctx, (const double *)cb[k].results->data, pairs[k]->size, cb[k].errors->data));
+        }
+        checkCudaErrors(cudaDeviceSynchronize());
+    }
+}
+
+// User-supplied task lists (src/evaluators/evaluator3d.cu:213-288): empty classes are skipped, no reversed pairs, no defect.
+void Evaluator3D::runPairs(const std::vector<int3> &userSimple, const std::vector<int3> &userAttached, const std::vector<int3> &userNot) {
+    if (userSimple.empty() && userAttached.empty() && userNot.empty()) return;
+    I2_CLASS_BUFFERS(this);
+    const std::vector<int3> *user[3] = {&userSimple, &userAttached, &userNot};
+    for (int k = 0; k < 3; ++k) {
+        if (user[k]->empty()) continue;
+        allocateClass(k, (int)user[k]->size());
+        copy_h2d(user[k]->data(), cb[k].tasks->data, user[k]->size());
+    }
+    checkCudaErrors(cudaDeviceSynchronize());
+    numIntegrator.prepareTasksAndMesh(simpleNeighborsTasks, attachedNeighborsTasks, notNeighborsTasks);
+
+    if (!userSimple.empty()) {
+        timer.start();
+        integrateOverSimpleNeighbors();
+        timer.stop("Simple neighbors integration");
+        requestFreeDeviceMemoryAmount();
+    }
+    if (!userAttached.empty()) {
+        timer.start();
+        integrateOverAttachedNeighbors();
+        timer.stop("Attached neighbors integration");
+        requestFreeDeviceMemoryAmount();
+    }
+    if (!userNot.empty()) {
+        timer.start();
+        integrateOverNotNeighbors();
+        timer.stop("Non-neighbors integration");
+        requestFreeDeviceMemoryAmount();
+    }
+}
+
+int Evaluator3D::compareIntegrationResults(neighbour_type_enum, bool) { return 0; }
+
+// Export format of the reference (src/evaluators/evaluator3d.cu:354-457): default ostream precision,
+// csv rows "i;j;x;y;z[;err]" with a quoted header, plain text rows "(i, j): [x, y, z][, error = e]".
+bool Evaluator3D::outputResultsToFile(neighbour_type_enum neighborType, output_format_enum outputFormat) const {
+    const int k = (int)neighborType;
+    if (k < 0 || k > 2) return false;
+    auto *self = const_cast<Evaluator3D *>(this);
+    I2_CLASS_BUFFERS(self);
+    const int n = cb[k].tasks->size;
+    std::string filename = neighborTypeString(neighborType) + (outputFormat == output_format_enum::csv ? ".csv" : ".dat");
+    if (!n) return false;
+
+    std::vector<Point3> hostResults(n);
+    std::vector<int3> hostTasks(n);
+    std::vector<double> hostErrors;
+    copy_d2h(cb[k].results->data, hostResults.data(), n);
+    copy_d2h(cb[k].tasks->data, hostTasks.data(), n);
+    const bool withErrors = cb[k].errors->data != nullptr;
+    if (withErrors) {
+        hostErrors.resize(n);
+        copy_d2h(cb[k].errors->data, hostErrors.data(), n);
+    }
+    checkCudaErrors(cudaDeviceSynchronize());
+
+    std::ofstream out(filename.c_str());
+    if (!out.is_open()) {
+        printf("Error while opening the file\n");
+        return false;
+    }
+    if (outputFormat == output_format_enum::csv) {
+        out << "\"TaskI\";\"TaskJ\";\"IntegralX\";\"IntegralY\";\"IntegralZ\"";
+        if (withErrors) out << ";\"Error\"";
+        out << std::endl;
+    }
+    for (int t = 0; t < n; ++t) {
+        const int3 task = hostTasks[t];
+        const Point3 J = hostResults[t];
+        if (outputFormat == output_format_enum::csv) {
+            out << task.x << ";" << task.y << ";" << J.x << ";" << J.y << ";" << J.z;
+            if (withErrors) out << ";" << hostErrors[t];
+        } else {
+            out << "(" << task.x << ", " << task.y << "): [" << J.x << ", " << J.y << ", " << J.z << "]";
+            if (withErrors) out << ", error = " << hostErrors[t];
+        }
+        out << std::endl;
+    }
+    out.close();
+    printf("%d results saved to file %s\n", n, filename.c_str());
+    return true;
+}

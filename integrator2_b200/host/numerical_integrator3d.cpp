@@ -1,0 +1,79 @@
+// NumericalIntegrator3D host class: quadrature upload, error-control mode, per-class bookkeeping buffers.
+#include "../../include/integrator2/NumericalIntegrator3d.cuh"
+#include "host_context.h"
+
+NumericalIntegrator3D::NumericalIntegrator3D(const Mesh3D &mesh_, const QuadratureFormula3D &qf_)
+    : GaussPointsNum((int)qf_.weights.size()), mesh(mesh_), qf(qf_), errorControlType(error_control_type_enum::automatic_error_control) {
+    std::vector<double> xy(2 * GaussPointsNum);
+    for (int g = 0; g < GaussPointsNum; ++g) {
+        xy[2 * g] = qf.coordinates[g].x;
+        xy[2 * g + 1] = qf.coordinates[g].y;
+    }
+    checkI2Errors(i2_set_quadrature(i2host::context(), xy.data(), qf.weights.data(), GaussPointsNum, qf.order));
+}
+
+void NumericalIntegrator3D::setFixedRefinementLevel(int refinementLevel) {
+    errorControlType = error_control_type_enum::fixed_refinement_level;
+    meshRefinementLevel = refinementLevel;
+}
+
+void NumericalIntegrator3D::prepareTasksAndMesh(const deviceVector<int3> &simpleTasks, const deviceVector<int3> &attachedTasks,
+                                                const deviceVector<int3> &notTasks) {
+    i2_context *ctx = i2host::context();
+    const int nv = mesh.getVertices().size, nc = mesh.getCells().size;
+    checkI2Errors(i2_set_mesh(ctx, (const double *)mesh.getVertices().data, nv, (const int *)mesh.getCells().data, nc,
+                              (const double *)mesh.getCellNormals().data, mesh.getCellMeasures().data));
+    const deviceVector<int3> *lists[3] = {&simpleTasks, &attachedTasks, &notTasks};
+
+    if (errorControlType == error_control_type_enum::automatic_error_control) {
+        for (int k = 0; k < 3; ++k) {
+            if (lists[k]->size) {
+                integralsConverged[k].allocate(lists[k]->size);
+                zero_value_device(integralsConverged[k].data, lists[k]->size);
+            }
+            refinementsRequired[k].allocate(nc);
+            zero_value_device(refinementsRequired[k].data, nc);
+        }
+        return;
+    }
+    if (meshRefinementLevel <= 0) return;
+
+    // fixed level N > 0: the CLI may export the refined mesh, so materialise it (level by level, deterministic slots)
+    const long long cellsFinal = (long long)nc << (2 * meshRefinementLevel);
+    const long long vertsFinal = (long long)nv + (long long)nc * ((1LL << (2 * meshRefinementLevel)) - 1);
+    if (cellsFinal <= 0x7fffffff / 3 && vertsFinal <= 0x7fffffff / 3) {
+        deviceVector<Point3> vA, vB;
+        deviceVector<int3> cA, cB;
+        deviceVector<double> mA, mB;
+        vA.allocate((int)vertsFinal); vB.allocate((int)vertsFinal);
+        cA.allocate((int)cellsFinal); cB.allocate((int)cellsFinal);
+        mA.allocate((int)cellsFinal); mB.allocate((int)cellsFinal);
+        copy_d2d(mesh.getVertices().data, vA.data, nv);
+        copy_d2d(mesh.getCells().data, cA.data, nc);
+        copy_d2d(mesh.getCellMeasures().data, mA.data, nc);
+        int curV = nv, curC = nc;
+        for (int l = 0; l < meshRefinementLevel; ++l) {
+            checkI2Errors(i2_refine_mesh_once(ctx, (const double *)vA.data, curV, (const int *)cA.data, curC, mA.data, (double *)vB.data,
+                                              (int *)cB.data, mB.data));
+            curV += 3 * curC;
+            curC *= 4;
+            vA.swap(vB); cA.swap(cB); mA.swap(mB);
+        }
+        vA.size = curV; cA.size = curC; mA.size = curC;
+        refinedVertices.swap(vA);
+        refinedCells.swap(cA);
+        refinedCellMeasures.swap(mA);
+        checkCudaErrors(cudaDeviceSynchronize());
+    }
+    const long long mult = 1LL << (2 * meshRefinementLevel);
+    printf("Refined mesh contains %d vertices and %d cells. Number of tasks: simple neighbors - %d, attached neighbors - %d, non-neighbors - %d\n",
+           (int)vertsFinal, (int)cellsFinal, (int)(simpleTasks.size * mult), (int)(attachedTasks.size * mult), (int)(notTasks.size * mult));
+}
+
+// The four entry points below are steps of the reference's host-driven refinement loop
+// (src/NumericalIntegrator3d.cu:369-499).  Here that loop runs on the device inside i2_integrate_class, so they
+// have nothing left to do; they remain so that code written against the reference links.
+void NumericalIntegrator3D::gatherResults(deviceVector<double4> &, neighbour_type_enum) const {}
+void NumericalIntegrator3D::refineMesh(neighbour_type_enum) {}
+void NumericalIntegrator3D::resetMesh() {}
+int NumericalIntegrator3D::determineCellsToBeRefined(const deviceVector<int> &, const deviceVector<int3> *, neighbour_type_enum) { return 0; }

@@ -11,6 +11,7 @@
 //
 // usage: ref_dump -f mesh.dat [-s scale] [-r N] -o out_prefix [--pairs file.bin]
 //   writes  <out_prefix>.{simple,attached,not}.bin  and <out_prefix>.meta.txt
+//   --not-stride K: keep only every K-th record of the (huge) not-neighbours class in the dump
 //   --pairs: instead of runAllPairs, run runPairs on 3 user lists read from a binary file
 //            (int32 n_simple, n_attached, n_not, then the int3 triples).
 //
@@ -32,7 +33,7 @@ class DumpEvaluator : public EvaluatorJ3DK
 public:
     DumpEvaluator(const Mesh3D &mesh_, NumericalIntegrator3D &ni_) : EvaluatorJ3DK(mesh_, ni_) {}
 
-    bool dumpClass(neighbour_type_enum type, const std::string &filename) const {
+    bool dumpClass(neighbour_type_enum type, const std::string &filename, int stride = 1) const {
         const deviceVector<int3> *tasks = getTasks(type);
         const deviceVector<Point3> *results = nullptr;
         const deviceVector<double4> *integrals = nullptr;
@@ -42,7 +43,7 @@ public:
         case neighbour_type_enum::not_neighbors:      results = &d_notNeighborsResults;      integrals = &d_notNeighborsIntegrals;      break;
         default: return false;
         }
-        const int n = tasks->size;
+        int n = tasks->size;
         std::vector<int3> hTasks(n);
         std::vector<Point3> hResults(n);
         std::vector<double4> hIntegrals(n);
@@ -50,6 +51,13 @@ public:
             checkCudaErrors(cudaMemcpy(hTasks.data(), tasks->data, n * sizeof(int3), cudaMemcpyDeviceToHost));
             checkCudaErrors(cudaMemcpy(hResults.data(), results->data, n * sizeof(Point3), cudaMemcpyDeviceToHost));
             checkCudaErrors(cudaMemcpy(hIntegrals.data(), integrals->data, n * sizeof(double4), cudaMemcpyDeviceToHost));
+        }
+        if (stride > 1) {  // keep records 0, stride, 2*stride, ...
+            int m = 0;
+            for (int t = 0; t < n; t += stride, ++m) { hTasks[m] = hTasks[t]; hResults[m] = hResults[t]; hIntegrals[m] = hIntegrals[t]; }
+            const int full = n;
+            n = m;
+            (void)full;
         }
         FILE *f = fopen(filename.c_str(), "wb");
         if (!f) return false;
@@ -66,12 +74,13 @@ int main(int argc, char **argv)
 {
     std::string meshfile, out = "ref", pairsfile;
     double scale = 1.0;
-    int refine = -1;
+    int refine = -1, notStride = 1;
     for (int a = 1; a < argc; ++a) {
         if (!strcmp(argv[a], "-f") && a + 1 < argc) meshfile = argv[++a];
         else if (!strcmp(argv[a], "-s") && a + 1 < argc) scale = atof(argv[++a]);
         else if (!strcmp(argv[a], "-r") && a + 1 < argc) refine = atoi(argv[++a]);
         else if (!strcmp(argv[a], "-o") && a + 1 < argc) out = argv[++a];
+        else if (!strcmp(argv[a], "--not-stride") && a + 1 < argc) notStride = atoi(argv[++a]);
         else if (!strcmp(argv[a], "--pairs") && a + 1 < argc) pairsfile = argv[++a];
         else { fprintf(stderr, "unknown argument %s\n", argv[a]); return 2; }
     }
@@ -108,7 +117,7 @@ int main(int argc, char **argv)
 
     evaluator.dumpClass(neighbour_type_enum::simple_neighbors, out + ".simple.bin");
     evaluator.dumpClass(neighbour_type_enum::attached_neighbors, out + ".attached.bin");
-    evaluator.dumpClass(neighbour_type_enum::not_neighbors, out + ".not.bin");
+    evaluator.dumpClass(neighbour_type_enum::not_neighbors, out + ".not.bin", notStride);
 
     // mesh as the reference sees it + adaptive refinement counters
     {
