@@ -12,6 +12,7 @@
 // usage: ref_dump -f mesh.dat [-s scale] [-r N] -o out_prefix [--pairs file.bin]
 //   writes  <out_prefix>.{simple,attached,not}.bin  and <out_prefix>.meta.txt
 //   --not-stride K: keep only every K-th record of the (huge) not-neighbours class in the dump
+//   --small-stride K: the same for the two adjacent classes
 //   --pairs: instead of runAllPairs, run runPairs on 3 user lists read from a binary file
 //            (int32 n_simple, n_attached, n_not, then the int3 triples).
 //
@@ -74,13 +75,14 @@ int main(int argc, char **argv)
 {
     std::string meshfile, out = "ref", pairsfile;
     double scale = 1.0;
-    int refine = -1, notStride = 1;
+    int refine = -1, notStride = 1, smallStride = 1;
     for (int a = 1; a < argc; ++a) {
         if (!strcmp(argv[a], "-f") && a + 1 < argc) meshfile = argv[++a];
         else if (!strcmp(argv[a], "-s") && a + 1 < argc) scale = atof(argv[++a]);
         else if (!strcmp(argv[a], "-r") && a + 1 < argc) refine = atoi(argv[++a]);
         else if (!strcmp(argv[a], "-o") && a + 1 < argc) out = argv[++a];
         else if (!strcmp(argv[a], "--not-stride") && a + 1 < argc) notStride = atoi(argv[++a]);
+        else if (!strcmp(argv[a], "--small-stride") && a + 1 < argc) smallStride = atoi(argv[++a]);
         else if (!strcmp(argv[a], "--pairs") && a + 1 < argc) pairsfile = argv[++a];
         else { fprintf(stderr, "unknown argument %s\n", argv[a]); return 2; }
     }
@@ -115,8 +117,8 @@ int main(int argc, char **argv)
     }
     checkCudaErrors(cudaDeviceSynchronize());
 
-    evaluator.dumpClass(neighbour_type_enum::simple_neighbors, out + ".simple.bin");
-    evaluator.dumpClass(neighbour_type_enum::attached_neighbors, out + ".attached.bin");
+    evaluator.dumpClass(neighbour_type_enum::simple_neighbors, out + ".simple.bin", smallStride);
+    evaluator.dumpClass(neighbour_type_enum::attached_neighbors, out + ".attached.bin", smallStride);
     evaluator.dumpClass(neighbour_type_enum::not_neighbors, out + ".not.bin", notStride);
 
     // mesh as the reference sees it + adaptive refinement counters

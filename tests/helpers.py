@@ -1,0 +1,108 @@
+"""Shared helpers of the parity tests: error measures and the conditioning-aware tolerance.
+
+Tolerance statement (DESIGN.md "Parity"): per ordered pair
+    |J_new - J_ref|_1  <=  1e-12 * |J_ref|_1  +  K * noise_ij ,   K = 8
+where noise_ij is a first-order bound of the rounding noise of the REFERENCE's own formula
+(thetaPsi, /root/reference/src/evaluators/evaluatorJ3DK.cu:266-313) for that pair.  The second term is needed
+because the reference evaluates ln[l_a(1+cos)/(l_b(1+cos))] and a triple product of unit vectors: both lose
+log2((l/L)^2) resp. log2(1/(1+cos)) bits for distant / nearly collinear configurations, so two compilations of
+the reference itself (-fmad on/off) already differ by far more than 1e-12 there.  For well-conditioned pairs
+noise_ij << 1e-12 |J| and the test is the plain 1e-12 relative bound of BASELINE.json.
+"""
+import numpy as np
+
+U = 2.0 ** -53
+K_NOISE = 8.0
+REL_TOL = 1e-12
+
+QF13_XY = None
+
+
+def _qf():
+    from integrator2_b200 import abi
+    xy = abi.QF13_XY
+    L = np.stack([xy[:, 0], xy[:, 1], 1.0 - xy[:, 0] - xy[:, 1]], axis=1)
+    return L, abi.QF13_W
+
+
+def rel_err_l1(a, b):
+    """|a-b|_1 / |b|_1 per row."""
+    return np.abs(a - b).sum(1) / np.maximum(np.abs(b).sum(1), 1e-300)
+
+
+def reference_noise_bound(vertices, cells, tasks):
+    """First-order rounding-noise bound (absolute, on |J|_1) of the reference formula for regular pairs."""
+    L, w = _qf()
+    i, j = tasks[:, 0], tasks[:, 1]
+    VI = vertices[cells[i]]          # [n,3,3]
+    VJ = vertices[cells[j]]
+    A, B, C = VJ[:, 0], VJ[:, 1], VJ[:, 2]
+    Si = 0.5 * np.linalg.norm(np.cross(VI[:, 1] - VI[:, 0], VI[:, 2] - VI[:, 0]), axis=1)
+    def unit(v):
+        return v / np.linalg.norm(v, axis=1, keepdims=True)
+    ta, tb, tc = unit(C - B), unit(A - C), unit(B - A)
+    acc = np.zeros(tasks.shape[0])
+    for g in range(L.shape[0]):
+        M = L[g, 0] * VI[:, 0] + L[g, 1] * VI[:, 1] + L[g, 2] * VI[:, 2]
+        oa, ob, oc = unit(M - A), unit(M - B), unit(M - C)
+        def d(p, q):
+            return np.einsum("ij,ij->i", p, q)
+        terms = 0.0
+        for (o1, o2, t) in ((oa, ob, tc), (ob, oc, ta), (oc, oa, tb)):
+            terms = terms + 2.0 / np.maximum(1.0 + d(o1, t), 1e-300) + 2.0 / np.maximum(1.0 + d(o2, t), 1e-300) + 4.0
+        y = d(np.cross(oa, ob), oc)
+        x = 1.0 + d(oa, ob) + d(ob, oc) + d(oc, oa)
+        dtheta = 8.0 * (np.abs(x) + np.abs(y)) / np.maximum(x * x + y * y, 1e-300)
+        acc += np.abs(w[g]) * (terms + dtheta)
+    return U * acc * Si * 0.079577471545947667884
+
+
+def check_regular_parity(vertices, cells, tasks, J_new, J_ref, label=""):
+    """Returns a dict of statistics and asserts the tolerance statement."""
+    err = np.abs(J_new - J_ref).sum(1)
+    ref = np.abs(J_ref).sum(1)
+    noise = reference_noise_bound(vertices, cells, tasks)
+    allowed = REL_TOL * ref + K_NOISE * noise
+    rel = err / np.maximum(ref, 1e-300)
+    stats = dict(n=int(tasks.shape[0]), rel_median=float(np.median(rel)), rel_p99=float(np.quantile(rel, 0.99)),
+                 rel_max=float(rel.max()), frac_within_1e12=float((rel <= REL_TOL).mean()),
+                 worst_ratio_to_allowed=float((err / allowed).max()))
+    bad = np.nonzero(err > allowed)[0]
+    assert bad.size == 0, f"{label}: {bad.size} pairs outside tolerance, worst {stats}; first bad task {tasks[bad[0]]}"
+    return stats
+
+
+def key(tasks):
+    return tasks[:, 0].astype(np.int64) * (1 << 32) + tasks[:, 1].astype(np.int64)
+
+
+def align_by_pair(tasks_a, tasks_b):
+    """index arrays (ia, ib) such that tasks_a[ia] and tasks_b[ib] list the same (i,j) pairs."""
+    ka, kb = key(tasks_a), key(tasks_b)
+    oa, ob = np.argsort(ka), np.argsort(kb)
+    common, ia, ib = np.intersect1d(ka[oa], kb[ob], return_indices=True)
+    return oa[ia], ob[ib]
+
+
+def read_class_dump(path):
+    """binary record written by oracle/ref_dump.cu: n, tasks[n][3], results[n][3], integrals[n][4]."""
+    with open(path, "rb") as f:
+        n = int(np.frombuffer(f.read(4), dtype=np.int32)[0])
+        tasks = np.frombuffer(f.read(12 * n), dtype=np.int32).reshape(n, 3).copy()
+        results = np.frombuffer(f.read(24 * n), dtype=np.float64).reshape(n, 3).copy()
+        integrals = np.frombuffer(f.read(32 * n), dtype=np.float64).reshape(n, 4).copy()
+    return dict(tasks=tasks, results=results, integrals=integrals)
+
+
+def read_mesh_dump(path):
+    with open(path, "rb") as f:
+        nv, nc = np.frombuffer(f.read(8), dtype=np.int32)
+        v = np.frombuffer(f.read(24 * nv), dtype=np.float64).reshape(nv, 3).copy()
+        c = np.frombuffer(f.read(12 * nc), dtype=np.int32).reshape(nc, 3).copy()
+        nrm = np.frombuffer(f.read(24 * nc), dtype=np.float64).reshape(nc, 3).copy()
+        area = np.frombuffer(f.read(8 * nc), dtype=np.float64).copy()
+        adaptive = int(np.frombuffer(f.read(4), dtype=np.int32)[0])
+        ref = None
+        if adaptive:
+            ref = [np.frombuffer(f.read(nc), dtype=np.uint8).copy() for _ in range(3)]
+    return dict(vertices=v, cells=c, normals=nrm, measures=area, adaptive=adaptive, refinements=ref)

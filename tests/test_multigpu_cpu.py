@@ -1,0 +1,57 @@
+"""Host-side logic of the multi-GPU path on CPU: shard bounds and the variable-length gather (gloo, world_size 2)."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+
+from conftest import ROOT
+from integrator2_b200.multigpu import predicted_task_cost, shard_bounds
+
+
+def test_shard_bounds_cover_everything_once():
+    for n in (0, 1, 7, 898, 286403650):
+        for w in (1, 2, 3, 4, 8):
+            b = shard_bounds(n, w)
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[r][1] == b[r + 1][0] for r in range(w - 1))
+            sizes = [hi - lo for lo, hi in b]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_cost_balanced_bounds():
+    rng = np.random.default_rng(0)
+    depth = rng.integers(1, 6, size=10000)
+    cost = np.array([predicted_task_cost(2, 0, d) for d in depth])
+    b = shard_bounds(cost.size, 8, cost)
+    per = np.array([cost[lo:hi].sum() for lo, hi in b])
+    assert per.max() / per.mean() < 1.02
+    assert b[0][0] == 0 and b[-1][1] == cost.size
+
+
+def test_gather_two_ranks_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys
+        sys.path.insert(0, {ROOT!r})
+        import torch, torch.distributed as dist
+        from integrator2_b200.multigpu import shard_bounds, gather_results
+        dist.init_process_group("gloo")
+        rank, world = dist.get_rank(), dist.get_world_size()
+        n = 1001
+        ref = torch.arange(n * 3, dtype=torch.float64).reshape(n, 3) * 0.5      # stand-in for per-pair results
+        b = shard_bounds(n, world)
+        lo, hi = b[rank]
+        local = ref[lo:hi].clone()
+        full = torch.zeros_like(ref) if rank == 0 else None
+        gather_results(local, full, b, rank, world)
+        if rank == 0:
+            assert torch.equal(full, ref)
+            print("GATHER_OK")
+        dist.destroy_process_group()
+    """))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29611")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29611", str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert "GATHER_OK" in out.stdout, out.stdout + out.stderr
