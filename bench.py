@@ -211,8 +211,10 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    ctx = abi.Context(local)
     dev = torch.device(f"cuda:{local}")
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)          # every torch op and every library kernel of this process runs on this stream
+    ctx = abi.Context(local)
 
     # ---- resident inputs: mesh SoA + the three ordered task lists (built on the device) ----------------------
     ctx.set_mesh(mesh.vertices, mesh.cells)
@@ -233,9 +235,6 @@ def main():
     if world > 1 and rank == 0:
         gathered = [torch.empty((n, 3), dtype=torch.float64, device=dev) for n in counts]
     refin = torch.zeros((mesh.n_cells,), dtype=torch.uint8, device=dev) if args.level < 0 else None
-
-    stream = torch.cuda.Stream(device=dev)
-    ctx.set_stream(stream.cuda_stream)
 
     def step():
         for cls in range(3):
@@ -313,8 +312,8 @@ def main():
         torch.cuda.empty_cache()
         c2 = abi.Context(local)
         cnt = c2.host_prepare(mesh.vertices, mesh.cells)
-        ht = [torch.empty((n, 3), dtype=torch.int32).pin_memory() for n in cnt]
-        hr = [torch.empty((n, 3), dtype=torch.float64).pin_memory() for n in cnt]
+        ht = [torch.empty((n, 3), dtype=torch.int32, pin_memory=True) for n in cnt]
+        hr = [torch.empty((n, 3), dtype=torch.float64, pin_memory=True) for n in cnt]
         for _ in range(2):
             c2.host_prepare(mesh.vertices, mesh.cells)
             c2.host_run(args.level, ht, hr)

@@ -40,7 +40,9 @@ typedef struct i2_context i2_context;
 #define I2_LEVEL_ADAPTIVE (-1) /* automatic error control (Runge rule), NumericalIntegrator3D default     */
 
 #define I2_MATH_STRICT 0 /* regular pairs evaluated in the reference's operation order                    */
-#define I2_MATH_FAST 1   /* hoisted / un-normalised formulation (default)                                 */
+#define I2_MATH_FAST 1   /* hoisted / un-normalised formulation, grouped logs/atan2, branch-free primitives (default) */
+#define I2_MATH_FAST_LIBDEVICE 2 /* hoisted algebra, point by point, libdevice sqrt/log/atan2 (diagnostic)  */
+#define I2_MATH_FAST_POINTWISE 3 /* hoisted algebra, point by point, branch-free primitives (diagnostic)    */
 
 /* per-class statistics of one i2_integrate_class call (printed by the drop-in classes exactly like the
  * reference prints them: src/evaluators/evaluatorJ3DK.cu:956,980 and src/evaluators/evaluator3d.cu:338) */

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_PKG, "libintegrator2_b200.so")
 
 SIMPLE, ATTACHED, NOT = 0, 1, 2
 LEVEL_ADAPTIVE = -1
-MATH_STRICT, MATH_FAST = 0, 1
+MATH_STRICT, MATH_FAST, MATH_FAST_LIBDEVICE, MATH_FAST_POINTWISE = 0, 1, 2, 3
 CLASS_NAMES = ("simple", "attached", "not")
 
 # Cowper rules as shipped by the reference (/root/reference/src/QuadratureFormula3d.cuh:181-213): 13 points, order 7
@@ -126,6 +126,11 @@ class Context:
         _check(self.L.i2_create(C.byref(h), device))
         self.h = h
         _check(self.L.i2_set_math_mode(self.h, math_mode))
+        # run on torch's current stream: tensors handed to the library are produced/consumed by torch ops on that
+        # stream, so kernels and torch copies stay ordered (a private stream would race with torch's fills/copies)
+        if torch.cuda.is_available():
+            with torch.cuda.device(device):
+                self.set_stream(torch.cuda.current_stream().cuda_stream)
         self.set_quadrature(QF13_XY, QF13_W, QF13_ORDER)
         self._keep = []
         self.nc = 0

@@ -161,7 +161,7 @@ int i2_synchronize(i2_context *c) {
 }
 
 int i2_set_math_mode(i2_context *c, int mode) {
-    if (!c || (mode != I2_MATH_STRICT && mode != I2_MATH_FAST)) return I2_E_BADARG;
+    if (!c || mode < I2_MATH_STRICT || mode > I2_MATH_FAST_POINTWISE) return I2_E_BADARG;
     c->mathMode = mode;
     return 0;
 }

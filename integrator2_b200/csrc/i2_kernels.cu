@@ -26,12 +26,24 @@ long long g_launchCount = 0;
 // Gauss rule in constant memory: (L_x, L_y, L_z, w) per point, broadcast to all lanes.
 __constant__ double c_gauss[MAX_GAUSS_POINTS * 4];
 __constant__ int c_ngauss;
+__constant__ int c_groupEnd[MAX_GAUSS_POINTS];   // 1 = last point of a run of equal weights (grouped evaluation)
 __constant__ double c_pow2p;
 
 cudaError_t upload_quadrature(const double *Lxyzw, int n, double pow2p, cudaStream_t s) {
     cudaError_t e = cudaMemcpyToSymbolAsync(c_gauss, Lxyzw, sizeof(double) * 4 * n, 0, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbolAsync(c_ngauss, &n, sizeof(int), 0, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return e;
+    // runs of equal weights (at most 6 points per run: the angle-sum argument of the grouped kernel needs <= 6)
+    static int groupEnd[MAX_GAUSS_POINTS];
+    int run = 0;
+    for (int g = 0; g < n; ++g) {
+        ++run;
+        const bool last = (g == n - 1) || (Lxyzw[4 * (g + 1) + 3] != Lxyzw[4 * g + 3]) || run == 6;
+        groupEnd[g] = last ? 1 : 0;
+        if (last) run = 0;
+    }
+    e = cudaMemcpyToSymbolAsync(c_groupEnd, groupEnd, sizeof(int) * n, 0, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) return e;
     return cudaMemcpyToSymbolAsync(c_pow2p, &pow2p, sizeof(double), 0, cudaMemcpyHostToDevice, s);
 }
@@ -163,7 +175,7 @@ k_integrate(PackedMesh pm, const int *__restrict__ tasks, const int *__restrict_
             double Si = __ldg(tri + PK_S * stride + i);
             for (int l = 0; l < level; ++l) Si *= 0.25;  // child area = parent/4 per level (exact)
 
-            if (CLS == 2 && MODE == MATH_FAST) {
+            if (CLS == 2 && MODE != MATH_STRICT) {
                 TriJ T;
                 T.A = ld3(tri + PK_A * stride, stride, j); T.B = ld3(tri + PK_B * stride, stride, j); T.C = ld3(tri + PK_C * stride, stride, j);
                 T.ta = ld3(tri + PK_TA * stride, stride, j); T.tb = ld3(tri + PK_TB * stride, stride, j); T.tc = ld3(tri + PK_TC * stride, stride, j);
@@ -176,7 +188,7 @@ k_integrate(PackedMesh pm, const int *__restrict__ tasks, const int *__restrict_
                     double a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0;
 #pragma unroll 1
                     for (int g = 0; g < ng; ++g) {
-                        const LogTheta v = theta_psi_fast(gauss_point(g, A, B, C), T);
+                        const LogTheta v = theta_psi_fast<MODE == MATH_FAST_POINTWISE>(gauss_point(g, A, B, C), T);
                         const double w = c_gauss[4 * g + 3];
                         a1 = fma(w, v.t1, a1); a2 = fma(w, v.t2, a2); a3 = fma(w, v.t3, a3); a4 = fma(w, v.theta, a4);
                     }
@@ -233,6 +245,111 @@ k_integrate(PackedMesh pm, const int *__restrict__ tasks, const int *__restrict_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// regular (not-neighbour) pairs, the dominant kernel: grouped evaluation (see i2_pair.cuh, point_terms)
+//   * one thread = one task at level 0 (G = min(4^level, 32) lanes per task otherwise);
+//   * the 13 Gauss points of the (child) control panel are staged in shared memory, [point][component][thread],
+//     so the loop keeps only the influence triangle (21 doubles) and the running products in registers;
+//   * per point: lengths, 6 log arguments, (num, den) of the solid angle -> running products;
+//     per group of equal weights: 3 x log_ratio + 1 x atan2_fast;
+//   * control flow is warp-uniform: the only data-dependent decision (angle-sum overflow of a group) is taken by
+//     __all_sync over the warp.
+// ---------------------------------------------------------------------------------------------------------
+template <int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__restrict__ list, const int *__restrict__ countDev,
+                  long long countHost, int level, double *__restrict__ out) {
+    __shared__ double smM[MAX_GAUSS_POINTS * 3 * kThreads];
+    const long long count = countDev ? (long long)*countDev : countHost;
+    const int children = 1 << (2 * level);
+    const int G = children < 32 ? children : 32;
+    const int perLane = children / G;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane & (G - 1);
+    const int groupsPerWarp = 32 / G;
+    const long long warpId = ((long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
+    const long long warpStride = ((long long)gridDim.x * kThreads) >> 5;
+    const int ng = c_ngauss;
+    const int stride = pm.stride;
+    const double *__restrict__ tri = pm.tri;
+    double *myM = smM + threadIdx.x;
+
+    for (long long base = warpId * groupsPerWarp; base < count; base += warpStride * groupsPerWarp) {
+        long long r = base + lane / G;
+        const bool active = r < count;
+        if (!active) r = count - 1;   // tail lanes recompute the last task (no write) so that warp votes stay full-mask
+        const int slot = list ? __ldg(list + r) : (int)r;
+        const int i = __ldg(tasks + 3 * (long long)slot), j = __ldg(tasks + 3 * (long long)slot + 1);
+        double Si = __ldg(tri + PK_S * stride + i);
+        for (int l = 0; l < level; ++l) Si *= 0.25;
+
+        TriJ T;
+        T.A = ld3(tri + PK_A * stride, stride, j); T.B = ld3(tri + PK_B * stride, stride, j); T.C = ld3(tri + PK_C * stride, stride, j);
+        T.ta = ld3(tri + PK_TA * stride, stride, j); T.tb = ld3(tri + PK_TB * stride, stride, j); T.tc = ld3(tri + PK_TC * stride, stride, j);
+        T.Nu = ld3(tri + PK_NU * stride, stride, j);
+
+        double s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;
+        for (int k = 0; k < perLane; ++k) {
+            {
+                d3 A = ld3(tri + PK_A * stride, stride, i), B = ld3(tri + PK_B * stride, stride, i), C = ld3(tri + PK_C * stride, stride, i);
+                descend(A, B, C, level, sub + G * k);
+#pragma unroll 1
+                for (int g = 0; g < ng; ++g) {
+                    const d3 M = gauss_point(g, A, B, C);
+                    myM[(3 * g + 0) * kThreads] = M.x; myM[(3 * g + 1) * kThreads] = M.y; myM[(3 * g + 2) * kThreads] = M.z;
+                }
+            }
+            double a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0;
+            double pn1 = 1.0, pd1 = 1.0, pn2 = 1.0, pd2 = 1.0, pn3 = 1.0, pd3 = 1.0, zr = 1.0, zi = 0.0;
+            bool safe = true;
+            int gStart = 0;
+#pragma unroll 1
+            for (int g = 0; g < ng; ++g) {
+                const d3 M = {myM[(3 * g + 0) * kThreads], myM[(3 * g + 1) * kThreads], myM[(3 * g + 2) * kThreads]};
+                const PointTerms t = point_terms(M, T);
+                pn1 *= t.N1; pd1 *= t.D1; pn2 *= t.N2; pd2 *= t.D2; pn3 *= t.N3; pd3 *= t.D3;
+                const double nr = fma(zr, t.den, -(zi * t.num)), ni = fma(zr, t.num, zi * t.den);
+                zr = nr; zi = ni;
+                safe = safe && (fabs(t.num) <= 0.5 * t.den);
+                if (c_groupEnd[g]) {
+                    const double w = c_gauss[4 * g + 3];
+                    a1 = fma(w, log_ratio(pn1, pd1), a1);
+                    a2 = fma(w, log_ratio(pn2, pd2), a2);
+                    a3 = fma(w, log_ratio(pn3, pd3), a3);
+                    double th;
+                    if (__all_sync(0xffffffffu, safe)) {
+                        th = atan2_fast(zi, zr);
+                    } else {  // some lane of the warp sees triangle j under a large solid angle: add the angles one by one
+                        th = 0.0;
+                        for (int h = gStart; h <= g; ++h) {
+                            const d3 Mh = {myM[(3 * h + 0) * kThreads], myM[(3 * h + 1) * kThreads], myM[(3 * h + 2) * kThreads]};
+                            const PointTerms u = point_terms(Mh, T);
+                            th += atan2_fast(u.num, u.den);
+                        }
+                    }
+                    a4 = fma(w, th + th, a4);
+                    pn1 = pd1 = pn2 = pd2 = pn3 = pd3 = zr = 1.0; zi = 0.0;
+                    safe = true;
+                    gStart = g + 1;
+                }
+            }
+            s1 = fma(Si, a1, s1); s2 = fma(Si, a2, s2); s3 = fma(Si, a3, s3); s4 = fma(Si, a4, s4);
+        }
+        d4 total = vec4(s1 * T.tc + s2 * T.ta + s3 * T.tb, s4);
+        for (int off = G >> 1; off > 0; off >>= 1) {
+            total.x += __shfl_xor_sync(0xffffffffu, total.x, off);
+            total.y += __shfl_xor_sync(0xffffffffu, total.y, off);
+            total.z += __shfl_xor_sync(0xffffffffu, total.z, off);
+            total.w += __shfl_xor_sync(0xffffffffu, total.w, off);
+        }
+        if (active && sub == 0) {
+            double2 *o = reinterpret_cast<double2 *>(out + 4 * (long long)slot);
+            o[0] = make_double2(total.x, total.y);
+            o[1] = make_double2(total.z, total.w);
+        }
+    }
+}
+
 // tuning knob (env I2_MINBLOCKS = 3|4|5): resident CTAs per SM the regular kernel is compiled for
 static int g_minBlocks = [] { const char *e = getenv("I2_MINBLOCKS"); return e ? atoi(e) : 4; }();
 
@@ -252,9 +369,11 @@ void launch_integrate(int cls, int mathMode, const PackedMesh &pm, const int *ta
     if (cls == 0) { ++g_launchCount; k_integrate<0, MATH_STRICT, 3><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4); }
     else if (cls == 1) { ++g_launchCount; k_integrate<1, MATH_STRICT, 3><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4); }
     else if (mathMode == MATH_STRICT) { ++g_launchCount; k_integrate<2, MATH_STRICT, 4><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4); }
-    else if (g_minBlocks == 3) { ++g_launchCount; k_integrate<2, MATH_FAST, 3><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4); }
-    else if (g_minBlocks == 5) { ++g_launchCount; k_integrate<2, MATH_FAST, 5><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4); }
-    else { ++g_launchCount; k_integrate<2, MATH_FAST, 4><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4); }
+    else if (mathMode == MATH_FAST_LIBDEVICE) { ++g_launchCount; k_integrate<2, MATH_FAST_LIBDEVICE, 4><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4); }
+    else if (mathMode == MATH_FAST_POINTWISE) { ++g_launchCount; k_integrate<2, MATH_FAST_POINTWISE, 4><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4); }
+    else if (g_minBlocks == 3) { ++g_launchCount; k_regular_grouped<3><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4); }
+    else if (g_minBlocks == 5) { ++g_launchCount; k_regular_grouped<5><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4); }
+    else { ++g_launchCount; k_regular_grouped<4><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4); }
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -39,7 +39,7 @@ extern long long g_launchCount;       // kernels launched by the launch_* wrappe
 constexpr int kThreads = 128;          // CTA size of the integrate kernels
 
 // math mode of the regular-pair point function
-enum MathMode { MATH_STRICT = 0, MATH_FAST = 1 };
+enum MathMode { MATH_STRICT = 0, MATH_FAST = 1, MATH_FAST_LIBDEVICE = 2, MATH_FAST_POINTWISE = 3 };
 
 void launch_pack(const double *verts, const int *cells, const double *normals, const double *measures, int nc, int stride,
                  double *tri, cudaStream_t s);

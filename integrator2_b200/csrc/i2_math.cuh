@@ -1,0 +1,158 @@
+// Branch-free FP64 primitives for the regular-pair kernel (the FP64 pipe is the roofline, so every DFMA counts):
+//   fast_sqrt      MUFU.RSQ64H seed + one coupled Goldschmidt step + one residual correction   (7 FP64 ops)
+//   fast_rcp       MUFU.RCP64H seed + two Newton steps                                          (4 FP64 ops)
+//   log_ratio      ln(N/D) with the division folded into the atanh argument (N-D)/(N+D)        (~25 FP64 ops)
+//   atan2_fast     atan2(y,x) with a 5-entry argument reduction, one division                  (~26 FP64 ops)
+// libdevice spends ~17 (sqrt) / ~19 (div) / ~30 (log) / ~46 (atan2) FP64-pipe instructions on the same jobs and
+// branches into slow paths; these versions assume finite, non-denormal inputs (triangle geometry) and have no
+// data-dependent branches: warp-uniform control flow by construction.
+// Accuracy (tests/test_math_primitives.py, host emulation with a 2^-20 seed): <= 2 ulp each.
+// Fast-math relaxations, stated: no denormal / inf / NaN handling, results not correctly rounded (<= 2 ulp).
+#pragma once
+#include "i2_vec.cuh"
+
+#if !defined(__CUDA_ARCH__)
+#include <cstdint>
+#include <cstring>
+#endif
+
+namespace i2 {
+
+I2_HD int hi_word(double x) {
+#if defined(__CUDA_ARCH__)
+    return __double2hiint(x);
+#else
+    uint64_t u; memcpy(&u, &x, 8); return (int)(u >> 32);
+#endif
+}
+I2_HD int lo_word(double x) {
+#if defined(__CUDA_ARCH__)
+    return __double2loint(x);
+#else
+    uint64_t u; memcpy(&u, &x, 8); return (int)(u & 0xffffffffu);
+#endif
+}
+I2_HD double make_double(int hi, int lo) {
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(hi, lo);
+#else
+    uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double x; memcpy(&x, &u, 8); return x;
+#endif
+}
+
+// hardware seeds: ~2^-22 relative accuracy, use only the high word of the operand
+I2_HD double rsqrt_seed(double x) {
+#if defined(__CUDA_ARCH__)
+    double y; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x)); return y;
+#else
+    return (1.0 / sqrt(x)) * (1.0 + 9.5e-7);   // host emulation: deliberately ~2^-20 off, any magnitude
+#endif
+}
+I2_HD double rcp_seed(double x) {
+#if defined(__CUDA_ARCH__)
+    double y; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x)); return y;
+#else
+    return (1.0 / x) * (1.0 - 9.5e-7);
+#endif
+}
+
+I2_HD double fast_sqrt(double x) {
+    const double y = rsqrt_seed(x);
+    double g = x * y, h = 0.5 * y;
+    const double r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    return fma(fma(-g, g, x), h, g);   // g + (x - g^2) * (1/(2 sqrt x))
+}
+
+I2_HD double fast_rcp(double x) {
+    double y = rcp_seed(x);
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
+// ln(N/D), N, D > 0.  N = 2^eN mN, D = 2^eD mD with mN, mD in [1,2); the pair is rescaled by one more factor 2 if
+// needed so that mN/mD lies in about [1/sqrt2, sqrt2] (decided on the FP32 pipe, the exact cut does not matter);
+// then ln(mN/mD) = 2 atanh(f), f = (mN-mD)/(mN+mD), |f| <= 0.1716: odd series in f up to f^21.
+// mN - mD is exact (Sterbenz), so the result keeps full RELATIVE accuracy when N/D -> 1, which log(N/D) does not.
+I2_HD double log_ratio(double N, double D) {
+    const int hN = hi_word(N), hD = hi_word(D);
+    int e = (hN >> 20) - (hD >> 20);
+    int mhN = (hN & 0x000fffff) | 0x3ff00000, mhD = (hD & 0x000fffff) | 0x3ff00000;
+    // FP32 views of the mantissas (top 20 bits are plenty to pick the branch)
+#if defined(__CUDA_ARCH__)
+    const float fN = __int_as_float(0x3f800000 | ((hN & 0x000fffff) << 3));
+    const float fD = __int_as_float(0x3f800000 | ((hD & 0x000fffff) << 3));
+#else
+    float fN, fD; { int a = 0x3f800000 | ((hN & 0x000fffff) << 3), b = 0x3f800000 | ((hD & 0x000fffff) << 3); memcpy(&fN, &a, 4); memcpy(&fD, &b, 4); }
+#endif
+    const bool big = fN > 1.41421356f * fD, small = fN * 1.41421356f < fD;
+    mhN -= big ? 0x00100000 : 0;     // mN /= 2
+    mhD -= small ? 0x00100000 : 0;   // mD /= 2
+    e += (big ? 1 : 0) - (small ? 1 : 0);
+    const double mN = make_double(mhN, lo_word(N)), mD = make_double(mhD, lo_word(D));
+    const double s = mN + mD, d = mN - mD;
+    const double r = fast_rcp(s);
+    double f = d * r;
+    f = fma(fma(-f, s, d), r, f);    // residual correction: f is now (mN-mD)/(mN+mD) to ~0.5 ulp
+    const double z = f * f;
+    double p = 2.0 / 21.0;
+    p = fma(p, z, 2.0 / 19.0);
+    p = fma(p, z, 2.0 / 17.0);
+    p = fma(p, z, 2.0 / 15.0);
+    p = fma(p, z, 2.0 / 13.0);
+    p = fma(p, z, 2.0 / 11.0);
+    p = fma(p, z, 2.0 / 9.0);
+    p = fma(p, z, 2.0 / 7.0);
+    p = fma(p, z, 2.0 / 5.0);
+    p = fma(p, z, 2.0 / 3.0);
+    const double lg = fma(f * z, p, f + f);                 // 2 atanh(f)
+    const double ed = (double)e;
+    return fma(ed, 6.93147180369123816490e-01, fma(ed, 1.90821492927058770002e-10, lg));   // ln2 split hi/lo
+}
+
+// atan2(y, x) for finite arguments, not both zero.  t = min/max in [0,1]; c = nearest of {0, 1/4, 1/2, 3/4, 1};
+// atan t = atan c + atan((t-c)/(1+tc)) = atan c + atan((mn - c mx)/(mx + c mn)), |arg| <= 0.1244: odd series to ^19.
+I2_HD double atan2_fast(double y, double x) {
+    const double ax = fabs(x), ay = fabs(y);
+    const double mx = fmax(ax, ay), mn = fmin(ax, ay);
+    // choose c on the integer / FP32 pipes from the leading bits of the operands (any magnitude: only the exponent
+    // difference and the top 20 mantissa bits are used, so nothing overflows a float)
+    const int hm = hi_word(mn), hx = hi_word(mx);
+    const int de = (hx >> 20) - (hm >> 20);                      // >= 0
+    const int bm = de < 64 ? (((127 - de) << 23) | ((hm & 0x000fffff) << 3)) : 0;
+    const int bx = 0x3f800000 | ((hx & 0x000fffff) << 3);
+#if defined(__CUDA_ARCH__)
+    const float q = __fdividef(__int_as_float(bm), __int_as_float(bx));
+#else
+    float fm, fx; memcpy(&fm, &bm, 4); memcpy(&fx, &bx, 4);
+    const float q = fm / fx;
+#endif
+    const int k = (int)(q * 4.0f + 0.5f);                       // 0..4
+    const double c = 0.25 * (double)k;
+    // atan(k/4), k = 0..4
+    const double at = k == 0 ? 0.0 : (k == 1 ? 2.44978663126864154172e-01 : (k == 2 ? 4.63647609000806116214e-01
+                      : (k == 3 ? 6.43501108793284386803e-01 : 7.85398163397448309616e-01)));
+    const double num = fma(-c, mx, mn), den = fma(c, mn, mx);
+    const double r = fast_rcp(den);
+    double t = num * r;
+    t = fma(fma(-t, den, num), r, t);
+    const double z = t * t;
+    double p = -1.0 / 19.0;
+    p = fma(p, z, 1.0 / 17.0);
+    p = fma(p, z, -1.0 / 15.0);
+    p = fma(p, z, 1.0 / 13.0);
+    p = fma(p, z, -1.0 / 11.0);
+    p = fma(p, z, 1.0 / 9.0);
+    p = fma(p, z, -1.0 / 7.0);
+    p = fma(p, z, 1.0 / 5.0);
+    p = fma(p, z, -1.0 / 3.0);
+    double a = at + fma(t * z, p, t);                           // atan(mn/mx) in [0, pi/4]
+    a = ay > ax ? 1.57079632679489655800e+00 - a : a;           // pi/2 - a
+    a = x < 0.0 ? 3.14159265358979311600e+00 - a : a;           // pi - a
+    return copysign(a, y);
+}
+
+}  // namespace i2

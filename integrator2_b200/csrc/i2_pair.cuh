@@ -19,6 +19,7 @@
 // The file also compiles as host code (tests/host_emu) so numerics can be pre-checked on CPU.
 #pragma once
 #include "i2_vec.cuh"
+#include "i2_math.cuh"
 
 namespace i2 {
 
@@ -58,9 +59,14 @@ I2_HD d4 theta_psi_strict(d3 M, d3 A, d3 B, d3 C) {
 // with selects on the log argument (warp-uniform control flow, no branch).
 struct LogTheta { double t1, t2, t3, theta; };
 
+// PRIM = true : branch-free primitives of i2_math.cuh (fast_sqrt / log_ratio / atan2_fast)  -> the product path
+// PRIM = false: same algebra with libdevice sqrt / log / atan2 and IEEE division             -> diagnostic variant
+template <bool PRIM>
 I2_HD LogTheta theta_psi_fast(d3 M, const TriJ &T) {
     const d3 da = M - T.A, db = M - T.B, dc = M - T.C;
-    const double la = sqrt(norm2(da)), lb = sqrt(norm2(db)), lc = sqrt(norm2(dc));
+    const double la = PRIM ? fast_sqrt(norm2(da)) : sqrt(norm2(da));
+    const double lb = PRIM ? fast_sqrt(norm2(db)) : sqrt(norm2(db));
+    const double lc = PRIM ? fast_sqrt(norm2(dc)) : sqrt(norm2(dc));
 
     const double n1 = la + dot(da, T.tc), q1 = lb + dot(db, T.tc);
     const double n2 = lb + dot(db, T.ta), q2 = lc + dot(dc, T.ta);
@@ -70,12 +76,48 @@ I2_HD LogTheta theta_psi_fast(d3 M, const TriJ &T) {
     const bool f3 = fabs(q3) < 0.5 * EPS_PSI_THETA2 * la;
 
     LogTheta r;
-    r.t1 = log((f1 ? lb : n1) / (f1 ? la : q1));
-    r.t2 = log((f2 ? lc : n2) / (f2 ? lb : q2));
-    r.t3 = log((f3 ? la : n3) / (f3 ? lc : q3));
     const double num = dot(da, T.Nu);
     const double den = la * lb * lc + dot(da, db) * lc + dot(db, dc) * la + dot(dc, da) * lb;
-    r.theta = 2.0 * atan2(num, den);
+    if (PRIM) {
+        r.t1 = log_ratio(f1 ? lb : n1, f1 ? la : q1);
+        r.t2 = log_ratio(f2 ? lc : n2, f2 ? lb : q2);
+        r.t3 = log_ratio(f3 ? la : n3, f3 ? lc : q3);
+        r.theta = 2.0 * atan2_fast(num, den);
+    } else {
+        r.t1 = log((f1 ? lb : n1) / (f1 ? la : q1));
+        r.t2 = log((f2 ? lc : n2) / (f2 ? lb : q2));
+        r.t3 = log((f3 ? la : n3) / (f3 ? lc : q3));
+        r.theta = 2.0 * atan2(num, den);
+    }
+    return r;
+}
+
+// ---- regular pairs, grouped form: one log per edge and one atan2 per GROUP of equal-weight Gauss points ---------
+// Cowper's rules repeat weights (13-point rule: 1 + 3 + 3 + 6 points), and
+//     sum_{g in G} w ln(N_g/D_g) = w ln( prod N_g / prod D_g ),   sum_{g in G} w atan2(y_g,x_g) = w arg prod (x_g + i y_g),
+// so a pair needs 4 x (3 logs + 1 atan2) instead of 13 x (3 logs + 1 atan2).  The argument identity holds while the
+// partial angle sums stay inside (-pi, pi); every point checks |y_g| <= x_g / 2 (|angle| < pi/6, groups have <= 6
+// points) and a group that fails the check anywhere in the WARP is redone point by point (warp-uniform branch).
+struct PointTerms {
+    double N1, D1, N2, D2, N3, D3;   // log arguments after the epsilon selects
+    double num, den;                 // Theta_g = 2 atan2(num, den)
+};
+
+I2_HD PointTerms point_terms(d3 M, const TriJ &T) {
+    const d3 da = M - T.A, db = M - T.B, dc = M - T.C;
+    const double la = fast_sqrt(norm2(da)), lb = fast_sqrt(norm2(db)), lc = fast_sqrt(norm2(dc));
+    const double n1 = la + dot(da, T.tc), q1 = lb + dot(db, T.tc);
+    const double n2 = lb + dot(db, T.ta), q2 = lc + dot(dc, T.ta);
+    const double n3 = lc + dot(dc, T.tb), q3 = la + dot(da, T.tb);
+    const bool f1 = fabs(q1) < 0.5 * EPS_PSI_THETA2 * lb;
+    const bool f2 = fabs(q2) < 0.5 * EPS_PSI_THETA2 * lc;
+    const bool f3 = fabs(q3) < 0.5 * EPS_PSI_THETA2 * la;
+    PointTerms r;
+    r.N1 = f1 ? lb : n1; r.D1 = f1 ? la : q1;
+    r.N2 = f2 ? lc : n2; r.D2 = f2 ? lb : q2;
+    r.N3 = f3 ? la : n3; r.D3 = f3 ? lc : q3;
+    r.num = dot(da, T.Nu);
+    r.den = la * lb * lc + dot(da, db) * lc + dot(db, dc) * la + dot(dc, da) * lb;
     return r;
 }
 

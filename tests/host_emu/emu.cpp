@@ -2,6 +2,7 @@
 // used to pre-check numerics of math variants on the CPU (no GPU in the build container).  It is never
 // loaded by the product; the product has no CPU path.
 #include "../../integrator2_b200/csrc/i2_pair.cuh"
+#include "../../integrator2_b200/csrc/i2_math.cuh"
 #include <cstring>
 
 using namespace i2;
@@ -30,6 +31,11 @@ static d3 gp(int g, d3 A, d3 B, d3 C) {
 
 extern "C" {
 
+void emu_fast_sqrt(const double *x, long long n, double *out) { for (long long k = 0; k < n; ++k) out[k] = fast_sqrt(x[k]); }
+void emu_fast_rcp(const double *x, long long n, double *out) { for (long long k = 0; k < n; ++k) out[k] = fast_rcp(x[k]); }
+void emu_log_ratio(const double *a, const double *b, long long n, double *out) { for (long long k = 0; k < n; ++k) out[k] = log_ratio(a[k], b[k]); }
+void emu_atan2(const double *y, const double *x, long long n, double *out) { for (long long k = 0; k < n; ++k) out[k] = atan2_fast(y[k], x[k]); }
+
 void emu_set_quadrature(const double *xy, const double *w, int n) {
     g_n = n;
     for (int g = 0; g < n; ++g) { g_L[g][0] = xy[2 * g]; g_L[g][1] = xy[2 * g + 1]; g_L[g][2] = 1.0 - xy[2 * g] - xy[2 * g + 1]; g_w[g] = w[g]; }
@@ -49,16 +55,75 @@ void emu_regular(const double *v, const int *cells, const double *measures, cons
                 acc.x = fma(g_w[g], f.x, acc.x); acc.y = fma(g_w[g], f.y, acc.y); acc.z = fma(g_w[g], f.z, acc.z); acc.w = fma(g_w[g], f.w, acc.w);
             }
             res = measures[i] * acc;
+        } else if (mode == 3) {
+            // grouped evaluation, same sequence as k_regular_grouped (per-thread safety flag instead of the warp vote)
+            double a1 = 0, a2 = 0, a3 = 0, a4 = 0, pn1 = 1, pd1 = 1, pn2 = 1, pd2 = 1, pn3 = 1, pd3 = 1, zr = 1, zi = 0;
+            bool safe = true;
+            int gStart = 0;
+            for (int g = 0; g < g_n; ++g) {
+                const PointTerms t = point_terms(gp(g, I.A, I.B, I.C), T);
+                pn1 *= t.N1; pd1 *= t.D1; pn2 *= t.N2; pd2 *= t.D2; pn3 *= t.N3; pd3 *= t.D3;
+                const double nr = fma(zr, t.den, -(zi * t.num)), ni = fma(zr, t.num, zi * t.den);
+                zr = nr; zi = ni;
+                safe = safe && (fabs(t.num) <= 0.5 * t.den);
+                const bool last = (g == g_n - 1) || (g_w[g + 1] != g_w[g]) || (g - gStart == 5);
+                if (last) {
+                    const double w = g_w[g];
+                    a1 = fma(w, log_ratio(pn1, pd1), a1); a2 = fma(w, log_ratio(pn2, pd2), a2); a3 = fma(w, log_ratio(pn3, pd3), a3);
+                    double th;
+                    if (safe) th = atan2_fast(zi, zr);
+                    else { th = 0; for (int h = gStart; h <= g; ++h) { const PointTerms u = point_terms(gp(h, I.A, I.B, I.C), T); th += atan2_fast(u.num, u.den); } }
+                    a4 = fma(w, th + th, a4);
+                    pn1 = pd1 = pn2 = pd2 = pn3 = pd3 = zr = 1.0; zi = 0.0; safe = true; gStart = g + 1;
+                }
+            }
+            const double S = measures[i];
+            res = vec4((S * a1) * T.tc + (S * a2) * T.ta + (S * a3) * T.tb, S * a4);
         } else {
             double a1 = 0, a2 = 0, a3 = 0, a4 = 0;
             for (int g = 0; g < g_n; ++g) {
-                const LogTheta r = theta_psi_fast(gp(g, I.A, I.B, I.C), T);
+                const LogTheta r = mode == 1 ? theta_psi_fast<true>(gp(g, I.A, I.B, I.C), T) : theta_psi_fast<false>(gp(g, I.A, I.B, I.C), T);
                 a1 = fma(g_w[g], r.t1, a1); a2 = fma(g_w[g], r.t2, a2); a3 = fma(g_w[g], r.t3, a3); a4 = fma(g_w[g], r.theta, a4);
             }
             const double S = measures[i];
             res = vec4((S * a1) * T.tc + (S * a2) * T.ta + (S * a3) * T.tb, S * a4);
         }
         out[4 * t] = res.x; out[4 * t + 1] = res.y; out[4 * t + 2] = res.z; out[4 * t + 3] = res.w;
+    }
+}
+
+
+// regular-pair integral at a uniform refinement level, hoisted algebra (mode 1: primitives, 2: libm), children as in the kernel
+static void descend_h(d3 &A, d3 &B, d3 &C, int level, int c) {
+    for (int s = level - 1; s >= 0; --s) {
+        const int d = (c >> (2 * s)) & 3;
+        const d3 ma = 0.5 * (B + C), mb = 0.5 * (C + A), mc = 0.5 * (A + B);
+        if (d == 0) { A = mc; C = ma; }
+        else if (d == 1) { A = ma; B = C; C = mb; }
+        else if (d == 2) { B = A; A = mb; C = mc; }
+        else { A = ma; B = mb; C = mc; }
+    }
+}
+void emu_regular_level(const double *v, const int *cells, const double *measures, const int *tasks, long long n, int mode, int level, double *out) {
+#pragma omp parallel for schedule(static)
+    for (long long t = 0; t < n; ++t) {
+        const int i = tasks[3 * t], j = tasks[3 * t + 1];
+        const TriJ I = make_tri(v, cells, i), T = make_tri(v, cells, j);
+        double Si = measures[i];
+        for (int l = 0; l < level; ++l) Si *= 0.25;
+        double s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+        for (int c = 0; c < (1 << (2 * level)); ++c) {
+            d3 A = I.A, B = I.B, C = I.C;
+            descend_h(A, B, C, level, c);
+            double a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+            for (int g = 0; g < g_n; ++g) {
+                const LogTheta r = mode == 1 ? theta_psi_fast<true>(gp(g, A, B, C), T) : theta_psi_fast<false>(gp(g, A, B, C), T);
+                a1 = fma(g_w[g], r.t1, a1); a2 = fma(g_w[g], r.t2, a2); a3 = fma(g_w[g], r.t3, a3); a4 = fma(g_w[g], r.theta, a4);
+            }
+            s1 = fma(Si, a1, s1); s2 = fma(Si, a2, s2); s3 = fma(Si, a3, s3); s4 = fma(Si, a4, s4);
+        }
+        const d3 psi = s1 * T.tc + s2 * T.ta + s3 * T.tb;
+        out[4 * t] = psi.x; out[4 * t + 1] = psi.y; out[4 * t + 2] = psi.z; out[4 * t + 3] = s4;
     }
 }
 

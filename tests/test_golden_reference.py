@@ -1,0 +1,142 @@
+"""Pins the CPU oracle against the reference's own CUDA build.
+
+tests/golden/reference_b200.npz holds binary dumps produced on a B200 by the UNMODIFIED reference sources
+(oracle/build_ref.sh + oracle/ref_dump.cu, run by tools/gpu_golden.sh, packed by tools/pack_golden.py): the reference
+ships no golden vectors of its own, so these are the known answers.  CPU-only tests."""
+import json
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from helpers import K_NOISE, REL_TOL, reference_noise_bound
+from integrator2_b200.meshio import load_fixture
+
+G = np.load(f"{ROOT}/tests/golden/reference_b200.npz")
+META = json.loads(bytes(G["meta"]).decode())
+CLS = ("simple", "attached", "not")
+
+MESH_OF = {"G1": ("G1", 1.0), "s5m": ("s5m", 0.0005), "s5m2": ("s5m2", 0.0005), "Vint16k": ("Vint16k", 1.0), "cubehole": ("cubehole", 1.0),
+           "ellipsoid2000": ("ellipsoid2000", 1.0), "extrafine": ("1x1x1_extrafine", 1.0)}
+
+
+def dump_mesh(name):
+    base = name.rsplit("_", 1)[0] if not name.endswith("_nofma") else name.rsplit("_", 2)[0]
+    fixture, scale = MESH_OF.get(base, (base, 1.0))
+    return load_fixture(fixture, scale)
+
+
+def level_of(name):
+    tag = name.replace("_nofma", "").rsplit("_", 1)[1]
+    return -1 if tag == "ad" else int(tag[1:])
+
+
+def parse_rounds(log):
+    """per class: list of (checked, converged, unconverged) from the reference's 'Out of ...' lines."""
+    out, cur = [], None
+    for ln in log:
+        if ln.startswith("Integrating over"):
+            cur = []
+            out.append(cur)
+        elif ln.startswith("Out of") and cur is not None:
+            a = [int(x) for x in ln.replace(":", " ").replace(",", " ").split() if x.isdigit()]
+            cur.append(tuple(a))
+    return out
+
+
+def test_fixture_has_the_headline_dumps():
+    for must in ("G1_r0", "G1_ad", "s5m_r0", "s5m_ad", "s5m2_ad", "Vint16k_r0", "Case-7-2_r0", "Case-9-1_ad"):
+        assert must in META
+    assert len([k for k in META if k.startswith("Case")]) >= 70
+
+
+@pytest.mark.parametrize("name", ["G1_r0", "G1_r1", "G1_ad"])
+def test_oracle_matches_reference_G1(oracle, name):
+    """Well-conditioned mesh: the oracle reproduces the reference's CUDA results to <= 1e-12 relative in every class,
+    including adaptive mode with its buffer ping-pong (D7) and the per-cell refinement counters."""
+    m = dump_mesh(name)
+    om = oracle.OracleMesh(m.vertices, m.cells)
+    level = level_of(name)
+    for c, cn in enumerate(CLS):
+        t = np.ascontiguousarray(G[f"{name}.{cn}.tasks"])
+        r = om.run_class(c, t, level)
+        J = G[f"{name}.{cn}.J"]
+        rel = np.abs(r["results"] - J).sum(1) / np.abs(J).sum(1)
+        assert rel.max() <= 1e-12, (name, cn, rel.max())
+        if f"{name}.{cn}.I" in G.files:
+            Iref = G[f"{name}.{cn}.I"]
+            assert (np.abs(r["integrals"] - Iref).sum(1) / np.abs(Iref).sum(1)).max() <= 1e-12
+        if level < 0:
+            assert np.array_equal(r["refinements"], G[f"{name}.refinements"][c]), (name, cn)
+            rounds = parse_rounds(META[name]["log"])[c]
+            assert int(r["stats"][0]) == len(rounds)
+            for k, (checked, conv, unconv) in enumerate(rounds, start=1):
+                assert int(r["stats"][2 + 2 * k]) == unconv
+
+
+def test_fixed_level_2_deviates_in_the_reference(oracle):
+    """at fixed level >= 2 the reference integrates tasks over the children of the WRONG cell (stale index
+    table), so its (i,j)/(j,i) results are not the integral of pair (i,j); level 0 and 1 are fine.  Documented deviation:
+    the oracle (and the product) integrate over the children of cell i."""
+    m = dump_mesh("G1_r2")
+    om = oracle.OracleMesh(m.vertices, m.cells)
+    t = np.ascontiguousarray(G["G1_r2.not.tasks"])
+    J = G["G1_r2.not.J"]
+    mine = om.run_class(2, t, 2)["results"]
+    rel = np.abs(mine - J).sum(1) / np.abs(J).sum(1)
+    assert np.median(rel) > 1e-3          # the reference's -r 2 output is NOT the level-2 integral of its own task
+    lvl1 = om.run_class(2, t, 1)["results"]
+    assert np.median(np.abs(mine - lvl1).sum(1) / np.abs(lvl1).sum(1)) < 1e-6   # while true level 2 ~ level 1
+
+
+TWO_TRI = sorted(k for k in META if k.startswith(("Case", "G1Sosed", "G1new", "G1Cont", "G1contact", "genCase", "Test")))
+
+
+@pytest.mark.parametrize("name", TWO_TRI)
+def test_oracle_matches_reference_two_triangle_cases(oracle, name):
+    """Two-triangle fixtures (special-case branches of the closed-form singular integrals), fixed and adaptive."""
+    m = dump_mesh(name)
+    om = oracle.OracleMesh(m.vertices, m.cells)
+    level = level_of(name)
+    for c, cn in enumerate(CLS):
+        t = np.ascontiguousarray(G[f"{name}.{cn}.tasks"])
+        if t.shape[0] == 0:
+            continue
+        r = om.run_class(c, t, level)
+        J = G[f"{name}.{cn}.J"]
+        assert np.isfinite(J).all() == np.isfinite(r["results"]).all()
+        rel = np.abs(r["results"] - J).sum(1) / np.maximum(np.abs(J).sum(1), 1e-300)
+        assert rel.max() <= 2e-10, (name, cn, rel, r["results"], J)
+        if level < 0:
+            rounds = parse_rounds(META[name]["log"])
+            assert int(r["stats"][0]) == len(rounds[c]), (name, r["stats"], rounds)
+
+
+@pytest.mark.parametrize("name", ["s5m_r0", "s5m_r1", "cubehole_r0", "ellipsoid2000_r0", "extrafine_r0", "Vint16k_r0"])
+def test_oracle_matches_reference_regular_pairs_with_noise_model(oracle, name):
+    """Regular pairs on meshes with distant / nearly collinear configurations: conditioning-aware tolerance (helpers.py)."""
+    m = dump_mesh(name)
+    om = oracle.OracleMesh(m.vertices, m.cells)
+    t = np.ascontiguousarray(G[f"{name}.not.tasks"])
+    J = G[f"{name}.not.J"]
+    mine = om.run_class(2, t, level_of(name))["results"]
+    err = np.abs(mine - J).sum(1)
+    allowed = REL_TOL * np.abs(J).sum(1) + K_NOISE * reference_noise_bound(m.vertices, m.cells, t)
+    assert (err <= allowed).all(), (name, float((err / allowed).max()))
+
+
+def test_reference_self_noise_fma_vs_nofma():
+    """The reference compiled with and without FMA contraction differs from ITSELF by far more than 1e-12 on s5m:
+    the empirical noise floor that motivates the conditioning-aware tolerance."""
+    a, b = "s5m_r0", "s5m_r0_nofma"
+    from helpers import align_by_pair
+    worst = {}
+    for cn in CLS:
+        ia, ib = align_by_pair(G[f"{a}.{cn}.tasks"], G[f"{b}.{cn}.tasks"])
+        Ja, Jb = G[f"{a}.{cn}.J"][ia], G[f"{b}.{cn}.J"][ib]
+        rel = np.abs(Ja - Jb).sum(1) / np.abs(Ja).sum(1)
+        worst[cn] = float(rel.max()) if rel.size else 0.0
+    assert worst["simple"] > 1e-10 and worst["attached"] > 1e-11
+    ia, ib = align_by_pair(G["G1_r0.not.tasks"], G["G1_r0_nofma.not.tasks"])
+    rel = np.abs(G["G1_r0.not.J"][ia] - G["G1_r0_nofma.not.J"][ib]).sum(1) / np.abs(G["G1_r0.not.J"][ia]).sum(1)
+    assert rel.max() < 1e-13      # while the well-conditioned sphere agrees to rounding

@@ -152,9 +152,9 @@ def test_host_buffer_entry_points(ctx, oracle):
     c2 = abi.Context(0)
     counts = c2.host_prepare(m.vertices, m.cells)
     assert counts == [19304, 5592, 3447736]
-    ht = [torch.empty((n, 3), dtype=torch.int32).pin_memory() for n in counts]
-    hr = [torch.empty((n, 3), dtype=torch.float64).pin_memory() for n in counts]
-    he = [torch.empty((n,), dtype=torch.float64).pin_memory() for n in counts]
+    ht = [torch.empty((n, 3), dtype=torch.int32, pin_memory=True) for n in counts]
+    hr = [torch.empty((n, 3), dtype=torch.float64, pin_memory=True) for n in counts]
+    he = [torch.empty((n,), dtype=torch.float64, pin_memory=True) for n in counts]
     c2.host_run(0, ht, hr)
     om = oracle.OracleMesh(m.vertices, m.cells)
     for cls in range(3):
@@ -164,7 +164,7 @@ def test_host_buffer_entry_points(ctx, oracle):
         r = ctx.integrate_class(cls, ht[cls].cuda(), 0)
         assert np.array_equal(r["results"].cpu().numpy(), hr[cls].numpy()), cls
     # with the (i,j)/(j,i) defect and in adaptive mode
-    href = [torch.zeros((m.n_cells,), dtype=torch.uint8).pin_memory() for _ in range(3)]
+    href = [torch.zeros((m.n_cells,), dtype=torch.uint8, pin_memory=True) for _ in range(3)]
     stats = c2.host_run(-1, ht, hr, he, href)
     assert stats[2]["last_round"] >= 2 and stats[2]["integrated"][1] == 4 * counts[2]
     assert href[2].numpy().max() >= 2 and np.isfinite(he[2].numpy()).all()
