@@ -357,28 +357,32 @@ def reference_total_pairs(mesh):
     return n * (n - 1)
 
 
-def cpu_oracle_rate_from_mesh(O, om, mesh, level):
-    """Bounded CPU sample without the O(N^2) host classification: regular tasks drawn as strided (i, j) pairs that share no vertex."""
+def cpu_oracle_rate_from_mesh(O, om, mesh, level, budget_s=15.0):
+    """Bounded CPU sample without the O(N^2) host classification: all regular partners j of every s-th control panel i
+    (rows of the pair matrix), s chosen so that the OpenMP oracle works for about budget_s seconds."""
     import numpy as np
     n = mesh.n_cells
-    rng_i = np.arange(0, n, max(1, n // 1500))
-    rng_j = np.arange(1, n, max(1, n // 1500))
-    I, J = np.meshgrid(rng_i, rng_j, indexing="ij")
-    I, J = I.ravel(), J.ravel()
-    ci, cj = mesh.cells[I], mesh.cells[J]
-    shared = (ci[:, :, None] == cj[:, None, :]).any(axis=(1, 2))
-    keep = (~shared) & (I != J)
-    t = np.stack([I[keep], J[keep], np.arange(keep.sum())], axis=1).astype(np.int32)
-    probe = t[:20000]
-    t0 = time.time()
-    om.run_class(2, np.ascontiguousarray(probe), level)
-    dt = max(time.time() - t0, 1e-3)
-    m = int(min(t.shape[0], max(20000, 20000 * 12.0 / dt)))
-    sample = np.ascontiguousarray(t[:m])
-    t0 = time.time()
-    om.run_class(2, sample, level)
-    dt = time.time() - t0
-    return m / dt, O.num_threads(), f"{m} regular pairs of the same mesh (strided (i,j) grid), OpenMP oracle, {dt:.1f} s"
+
+    def rows_tasks(rows):
+        I = np.repeat(rows, n)
+        J = np.tile(np.arange(n), rows.size)
+        ci, cj = mesh.cells[I], mesh.cells[J]
+        shared = (ci[:, :, None] == cj[:, None, :]).any(axis=(1, 2))
+        keep = ~shared
+        return np.ascontiguousarray(np.stack([I[keep], J[keep], np.arange(int(keep.sum()))], axis=1).astype(np.int32))
+
+    nrows, dt, sample, rows = 16, 0.0, None, None
+    for _ in range(4):   # grow the sample until it costs about budget_s (first calls also warm up the OpenMP team)
+        rows = np.unique(np.linspace(0, n - 1, nrows).astype(np.int64))
+        sample = rows_tasks(rows)
+        t0 = time.time()
+        om.run_class(2, sample, level)
+        dt = max(time.time() - t0, 1e-3)
+        if dt >= 0.6 * budget_s or rows.size >= n:
+            break
+        nrows = int(min(n, max(nrows + 1, nrows * budget_s / dt)))
+    return sample.shape[0] / dt, O.num_threads(), (f"{sample.shape[0]} regular pairs of the same mesh (all partners j of {rows.size} evenly spaced "
+                                                   f"control panels i), OpenMP oracle, {dt:.1f} s")
 
 
 if __name__ == "__main__":

@@ -129,6 +129,10 @@ int i2_launch_count(long long *h_count);
 int i2_set_profiling(i2_context *ctx, int enabled);
 int i2_profile_last(i2_context *ctx, float *ms_integrate, float *ms_finalize);
 
+/* self-test hook: evaluates one of the device math primitives of the regular-pair kernel element-wise on device arrays
+ * (op 0: fast_sqrt(a), 1: fast_rcp(a), 2: log_ratio(a, b), 3: atan2_fast(a, b)); used by tests/test_math_primitives.py */
+int i2_selftest_math(i2_context *ctx, int op, const double *d_a, const double *d_b, long long n, double *d_out);
+
 /* ---- measured roofline denominators: FP64-pipe DFMA rate and XU-pipe MUFU rate of this device ---------- */
 int i2_peak_rates(i2_context *ctx, double *dfma_tflops, double *mufu_gops);
 

@@ -48,7 +48,7 @@ EXPORTS = [
     "i2_create", "i2_destroy", "i2_set_stream", "i2_synchronize", "i2_set_math_mode", "i2_error_string",
     "i2_set_quadrature", "i2_mesh_geometry", "i2_set_mesh", "i2_classify_count", "i2_classify_fill",
     "i2_add_reversed_pairs", "i2_integrate_class", "i2_symmetry_error", "i2_host_prepare", "i2_host_run",
-    "i2_host_device_views", "i2_peak_rates", "i2_refine_mesh_once", "i2_launch_count", "i2_set_profiling", "i2_profile_last",
+    "i2_host_device_views", "i2_peak_rates", "i2_refine_mesh_once", "i2_launch_count", "i2_set_profiling", "i2_profile_last", "i2_selftest_math",
 ]
 
 _lib = None
@@ -87,6 +87,7 @@ def load_library():
     L.i2_host_run.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(Stats)]
     L.i2_host_device_views.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.i2_refine_mesh_once.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, vp]
+    L.i2_selftest_math.argtypes = [vp, i32, vp, vp, ll, vp]
     L.i2_launch_count.argtypes = [C.POINTER(ll)]
     L.i2_set_profiling.argtypes = [vp, i32]
     L.i2_profile_last.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
@@ -222,6 +223,11 @@ class Context:
         err = torch.empty((n,), dtype=torch.float64, device=results.device)
         _check(self.L.i2_symmetry_error(self.h, _ptr(results), n // 2, _ptr(err)))
         return err
+
+    def selftest_math(self, op, a, b=None):
+        out = self.torch.empty_like(a)
+        _check(self.L.i2_selftest_math(self.h, op, _ptr(a), _ptr(b), a.numel(), _ptr(out)))
+        return out
 
     def set_profiling(self, on=True):
         _check(self.L.i2_set_profiling(self.h, 1 if on else 0))

@@ -436,6 +436,14 @@ int i2_host_run(i2_context *c, int level, int *const hTasks[3], double *const hR
     return 0;
 }
 
+int i2_selftest_math(i2_context *c, int op, const double *a, const double *b, long long n, double *out) {
+    if (!c || op < 0 || op > 3 || n < 0 || (n > 0 && (!a || !out || (op >= 2 && !b)))) return I2_E_BADARG;
+    I2_CUDA(cudaSetDevice(c->device));
+    launch_selftest_math(op, a, b, n, out, c->stream);
+    I2_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int i2_launch_count(long long *count) {
     if (!count) return I2_E_BADARG;
     *count = g_launchCount;

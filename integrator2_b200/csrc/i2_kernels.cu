@@ -623,6 +623,19 @@ __global__ void __launch_bounds__(256) k_peak_mufu(double *sink, int iters) {
     const double r = (a0 + a1) + (a2 + a3);
     if (r == 123.456) sink[0] = r;
 }
+__global__ void k_selftest_math(int op, const double *__restrict__ a, const double *__restrict__ b, long long n, double *out) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    double r;
+    if (op == 0) r = fast_sqrt(a[t]);
+    else if (op == 1) r = fast_rcp(a[t]);
+    else if (op == 2) r = log_ratio(a[t], b[t]);
+    else r = atan2_fast(a[t], b[t]);
+    out[t] = r;
+}
+void launch_selftest_math(int op, const double *a, const double *b, long long n, double *out, cudaStream_t s) {
+    if (n > 0) { ++g_launchCount; k_selftest_math<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(op, a, b, n, out); }
+}
 void launch_peak_dfma(double *sink, int iters, int blocks, cudaStream_t s) { ++g_launchCount; k_peak_dfma<<<blocks, 256, 0, s>>>(sink, iters); }
 void launch_peak_mufu(double *sink, int iters, int blocks, cudaStream_t s) { ++g_launchCount; k_peak_mufu<<<blocks, 256, 0, s>>>(sink, iters); }
 

@@ -106,3 +106,40 @@ def read_mesh_dump(path):
         if adaptive:
             ref = [np.frombuffer(f.read(nc), dtype=np.uint8).copy() for _ in range(3)]
     return dict(vertices=v, cells=c, normals=nrm, measures=area, adaptive=adaptive, refinements=ref)
+
+
+def perturbation_noise(oracle, vertices, cells, cls, tasks, level, trials=8, seed=0):
+    """Empirical rounding-noise scale of the reference formula for each task: the spread of the oracle's result when
+    every vertex coordinate is moved by -1/0/+1 ulp OF THE MESH EXTENT (an input change of the size of one rounding
+    error of a coordinate difference, propagated through the same formulas, so it sees the same cancellations and the
+    same epsilon-branches).  Used for the adjacent classes, whose regular part is the difference of two singular
+    functions.  Returns (noise[n], J_base[n,3])."""
+    tasks = np.ascontiguousarray(tasks)
+    base = oracle.OracleMesh(vertices, cells).run_class(cls, tasks, level)["results"]
+    rng = np.random.default_rng(seed)
+    ulp = np.spacing(np.abs(vertices).max())
+    worst = np.zeros(tasks.shape[0])
+    for _ in range(trials):
+        step = rng.integers(-1, 2, size=vertices.shape).astype(np.float64)
+        J = oracle.OracleMesh(vertices + step * ulp, cells).run_class(cls, tasks, level)["results"]
+        worst = np.maximum(worst, np.abs(J - base).sum(1))
+    return worst, base
+
+
+K_PERTURB = 32.0
+
+
+def check_parity_perturbation(oracle, vertices, cells, cls, tasks, level, J_new, J_ref=None, label=""):
+    """|J_new - J_ref|_1 <= 1e-12 |J_ref|_1 + K_PERTURB * noise_ij  (J_ref defaults to the oracle's value)."""
+    noise, base = perturbation_noise(oracle, vertices, cells, cls, tasks, level)
+    if J_ref is None:
+        J_ref = base
+    err = np.abs(J_new - J_ref).sum(1)
+    ref = np.abs(J_ref).sum(1)
+    allowed = REL_TOL * ref + K_PERTURB * noise
+    rel = err / np.maximum(ref, 1e-300)
+    stats = dict(n=int(tasks.shape[0]), rel_median=float(np.median(rel)), rel_max=float(rel.max()),
+                 frac_within_1e12=float((rel <= REL_TOL).mean()), worst_ratio_to_allowed=float((err / allowed).max()))
+    bad = np.nonzero(err > allowed)[0]
+    assert bad.size == 0, f"{label}: {bad.size} pairs outside tolerance {stats}; first bad task {tasks[bad[0]]}"
+    return stats

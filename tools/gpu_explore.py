@@ -25,10 +25,10 @@ counts = [int(t.shape[0]) for t in tasks]
 if what == "time":
     ctx.set_profiling(True)
     out = {"mesh": mesh_name, "counts": counts, "minblocks": os.environ.get("I2_MINBLOCKS", "4")}
-    for mode in (1, 0):
+    for mode in (1, 3, 2, 0):
         ctx.set_math_mode(mode)
         for cls in (2, 1, 0):
-            if mode == 0 and cls != 2:
+            if mode != 1 and cls != 2:
                 continue
             n = counts[cls]
             buf = (torch.empty((n, 4), dtype=torch.float64, device="cuda"), torch.empty((n, 3), dtype=torch.float64, device="cuda"))
