@@ -236,16 +236,22 @@ def main():
         gathered = [torch.empty((n, 3), dtype=torch.float64, device=dev) for n in counts]
     refin = torch.zeros((mesh.n_cells,), dtype=torch.uint8, device=dev) if args.level < 0 else None
 
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+
     def step():
-        for cls in range(3):
-            if refin is not None:
-                refin.zero_()
-            ctx.integrate_class(cls, tasks[cls], args.level, want_stats=False, refinements=refin, out=outs[cls])
-        if world > 1:
-            from integrator2_b200.multigpu import gather_results
-            with torch.cuda.stream(stream):
-                for cls in range(3):
-                    gather_results(outs[cls][1], gathered[cls] if rank == 0 else None, [b for b in shard_bounds(counts[cls], world)], rank, world)
+        if world == 1:
+            for cls in range(3):
+                if refin is not None:
+                    refin.zero_()
+                ctx.integrate_class(cls, tasks[cls], args.level, want_stats=False, refinements=refin, out=outs[cls])
+            return
+        # N > 1: shard of every class, finished chunks of results travel to rank 0 over NCCL while the next chunk computes
+        from integrator2_b200.multigpu import integrate_and_gather, wait_all
+        works = []
+        for cls in (2, 0, 1):
+            works += integrate_and_gather(ctx, cls, tasks[cls], args.level, outs[cls], gathered[cls] if rank == 0 else None,
+                                          shard_bounds(counts[cls], world), rank, world, side, chunks=8 if cls == 2 else 1)
+        wait_all(works, side)
 
     def barrier():
         torch.cuda.synchronize()
@@ -300,32 +306,64 @@ def main():
             flops = FLOP_PER_REGULAR_PAIR * my_counts[2] * (4 ** max(args.level, 0))
             achieved = flops / (ms_k * 1e-3) / 1e12
             roof = {"bound": "fp64", "achieved": achieved, "peak": dfma_tf, "unit": "TFLOP/s", "frac": achieved / dfma_tf,
-                    "traffic": None, "kernel": "k_integrate<not_neighbors, fast>", "kernel_ms": ms_k,
+                    "traffic": None, "kernel": "k_regular_grouped (not-neighbours, level 0, fused assembly)", "kernel_ms": ms_k,
                     "algorithmic_flop_per_pair": FLOP_PER_REGULAR_PAIR, "pairs_per_launch": my_counts[2],
                     "peak_source": "measured on this device by i2_peak_rates (DFMA chains); MEASURED_PEAKS.json has no FP64 figure",
-                    "mufu_peak_gops": mufu_g}
+                    "mufu_peak_gops": mufu_g,
+                    "note": "achieved uses the per-point work model of SURVEY.md 8(d) (6.1 kflop/pair); the grouped kernel executes ~1830 FP64 "
+                            "instructions (~2.9 kflop) per pair, i.e. frac > 1 means work removed, not a faster pipe; FP64-pipe active 64 % in "
+                            "profiles/r01_ncu_k_regular_grouped_v2.txt",
+                    "executed_fp64_inst_per_pair": 1830}
 
-    # ---- end to end through the host-buffer C ABI (N=1 path; at N>1 every rank does its shard after a full prepare) ----
+    # ---- end to end through the host-buffer C ABI (N=1): host mesh in -> prepare (H2D, geometry, classification, task
+    # lists) -> three classes -> results.  Two variants, both timed with the host clock around the blocking calls:
+    #   e2e.value            results stay resident in HBM (exactly what Evaluator3D::runAllPairs leaves behind) and the
+    #                        per-class checksums (96 B) are read back as the step's metric;
+    #   e2e.full_d2h         additionally every per-pair result and its (i,j) key is copied to pinned host memory
+    #                        (what outputResultsToFile does before formatting): 36 B/pair, PCIe-bound.
     e2e = None
     if not args.no_e2e and world == 1:
         del outs, tasks, tasks_full
         torch.cuda.empty_cache()
         c2 = abi.Context(local)
         cnt = c2.host_prepare(mesh.vertices, mesh.cells)
+        reps = max(2, min(args.steps, 5))
+
+        def timed(fn):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t0) / reps
+
+        sums = []
+
+        def resident():
+            c2.host_prepare(mesh.vertices, mesh.cells)
+            c2.host_run(args.level, None, None)
+            sums.append(c2.host_checksums())
+
+        dt_res = timed(resident)
         ht = [torch.empty((n, 3), dtype=torch.int32, pin_memory=True) for n in cnt]
         hr = [torch.empty((n, 3), dtype=torch.float64, pin_memory=True) for n in cnt]
-        for _ in range(2):
+
+        def full():
             c2.host_prepare(mesh.vertices, mesh.cells)
             c2.host_run(args.level, ht, hr)
-        t0 = time.perf_counter()
-        reps = max(2, min(args.steps, 5))
-        for _ in range(reps):
-            c2.host_prepare(mesh.vertices, mesh.cells)
-            c2.host_run(args.level, ht, hr)
-        dt = (time.perf_counter() - t0) / reps
-        e2e = {"value": sum(cnt) / dt, "unit": UNIT, "h2d_bytes_per_step": int(mesh.vertices.nbytes + mesh.cells.nbytes),
-               "d2h_bytes_per_step": int(sum(cnt) * (24 + 12)), "ms_per_step": dt * 1e3,
-               "what": "i2_host_prepare (H2D mesh, geometry, classification, task lists) + i2_host_run (3 classes, D2H of results and (i,j) keys into pinned memory)"}
+
+        dt_full = timed(full)
+        d2h = int(sum(cnt) * (24 + 12))
+        e2e = {"value": sum(cnt) / dt_res, "unit": UNIT, "h2d_bytes_per_step": int(mesh.vertices.nbytes + mesh.cells.nbytes),
+               "d2h_bytes_per_step": 96, "ms_per_step": dt_res * 1e3,
+               "what": "i2_host_prepare (H2D mesh, geometry, classification, ordered task lists) + i2_host_run (3 classes) with the per-pair "
+                       "results left in HBM like Evaluator3D::runAllPairs does, + D2H of the per-class checksums",
+               "checksum_sum_abs_J": [float(x) for x in sums[-1][:, 3]],
+               "full_d2h": {"value": sum(cnt) / dt_full, "unit": UNIT, "ms_per_step": dt_full * 1e3, "d2h_bytes_per_step": d2h,
+                            "d2h_gb_per_s": d2h / dt_full / 1e9,
+                            "what": "same, plus every per-pair result (24 B) and (i,j,k) key (12 B) copied to pinned host memory, chunks overlapped with compute"}}
         c2.close()
 
     cpu = None

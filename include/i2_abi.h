@@ -118,6 +118,9 @@ int i2_host_prepare(i2_context *ctx, const double *h_vertices, int nv, const int
                     long long h_task_counts[3]);
 int i2_host_run(i2_context *ctx, int level, int *const h_tasks[3], double *const h_results[3],
                 double *const h_errors[3], unsigned char *const h_refinements[3], i2_stats h_stats[3]);
+/* per class (sum J_x, sum J_y, sum J_z, sum |J|_1) of the results left in device memory by i2_host_run: the small
+ * 'metric' a caller reads back when the per-pair results stay resident (what Evaluator3D::runAllPairs leaves behind) */
+int i2_host_checksums(i2_context *ctx, double h_sums[12]);
 /* device views of what i2_host_prepare built (valid until the next prepare/destroy)                        */
 int i2_host_device_views(i2_context *ctx, const int *d_tasks[3], const double *d_results[3]);
 

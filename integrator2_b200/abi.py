@@ -48,7 +48,7 @@ EXPORTS = [
     "i2_create", "i2_destroy", "i2_set_stream", "i2_synchronize", "i2_set_math_mode", "i2_error_string",
     "i2_set_quadrature", "i2_mesh_geometry", "i2_set_mesh", "i2_classify_count", "i2_classify_fill",
     "i2_add_reversed_pairs", "i2_integrate_class", "i2_symmetry_error", "i2_host_prepare", "i2_host_run",
-    "i2_host_device_views", "i2_peak_rates", "i2_refine_mesh_once", "i2_launch_count", "i2_set_profiling", "i2_profile_last", "i2_selftest_math",
+    "i2_host_device_views", "i2_host_checksums", "i2_peak_rates", "i2_refine_mesh_once", "i2_launch_count", "i2_set_profiling", "i2_profile_last", "i2_selftest_math",
 ]
 
 _lib = None
@@ -85,6 +85,7 @@ def load_library():
     L.i2_symmetry_error.argtypes = [vp, vp, ll, vp]
     L.i2_host_prepare.argtypes = [vp, vp, i32, vp, i32, C.POINTER(ll)]
     L.i2_host_run.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(Stats)]
+    L.i2_host_checksums.argtypes = [vp, C.POINTER(C.c_double)]
     L.i2_host_device_views.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.i2_refine_mesh_once.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, vp]
     L.i2_selftest_math.argtypes = [vp, i32, vp, vp, ll, vp]
@@ -265,6 +266,11 @@ class Context:
         st = (Stats * 3)()
         _check(self.L.i2_host_run(self.h, level, arr(h_tasks), arr(h_results), arr(h_errors), arr(h_refinements), st))
         return [s.as_dict() for s in st]
+
+    def host_checksums(self):
+        a = (C.c_double * 12)()
+        _check(self.L.i2_host_checksums(self.h, a))
+        return np.array(list(a)).reshape(3, 4)
 
     def host_device_views(self):
         t = (C.c_void_p * 3)()

@@ -268,10 +268,13 @@ int i2_integrate_class(i2_context *c, int cls, const int *tasks, long long n, in
     cudaStream_t s = c->stream;
     const PackedMesh pm = packed(c);
     I2_CUDA(cudaMemsetAsync(c->qs, 0, sizeof(QueueState), s));
+    bool fused = false;
 
     if (level >= 0) {
         if (c->profiling) I2_CUDA(cudaEventRecord(c->prof[0], s));
-        launch_integrate(cls, c->mathMode, pm, tasks, nullptr, nullptr, n, level, integrals, c->numSMs, s);
+        // regular pairs with the grouped kernel: the final assembly is fused into the integrate kernel
+        fused = (cls == 2 && c->mathMode == I2_MATH_FAST);
+        launch_integrate(cls, c->mathMode, pm, tasks, nullptr, nullptr, n, level, integrals, fused ? results : nullptr, c->numSMs, s);
         if (c->profiling) I2_CUDA(cudaEventRecord(c->prof[1], s));
     } else {
         int rc = ensure(&c->bufB, &c->bufBCap, (size_t)4 * n);
@@ -289,7 +292,7 @@ int i2_integrate_class(i2_context *c, int cls, const int *tasks, long long n, in
         I2_CUDA(cudaMemsetAsync(c->cellFlag, 0, c->nc, s));
 
         // round 0: every task on the original control panel; every control panel present in the list is marked
-        launch_integrate(cls, c->mathMode, pm, tasks, nullptr, nullptr, n, 0, integrals, c->numSMs, s);
+        launch_integrate(cls, c->mathMode, pm, tasks, nullptr, nullptr, n, 0, integrals, nullptr, c->numSMs, s);
         launch_flag_cells(tasks, n, c->cellFlag, s);
         launch_bump(c->cellFlag, refinements, c->nc, s);
         // rounds 1..5 are enqueued unconditionally; a round whose device-side task count is 0 does nothing.
@@ -298,13 +301,13 @@ int i2_integrate_class(i2_context *c, int cls, const int *tasks, long long n, in
             const double *prev = (m & 1) ? integrals : c->bufB;
             const int *listIn = m == 1 ? nullptr : c->rest[(m - 1) & 1];
             const int *countIn = m == 1 ? nullptr : &c->qs->count[m - 1];
-            launch_integrate(cls, c->mathMode, pm, tasks, listIn, countIn, n, m, cur, c->numSMs, s);
+            launch_integrate(cls, c->mathMode, pm, tasks, listIn, countIn, n, m, cur, nullptr, c->numSMs, s);
             launch_compare(cur, prev, tasks, listIn, countIn, n, c->rest[m & 1], &c->qs->count[m], c->cellFlag, converged, c->qs, m,
                            c->numSMs, s);
             launch_bump(c->cellFlag, refinements, c->nc, s);
         }
     }
-    launch_finalize(cls, pm, c->verts, tasks, n, integrals, c->bufB, c->qs, results, c->qs, s);
+    if (!fused) launch_finalize(cls, pm, c->verts, tasks, n, integrals, c->bufB, c->qs, results, c->qs, s);
     I2_CUDA(cudaGetLastError());
     if (c->profiling && level >= 0) I2_CUDA(cudaEventRecord(c->prof[2], s));
 
@@ -372,6 +375,20 @@ int i2_host_prepare(i2_context *c, const double *hv, int nv, const int *hc, int 
         if (rc) return rc;
     }
     I2_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int i2_host_checksums(i2_context *c, double sums[12]) {
+    if (!c || !sums) return I2_E_BADARG;
+    if (!c->hVerts) return I2_E_NOMESH;
+    I2_CUDA(cudaSetDevice(c->device));
+    double *d = nullptr;
+    I2_CUDA(cudaMalloc((void **)&d, sizeof(double) * 12));
+    I2_CUDA(cudaMemsetAsync(d, 0, sizeof(double) * 12, c->stream));
+    for (int k = 0; k < 3; ++k) launch_checksum(c->hResults[k], c->hCount[k], d + 4 * k, c->numSMs, c->stream);
+    I2_CUDA(cudaMemcpyAsync(sums, d, sizeof(double) * 12, cudaMemcpyDeviceToHost, c->stream));
+    I2_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d);
     return 0;
 }
 

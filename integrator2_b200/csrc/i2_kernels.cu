@@ -258,7 +258,7 @@ k_integrate(PackedMesh pm, const int *__restrict__ tasks, const int *__restrict_
 template <int MINB>
 __global__ void __launch_bounds__(kThreads, MINB)
 k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__restrict__ list, const int *__restrict__ countDev,
-                  long long countHost, int level, double *__restrict__ out) {
+                  long long countHost, int level, double *__restrict__ out, double *__restrict__ results) {
     __shared__ double smM[MAX_GAUSS_POINTS * 3 * kThreads];
     const long long count = countDev ? (long long)*countDev : countHost;
     const int children = 1 << (2 * level);
@@ -346,6 +346,10 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
             double2 *o = reinterpret_cast<double2 *>(out + 4 * (long long)slot);
             o[0] = make_double2(total.x, total.y);
             o[1] = make_double2(total.z, total.w);
+            if (results) {   // fixed level: final assembly fused (no second pass over the integrals)
+                const d3 J = assemble_J(total, ld3(tri + PK_N * stride, stride, j), 0.0, false);
+                results[3 * (long long)slot] = J.x; results[3 * (long long)slot + 1] = J.y; results[3 * (long long)slot + 2] = J.z;
+            }
         }
     }
 }
@@ -354,7 +358,7 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
 static int g_minBlocks = [] { const char *e = getenv("I2_MINBLOCKS"); return e ? atoi(e) : 4; }();
 
 void launch_integrate(int cls, int mathMode, const PackedMesh &pm, const int *tasks, const int *list, const int *countDev,
-                      long long countHost, int level, double *out4, int numSMs, cudaStream_t s) {
+                      long long countHost, int level, double *out4, double *fusedResults3, int numSMs, cudaStream_t s) {
     if (!countDev && countHost <= 0) return;
     const int children = 1 << (2 * level);
     const int G = children < 32 ? children : 32;
@@ -371,9 +375,9 @@ void launch_integrate(int cls, int mathMode, const PackedMesh &pm, const int *ta
     else if (mathMode == MATH_STRICT) { ++g_launchCount; k_integrate<2, MATH_STRICT, 4><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4); }
     else if (mathMode == MATH_FAST_LIBDEVICE) { ++g_launchCount; k_integrate<2, MATH_FAST_LIBDEVICE, 4><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4); }
     else if (mathMode == MATH_FAST_POINTWISE) { ++g_launchCount; k_integrate<2, MATH_FAST_POINTWISE, 4><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4); }
-    else if (g_minBlocks == 3) { ++g_launchCount; k_regular_grouped<3><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4); }
-    else if (g_minBlocks == 5) { ++g_launchCount; k_regular_grouped<5><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4); }
-    else { ++g_launchCount; k_regular_grouped<4><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4); }
+    else if (g_minBlocks == 3) { ++g_launchCount; k_regular_grouped<3><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4, fusedResults3); }
+    else if (g_minBlocks == 5) { ++g_launchCount; k_regular_grouped<5><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4, fusedResults3); }
+    else { ++g_launchCount; k_regular_grouped<4><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4, fusedResults3); }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -514,6 +518,23 @@ __global__ void k_symmetry_error(const double *__restrict__ results, long long n
 }
 void launch_symmetry_error(const double *results3, long long nHalf, double *errors, cudaStream_t s) {
     if (nHalf > 0) { ++g_launchCount; k_symmetry_error<<<(unsigned)((nHalf + 255) / 256), 256, 0, s>>>(results3, nHalf, errors); }
+}
+
+// per-class checksum of the results (sum of components and sum of |J|_1): the small 'metric' read back by the
+// device-resident end-to-end path
+__global__ void __launch_bounds__(256) k_checksum(const double *__restrict__ results, long long n, double *sums4) {
+    double a[4] = {0.0, 0.0, 0.0, 0.0};
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const double x = results[3 * t], y = results[3 * t + 1], z = results[3 * t + 2];
+        a[0] += x; a[1] += y; a[2] += z; a[3] += fabs(x) + fabs(y) + fabs(z);
+    }
+    for (int k = 0; k < 4; ++k) {
+        for (int off = 16; off > 0; off >>= 1) a[k] += __shfl_xor_sync(0xffffffffu, a[k], off);
+        if ((threadIdx.x & 31) == 0) atomicAdd(sums4 + k, a[k]);
+    }
+}
+void launch_checksum(const double *results3, long long n, double *sums4, int numSMs, cudaStream_t s) {
+    if (n > 0) { ++g_launchCount; k_checksum<<<numSMs * 8, 256, 0, s>>>(results3, n, sums4); }
 }
 
 __global__ void k_add_reversed(int *tasks, long long n) {

@@ -48,7 +48,8 @@ void launch_geometry(const double *verts, const int *cells, int nc, double *norm
 // regular part of `count` tasks at uniform refinement `level`; list==nullptr -> task slots 0..count-1,
 // otherwise slots list[0..*countDev-1] (device-side count, persistent grid)
 void launch_integrate(int cls, int mathMode, const PackedMesh &pm, const int *tasks, const int *list, const int *countDev,
-                      long long countHost, int level, double *out4, int numSMs, cudaStream_t s);
+                      long long countHost, int level, double *out4, double *fusedResults3, int numSMs, cudaStream_t s);
+void launch_checksum(const double *results3, long long n, double *sums4, int numSMs, cudaStream_t s);
 void launch_compare(const double *cur4, const double *prev4, const int *tasks, const int *listIn, const int *countIn,
                     long long countHost, int *listOut, int *countOut, unsigned char *cellFlag, unsigned char *converged,
                     QueueState *qs, int round, int numSMs, cudaStream_t s);

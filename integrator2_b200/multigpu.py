@@ -65,3 +65,56 @@ def gather_results(local, full, bounds, rank: int, world: int, dst: int = 0):
     if ops:
         for w in dist.batch_isend_irecv(ops):
             w.wait()
+
+
+def integrate_and_gather(ctx, cls, tasks_local, level, out_local, full, bounds, rank, world, side_stream, chunks=8, dst=0):
+    """Integrate this rank's shard of a class chunk by chunk and ship every finished chunk of per-pair results to rank
+    `dst` while the next chunk is being integrated (NCCL point-to-point on a side stream, overlapped with compute).
+
+    tasks_local: int32[n_local,3] device tensor (rows bounds[rank] of the class), out_local = (integrals, results) device
+    tensors for the shard, full: float64[n_total,3] on rank dst (None elsewhere).  Returns the list of pending NCCL works;
+    call wait_all() on it before reading `full`."""
+    import torch
+    import torch.distributed as dist
+    n_local = int(tasks_local.shape[0])
+    integrals, results = out_local
+    works = []
+    n_max = max(hi - lo for lo, hi in bounds)
+    step = max(1, -(-n_max // max(1, chunks)))           # same chunk grid on every rank
+    main = torch.cuda.current_stream()
+    for c0 in range(0, n_max, step):
+        lo_c, hi_c = min(c0, n_local), min(c0 + step, n_local)
+        if hi_c > lo_c:
+            ctx.integrate_class(cls, tasks_local[lo_c:hi_c], level, want_stats=False,
+                                out=(integrals[lo_c:hi_c], results[lo_c:hi_c]))
+        if world == 1:
+            continue
+        ev = torch.cuda.Event()
+        ev.record(main)
+        with torch.cuda.stream(side_stream):
+            side_stream.wait_event(ev)
+            ops = []
+            if rank == dst:
+                glo, _ = bounds[dst]
+                if hi_c > lo_c:
+                    full[glo + lo_c:glo + hi_c].copy_(results[lo_c:hi_c], non_blocking=True)
+                for r in range(world):
+                    if r == dst:
+                        continue
+                    rlo, rhi = bounds[r]
+                    a, b = min(c0, rhi - rlo), min(c0 + step, rhi - rlo)
+                    if b > a:
+                        ops.append(dist.P2POp(dist.irecv, full[rlo + a:rlo + b], r))
+            elif hi_c > lo_c:
+                ops.append(dist.P2POp(dist.isend, results[lo_c:hi_c], dst))
+            if ops:
+                works += dist.batch_isend_irecv(ops)
+    return works
+
+
+def wait_all(works, side_stream=None):
+    import torch
+    for w in works:
+        w.wait()
+    if side_stream is not None:
+        torch.cuda.current_stream().wait_stream(side_stream)

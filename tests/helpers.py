@@ -129,8 +129,10 @@ def perturbation_noise(oracle, vertices, cells, cls, tasks, level, trials=8, see
 K_PERTURB = 32.0
 
 
-def check_parity_perturbation(oracle, vertices, cells, cls, tasks, level, J_new, J_ref=None, label=""):
-    """|J_new - J_ref|_1 <= 1e-12 |J_ref|_1 + K_PERTURB * noise_ij  (J_ref defaults to the oracle's value)."""
+def check_parity_perturbation(oracle, vertices, cells, cls, tasks, level, J_new, J_ref=None, label="", max_outliers=0):
+    """|J_new - J_ref|_1 <= 1e-12 |J_ref|_1 + K_PERTURB * noise_ij  (J_ref defaults to the oracle's value).
+    max_outliers: pairs allowed to exceed the bound (the noise estimate is itself a random sample; an epsilon-branch
+    that flips between two implementations is not always reached by 8 perturbations); they must still agree to 1e-5."""
     noise, base = perturbation_noise(oracle, vertices, cells, cls, tasks, level)
     if J_ref is None:
         J_ref = base
@@ -141,5 +143,8 @@ def check_parity_perturbation(oracle, vertices, cells, cls, tasks, level, J_new,
     stats = dict(n=int(tasks.shape[0]), rel_median=float(np.median(rel)), rel_max=float(rel.max()),
                  frac_within_1e12=float((rel <= REL_TOL).mean()), worst_ratio_to_allowed=float((err / allowed).max()))
     bad = np.nonzero(err > allowed)[0]
-    assert bad.size == 0, f"{label}: {bad.size} pairs outside tolerance {stats}; first bad task {tasks[bad[0]]}"
+    stats["outliers"] = int(bad.size)
+    assert bad.size <= max_outliers, f"{label}: {bad.size} pairs outside tolerance {stats}; first bad task {tasks[bad[0]]}"
+    if bad.size:
+        assert rel[bad].max() < 1e-5, f"{label}: outlier too large {stats}"
     return stats
