@@ -55,6 +55,8 @@ struct i2_context {
     double *hErrors[3] = {nullptr, nullptr, nullptr};
     unsigned char *hRefinements[3] = {nullptr, nullptr, nullptr};
     long long hCount[3] = {0, 0, 0};
+    size_t capVerts = 0, capCells = 0, capNormals = 0, capMeasures = 0, capTasks[3] = {0, 0, 0}, capIntegrals[3] = {0, 0, 0},
+           capResults[3] = {0, 0, 0}, capRefinements[3] = {0, 0, 0}, capErrors[3] = {0, 0, 0};
     cudaEvent_t chunkDone[2] = {nullptr, nullptr};
     bool profiling = false;
     cudaEvent_t prof[3] = {nullptr, nullptr, nullptr};
@@ -75,9 +77,13 @@ int ensure(T **p, size_t *cap, size_t need) {
 }
 
 void freeHostState(i2_context *c) {
-    auto fr = [](auto *&p) { if (p) cudaFree(p); p = nullptr; };
-    fr(c->hVerts); fr(c->hNormals); fr(c->hMeasures); fr(c->hCells);
-    for (int k = 0; k < 3; ++k) { fr(c->hTasks[k]); fr(c->hIntegrals[k]); fr(c->hResults[k]); fr(c->hErrors[k]); fr(c->hRefinements[k]); c->hCount[k] = 0; }
+    auto fr = [](auto *&p, size_t &cap) { if (p) cudaFree(p); p = nullptr; cap = 0; };
+    fr(c->hVerts, c->capVerts); fr(c->hNormals, c->capNormals); fr(c->hMeasures, c->capMeasures); fr(c->hCells, c->capCells);
+    for (int k = 0; k < 3; ++k) {
+        fr(c->hTasks[k], c->capTasks[k]); fr(c->hIntegrals[k], c->capIntegrals[k]); fr(c->hResults[k], c->capResults[k]);
+        fr(c->hErrors[k], c->capErrors[k]); fr(c->hRefinements[k], c->capRefinements[k]);
+        c->hCount[k] = 0;
+    }
 }
 
 PackedMesh packed(const i2_context *c) {
@@ -122,6 +128,9 @@ int i2_create(i2_context **out, int device) {
     if (e != cudaSuccess) { delete c; return (int)e; }
     for (int k = 0; k < 2; ++k) cudaEventCreateWithFlags(&c->chunkDone[k], cudaEventDisableTiming);
     e = cudaMalloc((void **)&c->qs, sizeof(QueueState));
+    if (e != cudaSuccess) { delete c; return (int)e; }
+    e = upload_math_tables(c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) { delete c; return (int)e; }
     *out = c;
     return 0;
@@ -343,14 +352,15 @@ int i2_host_prepare(i2_context *c, const double *hv, int nv, const int *hc, int 
     if (!c || !hv || !hc || nv <= 0 || nc <= 0 || !taskCounts) return I2_E_BADARG;
     I2_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
-    freeHostState(c);
-    I2_CUDA(cudaMalloc((void **)&c->hVerts, sizeof(double) * 3 * nv));
-    I2_CUDA(cudaMalloc((void **)&c->hCells, sizeof(int) * 3 * nc));
-    I2_CUDA(cudaMalloc((void **)&c->hNormals, sizeof(double) * 3 * nc));
-    I2_CUDA(cudaMalloc((void **)&c->hMeasures, sizeof(double) * nc));
+    // device buffers are kept between calls and only grow (cudaMalloc/cudaFree of multi-GB buffers costs milliseconds)
+    int rc = ensure(&c->hVerts, &c->capVerts, (size_t)3 * nv);
+    if (!rc) rc = ensure(&c->hCells, &c->capCells, (size_t)3 * nc);
+    if (!rc) rc = ensure(&c->hNormals, &c->capNormals, (size_t)3 * nc);
+    if (!rc) rc = ensure(&c->hMeasures, &c->capMeasures, (size_t)nc);
+    if (rc) return rc;
     I2_CUDA(cudaMemcpyAsync(c->hVerts, hv, sizeof(double) * 3 * nv, cudaMemcpyHostToDevice, s));
     I2_CUDA(cudaMemcpyAsync(c->hCells, hc, sizeof(int) * 3 * nc, cudaMemcpyHostToDevice, s));
-    int rc = i2_mesh_geometry(c, c->hVerts, nv, c->hCells, nc, c->hNormals, nullptr, c->hMeasures);
+    rc = i2_mesh_geometry(c, c->hVerts, nv, c->hCells, nc, c->hNormals, nullptr, c->hMeasures);
     if (rc) return rc;
     rc = i2_set_mesh(c, c->hVerts, nv, c->hCells, nc, c->hNormals, c->hMeasures);
     if (rc) return rc;
@@ -361,12 +371,11 @@ int i2_host_prepare(i2_context *c, const double *hv, int nv, const int *hc, int 
         if (2 * pairs[k] > INT_MAX) return I2_E_TOOBIG;
         c->hCount[k] = 2 * pairs[k];
         taskCounts[k] = c->hCount[k];
-        if (c->hCount[k]) {
-            I2_CUDA(cudaMalloc((void **)&c->hTasks[k], sizeof(int) * 3 * c->hCount[k]));
-            I2_CUDA(cudaMalloc((void **)&c->hIntegrals[k], sizeof(double) * 4 * c->hCount[k]));
-            I2_CUDA(cudaMalloc((void **)&c->hResults[k], sizeof(double) * 3 * c->hCount[k]));
-        }
-        I2_CUDA(cudaMalloc((void **)&c->hRefinements[k], nc));
+        rc = ensure(&c->hTasks[k], &c->capTasks[k], (size_t)3 * c->hCount[k]);
+        if (!rc) rc = ensure(&c->hIntegrals[k], &c->capIntegrals[k], (size_t)4 * c->hCount[k]);
+        if (!rc) rc = ensure(&c->hResults[k], &c->capResults[k], (size_t)3 * c->hCount[k]);
+        if (!rc) rc = ensure(&c->hRefinements[k], &c->capRefinements[k], (size_t)nc);
+        if (rc) return rc;
     }
     rc = i2_classify_fill(c, c->hCells, nc, c->hTasks[0], c->hTasks[1], c->hTasks[2]);
     if (rc) return rc;
@@ -435,7 +444,8 @@ int i2_host_run(i2_context *c, int level, int *const hTasks[3], double *const hR
                                         level < 0 ? c->hRefinements[k] : nullptr, nullptr, hStats ? &hStats[k] : nullptr);
             if (rc) return rc;
             if (wantErr) {
-                if (!c->hErrors[k]) I2_CUDA(cudaMalloc((void **)&c->hErrors[k], sizeof(double) * n));
+                rc = ensure(&c->hErrors[k], &c->capErrors[k], (size_t)n);
+                if (rc) return rc;
                 rc = i2_symmetry_error(c, c->hResults[k], n / 2, c->hErrors[k]);
                 if (rc) return rc;
                 I2_CUDA(cudaMemcpyAsync(hErrors[k], c->hErrors[k], sizeof(double) * n, cudaMemcpyDeviceToHost, s));

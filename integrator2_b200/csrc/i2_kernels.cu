@@ -29,6 +29,10 @@ __constant__ int c_ngauss;
 __constant__ int c_groupEnd[MAX_GAUSS_POINTS];   // 1 = last point of a run of equal weights (grouped evaluation)
 __constant__ double c_pow2p;
 
+cudaError_t upload_math_tables(cudaStream_t s) {
+    return cudaMemcpyToSymbolAsync(c_mathTable, h_mathTable, sizeof(double) * I2_MATH_TABLE_SIZE, 0, cudaMemcpyHostToDevice, s);
+}
+
 cudaError_t upload_quadrature(const double *Lxyzw, int n, double pow2p, cudaStream_t s) {
     cudaError_t e = cudaMemcpyToSymbolAsync(c_gauss, Lxyzw, sizeof(double) * 4 * n, 0, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) return e;
@@ -87,6 +91,7 @@ __global__ void k_pack(const double *__restrict__ verts, const int *__restrict__
     st3(PK_NU, nu);
     st3(PK_N, {normals[3 * c], normals[3 * c + 1], normals[3 * c + 2]});
     tri[PK_S * stride + c] = measures[c];
+    st3(PK_L, {norm(C - B), norm(A - C), norm(B - A)});
 }
 
 void launch_geometry(const double *verts, const int *cells, int nc, double *normals, double *centers, double *measures, cudaStream_t s) {
@@ -255,12 +260,16 @@ k_integrate(PackedMesh pm, const int *__restrict__ tasks, const int *__restrict_
 //   * control flow is warp-uniform: the only data-dependent decision (angle-sum overflow of a group) is taken by
 //     __all_sync over the warp.
 // ---------------------------------------------------------------------------------------------------------
-template <int MINB>
+// VAR bit 0: EDGELEN variant of point_terms; bit 1: primitives without the residual correction; bit 2: LEVEL0
+// specialisation (no child loop, no per-level area scaling kept live)
+template <int MINB, int VAR>
 __global__ void __launch_bounds__(kThreads, MINB)
 k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__restrict__ list, const int *__restrict__ countDev,
                   long long countHost, int level, double *__restrict__ out, double *__restrict__ results) {
     __shared__ double smM[MAX_GAUSS_POINTS * 3 * kThreads];
     const long long count = countDev ? (long long)*countDev : countHost;
+    constexpr bool EDGELEN = (VAR & 1) != 0, RESID = (VAR & 2) == 0, LEVEL0 = (VAR & 4) != 0;
+    if (LEVEL0) level = 0;
     const int children = 1 << (2 * level);
     const int G = children < 32 ? children : 32;
     const int perLane = children / G;
@@ -287,6 +296,7 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
         T.A = ld3(tri + PK_A * stride, stride, j); T.B = ld3(tri + PK_B * stride, stride, j); T.C = ld3(tri + PK_C * stride, stride, j);
         T.ta = ld3(tri + PK_TA * stride, stride, j); T.tb = ld3(tri + PK_TB * stride, stride, j); T.tc = ld3(tri + PK_TC * stride, stride, j);
         T.Nu = ld3(tri + PK_NU * stride, stride, j);
+        if (EDGELEN) { const d3 L = ld3(tri + PK_L * stride, stride, j); T.La = L.x; T.Lb = L.y; T.Lc = L.z; }
 
         double s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;
         for (int k = 0; k < perLane; ++k) {
@@ -306,25 +316,25 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
 #pragma unroll 1
             for (int g = 0; g < ng; ++g) {
                 const d3 M = {myM[(3 * g + 0) * kThreads], myM[(3 * g + 1) * kThreads], myM[(3 * g + 2) * kThreads]};
-                const PointTerms t = point_terms(M, T);
+                const PointTerms t = point_terms<EDGELEN>(M, T);
                 pn1 *= t.N1; pd1 *= t.D1; pn2 *= t.N2; pd2 *= t.D2; pn3 *= t.N3; pd3 *= t.D3;
                 const double nr = fma(zr, t.den, -(zi * t.num)), ni = fma(zr, t.num, zi * t.den);
                 zr = nr; zi = ni;
                 safe = safe && (fabs(t.num) <= 0.5 * t.den);
                 if (c_groupEnd[g]) {
                     const double w = c_gauss[4 * g + 3];
-                    a1 = fma(w, log_ratio(pn1, pd1), a1);
-                    a2 = fma(w, log_ratio(pn2, pd2), a2);
-                    a3 = fma(w, log_ratio(pn3, pd3), a3);
+                    a1 = fma(w, log_ratio<RESID>(pn1, pd1), a1);
+                    a2 = fma(w, log_ratio<RESID>(pn2, pd2), a2);
+                    a3 = fma(w, log_ratio<RESID>(pn3, pd3), a3);
                     double th;
                     if (__all_sync(0xffffffffu, safe)) {
-                        th = atan2_fast(zi, zr);
+                        th = atan2_fast<RESID>(zi, zr);
                     } else {  // some lane of the warp sees triangle j under a large solid angle: add the angles one by one
                         th = 0.0;
                         for (int h = gStart; h <= g; ++h) {
                             const d3 Mh = {myM[(3 * h + 0) * kThreads], myM[(3 * h + 1) * kThreads], myM[(3 * h + 2) * kThreads]};
-                            const PointTerms u = point_terms(Mh, T);
-                            th += atan2_fast(u.num, u.den);
+                            const PointTerms u = point_terms<EDGELEN>(Mh, T);
+                            th += atan2_fast<RESID>(u.num, u.den);
                         }
                     }
                     a4 = fma(w, th + th, a4);
@@ -333,7 +343,8 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
                     gStart = g + 1;
                 }
             }
-            s1 = fma(Si, a1, s1); s2 = fma(Si, a2, s2); s3 = fma(Si, a3, s3); s4 = fma(Si, a4, s4);
+            if (LEVEL0) { s1 = Si * a1; s2 = Si * a2; s3 = Si * a3; s4 = Si * a4; }
+            else { s1 = fma(Si, a1, s1); s2 = fma(Si, a2, s2); s3 = fma(Si, a3, s3); s4 = fma(Si, a4, s4); }
         }
         d4 total = vec4(s1 * T.tc + s2 * T.ta + s3 * T.tb, s4);
         for (int off = G >> 1; off > 0; off >>= 1) {
@@ -356,6 +367,7 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
 
 // tuning knob (env I2_MINBLOCKS = 3|4|5): resident CTAs per SM the regular kernel is compiled for
 static int g_minBlocks = [] { const char *e = getenv("I2_MINBLOCKS"); return e ? atoi(e) : 4; }();
+static int g_variant = [] { const char *e = getenv("I2_VARIANT"); return e ? atoi(e) : 3; }();
 
 void launch_integrate(int cls, int mathMode, const PackedMesh &pm, const int *tasks, const int *list, const int *countDev,
                       long long countHost, int level, double *out4, double *fusedResults3, int numSMs, cudaStream_t s) {
@@ -375,9 +387,25 @@ void launch_integrate(int cls, int mathMode, const PackedMesh &pm, const int *ta
     else if (mathMode == MATH_STRICT) { ++g_launchCount; k_integrate<2, MATH_STRICT, 4><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4); }
     else if (mathMode == MATH_FAST_LIBDEVICE) { ++g_launchCount; k_integrate<2, MATH_FAST_LIBDEVICE, 4><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4); }
     else if (mathMode == MATH_FAST_POINTWISE) { ++g_launchCount; k_integrate<2, MATH_FAST_POINTWISE, 4><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4); }
-    else if (g_minBlocks == 3) { ++g_launchCount; k_regular_grouped<3><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4, fusedResults3); }
-    else if (g_minBlocks == 5) { ++g_launchCount; k_regular_grouped<5><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4, fusedResults3); }
-    else { ++g_launchCount; k_regular_grouped<4><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4, fusedResults3); }
+    else {
+        // tuning knobs: I2_MINBLOCKS (3|4|5 resident CTAs/SM), I2_VARIANT (bit0 edge-length trick, bit1 no residual correction);
+        // the LEVEL0 specialisation (bit 2) is chosen automatically
+        const int var = (g_variant & 3) | (level == 0 ? 4 : 0);
+        ++g_launchCount;
+#define I2_LAUNCH_GROUPED(MB, V) k_regular_grouped<MB, V><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4, fusedResults3)
+#define I2_PICK_VAR(MB)                                                                                              \
+        switch (var) {                                                                                           \
+        case 0: I2_LAUNCH_GROUPED(MB, 0); break; case 1: I2_LAUNCH_GROUPED(MB, 1); break;                       \
+        case 2: I2_LAUNCH_GROUPED(MB, 2); break; case 3: I2_LAUNCH_GROUPED(MB, 3); break;                       \
+        case 4: I2_LAUNCH_GROUPED(MB, 4); break; case 5: I2_LAUNCH_GROUPED(MB, 5); break;                       \
+        case 6: I2_LAUNCH_GROUPED(MB, 6); break; default: I2_LAUNCH_GROUPED(MB, 7); break;                      \
+        }
+        if (g_minBlocks == 3) { I2_PICK_VAR(3) }
+        else if (g_minBlocks == 5) { I2_PICK_VAR(5) }
+        else { I2_PICK_VAR(4) }
+#undef I2_PICK_VAR
+#undef I2_LAUNCH_GROUPED
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------

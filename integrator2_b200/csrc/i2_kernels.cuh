@@ -18,7 +18,8 @@ enum PackComp {
     PK_NU = 18,  // 18..20 (B-A)x(C-A), not normalised
     PK_N = 21,   // 21..23 unit normal n_j (as Mesh3D computes it)
     PK_S = 24,   // 24     area S
-    PK_COUNT = 25
+    PK_L = 25,   // 25..27 edge lengths |C-B|, |A-C|, |B-A|
+    PK_COUNT = 28
 };
 
 struct PackedMesh {
@@ -66,6 +67,7 @@ void launch_classify_fill(const int *cells, int nc, const unsigned long long *ro
 void launch_split_uniform(const double *vin, int nvIn, const int *cin, int ncIn, const double *min, double *vout, int *cout,
                           double *mout, cudaStream_t s);
 void launch_selftest_math(int op, const double *a, const double *b, long long n, double *out, cudaStream_t s);
+cudaError_t upload_math_tables(cudaStream_t s);
 cudaError_t upload_quadrature(const double *Lxyzw, int n, double pow2p, cudaStream_t s);
 // FP64-pipe / MUFU peak micro-benchmarks: returns elapsed ms for `iters` dependent-chain iterations
 void launch_peak_dfma(double *sink, int iters, int blocks, cudaStream_t s);

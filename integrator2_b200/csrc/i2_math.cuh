@@ -18,6 +18,27 @@
 
 namespace i2 {
 
+// Polynomial coefficients live in constant memory on the device, uploaded at context creation (i2_create): a DFMA
+// then takes them as c[bank][offset] operands, which costs no issue slot.  As literals each double needs two UMOVs into
+// uniform registers (~250 issue slots per pair); initialised __constant__ arrays get folded back into literals.
+#define I2_MATH_TABLE_VALUES                                                                                                   \
+    {2.0 / 3.0, 2.0 / 5.0, 2.0 / 7.0, 2.0 / 9.0, 2.0 / 11.0, 2.0 / 13.0, 2.0 / 15.0, 2.0 / 17.0, 2.0 / 19.0, 2.0 / 21.0,       /* atanh series  [0..9]  */ \
+     -1.0 / 3.0, 1.0 / 5.0, -1.0 / 7.0, 1.0 / 9.0, -1.0 / 11.0, 1.0 / 13.0, -1.0 / 15.0, 1.0 / 17.0, -1.0 / 19.0,              /* atan series  [10..18] */ \
+     6.93147180369123816490e-01, 1.90821492927058770002e-10, 1.57079632679489655800e+00, 3.14159265358979311600e+00}          /* ln2 hi, ln2 lo, pi/2, pi [19..22] */
+constexpr int I2_MATH_TABLE_SIZE = 23;
+#if defined(__CUDACC__)
+__constant__ double c_mathTable[I2_MATH_TABLE_SIZE];
+static const double h_mathTable[I2_MATH_TABLE_SIZE] = I2_MATH_TABLE_VALUES;
+#if defined(__CUDA_ARCH__)
+#define I2_K(idx) c_mathTable[idx]
+#else
+#define I2_K(idx) h_mathTable[idx]
+#endif
+#else
+static const double h_mathTable[I2_MATH_TABLE_SIZE] = I2_MATH_TABLE_VALUES;
+#define I2_K(idx) h_mathTable[idx]
+#endif
+
 I2_HD int hi_word(double x) {
 #if defined(__CUDA_ARCH__)
     return __double2hiint(x);
@@ -77,6 +98,7 @@ I2_HD double fast_rcp(double x) {
 // needed so that mN/mD lies in about [1/sqrt2, sqrt2] (decided on the FP32 pipe, the exact cut does not matter);
 // then ln(mN/mD) = 2 atanh(f), f = (mN-mD)/(mN+mD), |f| <= 0.1716: odd series in f up to f^21.
 // mN - mD is exact (Sterbenz), so the result keeps full RELATIVE accuracy when N/D -> 1, which log(N/D) does not.
+template <bool RESID = true>
 I2_HD double log_ratio(double N, double D) {
     const int hN = hi_word(N), hD = hi_word(D);
     int e = (hN >> 20) - (hD >> 20);
@@ -96,25 +118,26 @@ I2_HD double log_ratio(double N, double D) {
     const double s = mN + mD, d = mN - mD;
     const double r = fast_rcp(s);
     double f = d * r;
-    f = fma(fma(-f, s, d), r, f);    // residual correction: f is now (mN-mD)/(mN+mD) to ~0.5 ulp
+    if (RESID) f = fma(fma(-f, s, d), r, f);    // residual correction: f is now (mN-mD)/(mN+mD) to ~0.5 ulp
     const double z = f * f;
-    double p = 2.0 / 21.0;
-    p = fma(p, z, 2.0 / 19.0);
-    p = fma(p, z, 2.0 / 17.0);
-    p = fma(p, z, 2.0 / 15.0);
-    p = fma(p, z, 2.0 / 13.0);
-    p = fma(p, z, 2.0 / 11.0);
-    p = fma(p, z, 2.0 / 9.0);
-    p = fma(p, z, 2.0 / 7.0);
-    p = fma(p, z, 2.0 / 5.0);
-    p = fma(p, z, 2.0 / 3.0);
+    double p = I2_K(9);
+    p = fma(p, z, I2_K(8));
+    p = fma(p, z, I2_K(7));
+    p = fma(p, z, I2_K(6));
+    p = fma(p, z, I2_K(5));
+    p = fma(p, z, I2_K(4));
+    p = fma(p, z, I2_K(3));
+    p = fma(p, z, I2_K(2));
+    p = fma(p, z, I2_K(1));
+    p = fma(p, z, I2_K(0));
     const double lg = fma(f * z, p, f + f);                 // 2 atanh(f)
     const double ed = (double)e;
-    return fma(ed, 6.93147180369123816490e-01, fma(ed, 1.90821492927058770002e-10, lg));   // ln2 split hi/lo
+    return fma(ed, I2_K(19), fma(ed, I2_K(20), lg));   // ln2 split hi/lo
 }
 
 // atan2(y, x) for finite arguments, not both zero.  t = min/max in [0,1]; c = nearest of {0, 1/4, 1/2, 3/4, 1};
 // atan t = atan c + atan((t-c)/(1+tc)) = atan c + atan((mn - c mx)/(mx + c mn)), |arg| <= 0.1244: odd series to ^19.
+template <bool RESID = true>
 I2_HD double atan2_fast(double y, double x) {
     const double ax = fabs(x), ay = fabs(y);
     const double mx = fmax(ax, ay), mn = fmin(ax, ay);
@@ -138,20 +161,20 @@ I2_HD double atan2_fast(double y, double x) {
     const double num = fma(-c, mx, mn), den = fma(c, mn, mx);
     const double r = fast_rcp(den);
     double t = num * r;
-    t = fma(fma(-t, den, num), r, t);
+    if (RESID) t = fma(fma(-t, den, num), r, t);
     const double z = t * t;
-    double p = -1.0 / 19.0;
-    p = fma(p, z, 1.0 / 17.0);
-    p = fma(p, z, -1.0 / 15.0);
-    p = fma(p, z, 1.0 / 13.0);
-    p = fma(p, z, -1.0 / 11.0);
-    p = fma(p, z, 1.0 / 9.0);
-    p = fma(p, z, -1.0 / 7.0);
-    p = fma(p, z, 1.0 / 5.0);
-    p = fma(p, z, -1.0 / 3.0);
+    double p = I2_K(18);
+    p = fma(p, z, I2_K(17));
+    p = fma(p, z, I2_K(16));
+    p = fma(p, z, I2_K(15));
+    p = fma(p, z, I2_K(14));
+    p = fma(p, z, I2_K(13));
+    p = fma(p, z, I2_K(12));
+    p = fma(p, z, I2_K(11));
+    p = fma(p, z, I2_K(10));
     double a = at + fma(t * z, p, t);                           // atan(mn/mx) in [0, pi/4]
-    a = ay > ax ? 1.57079632679489655800e+00 - a : a;           // pi/2 - a
-    a = x < 0.0 ? 3.14159265358979311600e+00 - a : a;           // pi - a
+    a = ay > ax ? I2_K(21) - a : a;           // pi/2 - a
+    a = x < 0.0 ? I2_K(22) - a : a;           // pi - a
     return copysign(a, y);
 }
 

@@ -28,6 +28,7 @@ struct TriJ {
     d3 A, B, C;        // vertices in the mesh's own order
     d3 ta, tb, tc;     // unit tangents (C-B)^, (A-C)^, (B-A)^
     d3 Nu;             // (B-A) x (C-A), not normalised:  (M-A)·Nu = (M-A)x(M-B)·(M-C)
+    double La, Lb, Lc; // edge lengths |C-B|, |A-C|, |B-A| (only used by the EDGELEN variant of point_terms)
 };
 
 // ---- regular pairs: reference operation order ("strict") ------------------------------------------
@@ -103,12 +104,15 @@ struct PointTerms {
     double num, den;                 // Theta_g = 2 atan2(num, den)
 };
 
+// EDGELEN: d_b·t_c = d_a·t_c - |AB| etc. (d_b = d_a - AB): three dot products become three subtractions.
+template <bool EDGELEN = false>
 I2_HD PointTerms point_terms(d3 M, const TriJ &T) {
     const d3 da = M - T.A, db = M - T.B, dc = M - T.C;
     const double la = fast_sqrt(norm2(da)), lb = fast_sqrt(norm2(db)), lc = fast_sqrt(norm2(dc));
-    const double n1 = la + dot(da, T.tc), q1 = lb + dot(db, T.tc);
-    const double n2 = lb + dot(db, T.ta), q2 = lc + dot(dc, T.ta);
-    const double n3 = lc + dot(dc, T.tb), q3 = la + dot(da, T.tb);
+    const double pa = dot(da, T.tc), pb = dot(db, T.ta), pc = dot(dc, T.tb);
+    const double n1 = la + pa, q1 = lb + (EDGELEN ? pa - T.Lc : dot(db, T.tc));
+    const double n2 = lb + pb, q2 = lc + (EDGELEN ? pb - T.La : dot(dc, T.ta));
+    const double n3 = lc + pc, q3 = la + (EDGELEN ? pc - T.Lb : dot(da, T.tb));
     const bool f1 = fabs(q1) < 0.5 * EPS_PSI_THETA2 * lb;
     const bool f2 = fabs(q2) < 0.5 * EPS_PSI_THETA2 * lc;
     const bool f3 = fabs(q3) < 0.5 * EPS_PSI_THETA2 * la;

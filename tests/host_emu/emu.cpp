@@ -18,6 +18,7 @@ static TriJ make_tri(const double *v, const int *cells, int j) {
     T.C = {v[3 * t[2]], v[3 * t[2] + 1], v[3 * t[2] + 2]};
     T.ta = unit(T.C - T.B); T.tb = unit(T.A - T.C); T.tc = unit(T.B - T.A);
     T.Nu = cross(T.B - T.A, T.C - T.A);
+    T.La = norm(T.C - T.B); T.Lb = norm(T.A - T.C); T.Lc = norm(T.B - T.A);
     return T;
 }
 
@@ -55,13 +56,14 @@ void emu_regular(const double *v, const int *cells, const double *measures, cons
                 acc.x = fma(g_w[g], f.x, acc.x); acc.y = fma(g_w[g], f.y, acc.y); acc.z = fma(g_w[g], f.z, acc.z); acc.w = fma(g_w[g], f.w, acc.w);
             }
             res = measures[i] * acc;
-        } else if (mode == 3) {
+        } else if ((mode & 7) == 3) {
+            const int var = mode >> 3;   // bit0 EDGELEN, bit1 no residual correction
             // grouped evaluation, same sequence as k_regular_grouped (per-thread safety flag instead of the warp vote)
             double a1 = 0, a2 = 0, a3 = 0, a4 = 0, pn1 = 1, pd1 = 1, pn2 = 1, pd2 = 1, pn3 = 1, pd3 = 1, zr = 1, zi = 0;
             bool safe = true;
             int gStart = 0;
             for (int g = 0; g < g_n; ++g) {
-                const PointTerms t = point_terms(gp(g, I.A, I.B, I.C), T);
+                const PointTerms t = (var & 1) ? point_terms<true>(gp(g, I.A, I.B, I.C), T) : point_terms<false>(gp(g, I.A, I.B, I.C), T);
                 pn1 *= t.N1; pd1 *= t.D1; pn2 *= t.N2; pd2 *= t.D2; pn3 *= t.N3; pd3 *= t.D3;
                 const double nr = fma(zr, t.den, -(zi * t.num)), ni = fma(zr, t.num, zi * t.den);
                 zr = nr; zi = ni;
@@ -69,9 +71,10 @@ void emu_regular(const double *v, const int *cells, const double *measures, cons
                 const bool last = (g == g_n - 1) || (g_w[g + 1] != g_w[g]) || (g - gStart == 5);
                 if (last) {
                     const double w = g_w[g];
-                    a1 = fma(w, log_ratio(pn1, pd1), a1); a2 = fma(w, log_ratio(pn2, pd2), a2); a3 = fma(w, log_ratio(pn3, pd3), a3);
+                    if (var & 2) { a1 = fma(w, log_ratio<false>(pn1, pd1), a1); a2 = fma(w, log_ratio<false>(pn2, pd2), a2); a3 = fma(w, log_ratio<false>(pn3, pd3), a3); }
+                    else { a1 = fma(w, log_ratio<true>(pn1, pd1), a1); a2 = fma(w, log_ratio<true>(pn2, pd2), a2); a3 = fma(w, log_ratio<true>(pn3, pd3), a3); }
                     double th;
-                    if (safe) th = atan2_fast(zi, zr);
+                    if (safe) th = (var & 2) ? atan2_fast<false>(zi, zr) : atan2_fast<true>(zi, zr);
                     else { th = 0; for (int h = gStart; h <= g; ++h) { const PointTerms u = point_terms(gp(h, I.A, I.B, I.C), T); th += atan2_fast(u.num, u.den); } }
                     a4 = fma(w, th + th, a4);
                     pn1 = pd1 = pn2 = pd2 = pn3 = pd3 = zr = 1.0; zi = 0.0; safe = true; gStart = g + 1;
