@@ -104,6 +104,14 @@ int i2_integrate_class(i2_context *ctx, int cls, const int *d_tasks, long long n
                        double *d_integrals, double *d_results, unsigned char *d_refinements,
                        unsigned char *d_converged, i2_stats *h_stats);
 
+/* ---- list-free regular class ("next" row f1 of SURVEY.md §8: implicit tiled enumeration, no N^2 list) ---------------
+ * d_out[i - row_lo] = sum over all triangles j that share no vertex with i (j != i) of w_j * J(K_i, K_j), level 0,
+ * for rows row_lo <= i < row_hi; d_weights = double[nc] or NULL (all ones); d_out = Point3[row_hi - row_lo].
+ * The pairs are enumerated on the fly (the vertex-id comparison of src/Mesh3d.cu:115-122 is the classification), no
+ * task list and no per-pair result is stored: this is the entry point for meshes beyond the reference's int32 / N^2
+ * limits (N > 46 340 triangles) and the unit that shards by rows across GPUs.                                    */
+int i2_apply_regular(i2_context *ctx, int row_lo, int row_hi, const double *d_weights, double *d_out);
+
 /* delta = |J_ij + J_ji|_1 / max(|J_ij|_1, |J_ji|_1) for slots t and n_half+t: replaces
  * kCalculateIntegrationError (src/evaluators/evaluator3d.cu:45-57)                                         */
 int i2_symmetry_error(i2_context *ctx, const double *d_results, long long n_half, double *d_errors);

@@ -48,7 +48,7 @@ EXPORTS = [
     "i2_create", "i2_destroy", "i2_set_stream", "i2_synchronize", "i2_set_math_mode", "i2_error_string",
     "i2_set_quadrature", "i2_mesh_geometry", "i2_set_mesh", "i2_classify_count", "i2_classify_fill",
     "i2_add_reversed_pairs", "i2_integrate_class", "i2_symmetry_error", "i2_host_prepare", "i2_host_run",
-    "i2_host_device_views", "i2_host_checksums", "i2_peak_rates", "i2_refine_mesh_once", "i2_launch_count", "i2_set_profiling", "i2_profile_last", "i2_selftest_math",
+    "i2_host_device_views", "i2_host_checksums", "i2_peak_rates", "i2_refine_mesh_once", "i2_launch_count", "i2_set_profiling", "i2_profile_last", "i2_selftest_math", "i2_apply_regular",
 ]
 
 _lib = None
@@ -88,6 +88,7 @@ def load_library():
     L.i2_host_checksums.argtypes = [vp, C.POINTER(C.c_double)]
     L.i2_host_device_views.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.i2_refine_mesh_once.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, vp]
+    L.i2_apply_regular.argtypes = [vp, i32, i32, vp, vp]
     L.i2_selftest_math.argtypes = [vp, i32, vp, vp, ll, vp]
     L.i2_launch_count.argtypes = [C.POINTER(ll)]
     L.i2_set_profiling.argtypes = [vp, i32]
@@ -217,6 +218,14 @@ class Context:
                                          C.byref(st) if want_stats else None))
         return dict(integrals=integrals, results=results, refinements=refinements, converged=conv,
                     stats=st.as_dict() if want_stats else None)
+
+    def apply_regular(self, row_lo, row_hi, weights=None, out=None):
+        """out[i-row_lo] = sum_{j not sharing a vertex with i} w_j J(K_i,K_j) without any task list (device tensors)."""
+        torch = self.torch
+        if out is None:
+            out = torch.empty((row_hi - row_lo, 3), dtype=torch.float64, device=f"cuda:{self.device}")
+        _check(self.L.i2_apply_regular(self.h, int(row_lo), int(row_hi), _ptr(weights), _ptr(out)))
+        return out
 
     def symmetry_error(self, results):
         torch = self.torch

@@ -42,6 +42,10 @@ struct i2_context {
     size_t cellFlagCap = 0;
     QueueState *qs = nullptr;
 
+    // matrix-free path scratch (per-chunk partial row sums)
+    double *partial = nullptr;
+    size_t partialCap = 0;
+
     // classification scratch
     unsigned long long *rowCounts = nullptr;
     size_t rowCap = 0;
@@ -148,6 +152,7 @@ int i2_destroy(i2_context *c) {
     if (c->qs) cudaFree(c->qs);
     for (int k = 0; k < 3; ++k) if (c->prof[k]) cudaEventDestroy(c->prof[k]);
     if (c->rowCounts) cudaFree(c->rowCounts);
+    if (c->partial) cudaFree(c->partial);
     if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
     if (c->copyStream) cudaStreamDestroy(c->copyStream);
     delete c;
@@ -334,6 +339,28 @@ int i2_integrate_class(i2_context *c, int cls, const int *tasks, long long n, in
             before = h.count[m];
         }
     }
+    return 0;
+}
+
+int i2_apply_regular(i2_context *c, int rowLo, int rowHi, const double *weights, double *out) {
+    if (!c || rowLo < 0 || rowHi < rowLo) return I2_E_BADARG;
+    if (!c->tri) return I2_E_NOMESH;
+    if (!c->haveQuad) return I2_E_NOQUAD;
+    if (rowHi > c->nc) return I2_E_BADARG;
+    if (rowHi == rowLo) return 0;
+    if (!out) return I2_E_BADARG;
+    I2_CUDA(cudaSetDevice(c->device));
+    const int rows = rowHi - rowLo;
+    // enough CTAs for a few waves of 4 CTAs/SM: split the columns when there are few row blocks
+    const int rowBlocks = (rows + kThreads - 1) / kThreads;
+    int chunks = (c->numSMs * 4 * 2 + rowBlocks - 1) / rowBlocks;
+    if (chunks < 1) chunks = 1;
+    const int maxChunks = (c->nc + 255) / 256;
+    if (chunks > maxChunks) chunks = maxChunks;
+    int rc = ensure(&c->partial, &c->partialCap, (size_t)chunks * rows * 3);
+    if (rc) return rc;
+    launch_apply_regular(packed(c), rowLo, rowHi, 0, c->nc, chunks, weights, c->partial, out, c->stream);
+    I2_CUDA(cudaGetLastError());
     return 0;
 }
 

@@ -250,6 +250,47 @@ k_integrate(PackedMesh pm, const int *__restrict__ tasks, const int *__restrict_
     }
 }
 
+// Grouped evaluation of one (child) control panel against triangle T: on return a1..a3 = sum_g w_g ln(N/D) per edge,
+// a4 = sum_g w_g Theta_g.  myM points at this thread's staged Gauss points ([point][component], stride kThreads).
+// Must be called by all 32 lanes of a warp (one __all_sync per group of equal weights).
+template <bool EDGELEN, bool RESID>
+static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, const TriJ &T, double &a1, double &a2, double &a3, double &a4) {
+    a1 = 0.0; a2 = 0.0; a3 = 0.0; a4 = 0.0;
+    double pn1 = 1.0, pd1 = 1.0, pn2 = 1.0, pd2 = 1.0, pn3 = 1.0, pd3 = 1.0, zr = 1.0, zi = 0.0;
+    bool safe = true;
+    int gStart = 0;
+#pragma unroll 1
+    for (int g = 0; g < ng; ++g) {
+        const d3 M = {myM[(3 * g + 0) * kThreads], myM[(3 * g + 1) * kThreads], myM[(3 * g + 2) * kThreads]};
+        const PointTerms t = point_terms<EDGELEN>(M, T);
+        pn1 *= t.N1; pd1 *= t.D1; pn2 *= t.N2; pd2 *= t.D2; pn3 *= t.N3; pd3 *= t.D3;
+        const double nr = fma(zr, t.den, -(zi * t.num)), ni = fma(zr, t.num, zi * t.den);
+        zr = nr; zi = ni;
+        safe = safe && (fabs(t.num) <= 0.5 * t.den);
+        if (c_groupEnd[g]) {
+            const double w = c_gauss[4 * g + 3];
+            a1 = fma(w, log_ratio<RESID>(pn1, pd1), a1);
+            a2 = fma(w, log_ratio<RESID>(pn2, pd2), a2);
+            a3 = fma(w, log_ratio<RESID>(pn3, pd3), a3);
+            double th;
+            if (__all_sync(0xffffffffu, safe)) {
+                th = atan2_fast<RESID>(zi, zr);
+            } else {  // some lane of the warp sees triangle j under a large solid angle: add the angles one by one
+                th = 0.0;
+                for (int h = gStart; h <= g; ++h) {
+                    const d3 Mh = {myM[(3 * h + 0) * kThreads], myM[(3 * h + 1) * kThreads], myM[(3 * h + 2) * kThreads]};
+                    const PointTerms u = point_terms<EDGELEN>(Mh, T);
+                    th += atan2_fast<RESID>(u.num, u.den);
+                }
+            }
+            a4 = fma(w, th + th, a4);
+            pn1 = pd1 = pn2 = pd2 = pn3 = pd3 = zr = 1.0; zi = 0.0;
+            safe = true;
+            gStart = g + 1;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // regular (not-neighbour) pairs, the dominant kernel: grouped evaluation (see i2_pair.cuh, point_terms)
 //   * one thread = one task at level 0 (G = min(4^level, 32) lanes per task otherwise);
@@ -309,40 +350,8 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
                     myM[(3 * g + 0) * kThreads] = M.x; myM[(3 * g + 1) * kThreads] = M.y; myM[(3 * g + 2) * kThreads] = M.z;
                 }
             }
-            double a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0;
-            double pn1 = 1.0, pd1 = 1.0, pn2 = 1.0, pd2 = 1.0, pn3 = 1.0, pd3 = 1.0, zr = 1.0, zi = 0.0;
-            bool safe = true;
-            int gStart = 0;
-#pragma unroll 1
-            for (int g = 0; g < ng; ++g) {
-                const d3 M = {myM[(3 * g + 0) * kThreads], myM[(3 * g + 1) * kThreads], myM[(3 * g + 2) * kThreads]};
-                const PointTerms t = point_terms<EDGELEN>(M, T);
-                pn1 *= t.N1; pd1 *= t.D1; pn2 *= t.N2; pd2 *= t.D2; pn3 *= t.N3; pd3 *= t.D3;
-                const double nr = fma(zr, t.den, -(zi * t.num)), ni = fma(zr, t.num, zi * t.den);
-                zr = nr; zi = ni;
-                safe = safe && (fabs(t.num) <= 0.5 * t.den);
-                if (c_groupEnd[g]) {
-                    const double w = c_gauss[4 * g + 3];
-                    a1 = fma(w, log_ratio<RESID>(pn1, pd1), a1);
-                    a2 = fma(w, log_ratio<RESID>(pn2, pd2), a2);
-                    a3 = fma(w, log_ratio<RESID>(pn3, pd3), a3);
-                    double th;
-                    if (__all_sync(0xffffffffu, safe)) {
-                        th = atan2_fast<RESID>(zi, zr);
-                    } else {  // some lane of the warp sees triangle j under a large solid angle: add the angles one by one
-                        th = 0.0;
-                        for (int h = gStart; h <= g; ++h) {
-                            const d3 Mh = {myM[(3 * h + 0) * kThreads], myM[(3 * h + 1) * kThreads], myM[(3 * h + 2) * kThreads]};
-                            const PointTerms u = point_terms<EDGELEN>(Mh, T);
-                            th += atan2_fast<RESID>(u.num, u.den);
-                        }
-                    }
-                    a4 = fma(w, th + th, a4);
-                    pn1 = pd1 = pn2 = pd2 = pn3 = pd3 = zr = 1.0; zi = 0.0;
-                    safe = true;
-                    gStart = g + 1;
-                }
-            }
+            double a1, a2, a3, a4;
+            grouped_eval<EDGELEN, RESID>(myM, ng, T, a1, a2, a3, a4);
             if (LEVEL0) { s1 = Si * a1; s2 = Si * a2; s3 = Si * a3; s4 = Si * a4; }
             else { s1 = fma(Si, a1, s1); s2 = fma(Si, a2, s2); s3 = fma(Si, a3, s3); s4 = fma(Si, a4, s4); }
         }
@@ -363,6 +372,116 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
             }
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// list-free ("matrix-free") regular class: out[i] = sum over all j that share no vertex with i of w_j J(K_i, K_j).
+// No task list and no per-pair result is materialised, so meshes beyond the reference's int32 / N^2-list limits
+// (N > 46 340 triangles) fit: the classification IS the vertex-id comparison done here on the fly.
+//   thread = one control panel i (its Gauss points staged in shared memory, its row sum in registers);
+//   CTA    = 128 rows x one chunk of columns; columns stream through shared memory in tiles of kTileJ
+//            (SoA -> smem coalesced, then every thread reads the same j: broadcast);
+//   grid.y = column chunks; per-chunk partial row sums are written out and reduced in fixed order (deterministic).
+// Pairs that share a vertex (and i == j) are evaluated like the others and discarded by a select, so the warp votes of
+// grouped_eval stay full-mask and the j loop is uniform.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kTileJ = 32;
+constexpr int kTileStride = 29;   // 24 geometry + 3 normal + 1 weight + 1 pad(ids live in a separate int array)
+
+template <int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+k_apply_regular(PackedMesh pm, int rowLo, int rowHi, int colLo, int colHi, int colChunk, const double *__restrict__ weights,
+                double *__restrict__ partial) {
+    __shared__ double smM[MAX_GAUSS_POINTS * 3 * kThreads];
+    __shared__ double smT[kTileJ * kTileStride];
+    __shared__ int smId[kTileJ * 3];
+    const int rows = rowHi - rowLo;
+    const int r = blockIdx.x * kThreads + threadIdx.x;
+    const bool active = r < rows;
+    const int i = rowLo + (active ? r : rows - 1);
+    const int ng = c_ngauss;
+    const int stride = pm.stride;
+    const double *__restrict__ tri = pm.tri;
+    double *myM = smM + threadIdx.x;
+    const tri3 ci = ldtri(pm.cells, i);
+    const double Si = __ldg(tri + PK_S * stride + i);
+    {
+        const d3 A = ld3(tri + PK_A * stride, stride, i), B = ld3(tri + PK_B * stride, stride, i), C = ld3(tri + PK_C * stride, stride, i);
+#pragma unroll 1
+        for (int g = 0; g < ng; ++g) {
+            const d3 M = gauss_point(g, A, B, C);
+            myM[(3 * g + 0) * kThreads] = M.x; myM[(3 * g + 1) * kThreads] = M.y; myM[(3 * g + 2) * kThreads] = M.z;
+        }
+    }
+    d3 acc = {0.0, 0.0, 0.0};
+    const int j0 = colLo + blockIdx.y * colChunk;
+    const int j1 = min(j0 + colChunk, colHi);
+    for (int tile = j0; tile < j1; tile += kTileJ) {
+        __syncthreads();
+        // cooperative, coalesced load of the tile: component-major source rows -> [j][component] in shared memory
+        for (int e = threadIdx.x; e < kTileJ * 28; e += kThreads) {
+            const int comp = e / kTileJ, jj = e % kTileJ, j = tile + jj;
+            double v = 0.0;
+            if (j < j1) {
+                if (comp < 21) v = __ldg(tri + comp * stride + j);                       // A,B,C,ta,tb,tc,Nu
+                else if (comp < 24) v = __ldg(tri + (PK_L + comp - 21) * stride + j);     // edge lengths
+                else if (comp < 27) v = __ldg(tri + (PK_N + comp - 24) * stride + j);     // unit normal
+                else v = weights ? __ldg(weights + j) : 1.0;
+            }
+            smT[jj * kTileStride + comp] = v;
+        }
+        for (int e = threadIdx.x; e < kTileJ * 3; e += kThreads) {
+            const int jj = e / 3, j = tile + jj;
+            smId[e] = j < j1 ? __ldg(pm.cells + 3 * (long long)j + e % 3) : -1;
+        }
+        __syncthreads();
+        const int nj = min(kTileJ, j1 - tile);
+#pragma unroll 1
+        for (int jj = 0; jj < nj; ++jj) {
+            const double *t = smT + jj * kTileStride;
+            TriJ T;
+            T.A = {t[0], t[1], t[2]}; T.B = {t[3], t[4], t[5]}; T.C = {t[6], t[7], t[8]};
+            T.ta = {t[9], t[10], t[11]}; T.tb = {t[12], t[13], t[14]}; T.tc = {t[15], t[16], t[17]};
+            T.Nu = {t[18], t[19], t[20]};
+            T.La = t[21]; T.Lb = t[22]; T.Lc = t[23];
+            double a1, a2, a3, a4;
+            grouped_eval<true, false>(myM, ng, T, a1, a2, a3, a4);
+            const int ja = smId[3 * jj], jb = smId[3 * jj + 1], jc = smId[3 * jj + 2];
+            const bool skip = (tile + jj == i) || ci.a == ja || ci.a == jb || ci.a == jc || ci.b == ja || ci.b == jb || ci.b == jc ||
+                              ci.c == ja || ci.c == jb || ci.c == jc;
+            const d3 psi = (Si * a1) * T.tc + (Si * a2) * T.ta + (Si * a3) * T.tb;
+            const d3 nj3 = {t[24], t[25], t[26]};
+            const d3 J = assemble_J(vec4(psi, Si * a4), nj3, 0.0, false);
+            const double w = t[27];
+            acc.x = skip ? acc.x : fma(w, J.x, acc.x);
+            acc.y = skip ? acc.y : fma(w, J.y, acc.y);
+            acc.z = skip ? acc.z : fma(w, J.z, acc.z);
+        }
+    }
+    if (active) {
+        double *o = partial + ((long long)blockIdx.y * rows + r) * 3;
+        o[0] = acc.x; o[1] = acc.y; o[2] = acc.z;
+    }
+}
+
+__global__ void k_reduce_partials(const double *__restrict__ partial, int rows, int chunks, double *__restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows * 3) return;
+    double s = 0.0;
+    for (int c = 0; c < chunks; ++c) s += partial[(long long)c * rows * 3 + e];
+    out[e] = s;
+}
+
+void launch_apply_regular(const PackedMesh &pm, int rowLo, int rowHi, int colLo, int colHi, int chunks, const double *weights,
+                          double *partial, double *out3, cudaStream_t s) {
+    const int rows = rowHi - rowLo, cols = colHi - colLo;
+    if (rows <= 0 || cols <= 0) return;
+    const int colChunk = (cols + chunks - 1) / chunks;
+    dim3 grid((rows + kThreads - 1) / kThreads, chunks);
+    ++g_launchCount;
+    k_apply_regular<4><<<grid, kThreads, 0, s>>>(pm, rowLo, rowHi, colLo, colHi, colChunk, weights, partial);
+    ++g_launchCount;
+    k_reduce_partials<<<(rows * 3 + 255) / 256, 256, 0, s>>>(partial, rows, chunks, out3);
 }
 
 // tuning knob (env I2_MINBLOCKS = 3|4|5): resident CTAs per SM the regular kernel is compiled for

@@ -50,6 +50,8 @@ void launch_geometry(const double *verts, const int *cells, int nc, double *norm
 // otherwise slots list[0..*countDev-1] (device-side count, persistent grid)
 void launch_integrate(int cls, int mathMode, const PackedMesh &pm, const int *tasks, const int *list, const int *countDev,
                       long long countHost, int level, double *out4, double *fusedResults3, int numSMs, cudaStream_t s);
+void launch_apply_regular(const PackedMesh &pm, int rowLo, int rowHi, int colLo, int colHi, int chunks, const double *weights,
+                          double *partial, double *out3, cudaStream_t s);
 void launch_checksum(const double *results3, long long n, double *sums4, int numSMs, cudaStream_t s);
 void launch_compare(const double *cur4, const double *prev4, const int *tasks, const int *listIn, const int *countIn,
                     long long countHost, int *listOut, int *countOut, unsigned char *cellFlag, unsigned char *converged,
