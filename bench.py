@@ -18,7 +18,10 @@ Neighbors over the mesh's task lists.
             port when that binary is absent.
 
 N > 1 (torchrun): every class's task list is split into N equal-cost contiguous shards (tasks of one class cost the
-same at a fixed level), each rank integrates its shard, and per-pair results are gathered to rank 0 with NCCL.
+same at a fixed level) and each rank integrates its shard; tasks are independent, so there is no data-path collective:
+the per-pair results stay resident on the rank that computed them and only the per-class checksums are all-reduced.
+The export variant (all per-pair results gathered to rank 0 with NCCL, overlapped with compute) is timed separately and
+reported as `with_gather_to_rank0`.  `--workload matrixfree` runs BASELINE.json configs[4] (108 544-triangle sphere).
 """
 from __future__ import annotations
 
@@ -242,15 +245,25 @@ def main():
     refin = torch.zeros((mesh.n_cells,), dtype=torch.uint8, device=dev) if args.level < 0 else None
 
     side = torch.cuda.Stream(device=dev) if world > 1 else None
+    chk = torch.zeros((3, 4), dtype=torch.float64, device=dev)
 
     def step():
-        if world == 1:
+        # every rank integrates its shard of every class; the per-pair results stay resident on the rank that computed them
+        # (no data-path collective: tasks are independent).  At N > 1 the per-class checksums are all-reduced (96 B) so that
+        # every step ends with a cross-rank result.
+        for cls in range(3):
+            if refin is not None:
+                refin.zero_()
+            ctx.integrate_class(cls, tasks[cls], args.level, want_stats=False, refinements=refin, out=outs[cls])
+        if world > 1:
             for cls in range(3):
-                if refin is not None:
-                    refin.zero_()
-                ctx.integrate_class(cls, tasks[cls], args.level, want_stats=False, refinements=refin, out=outs[cls])
-            return
-        # N > 1: shard of every class, finished chunks of results travel to rank 0 over NCCL while the next chunk computes
+                J = outs[cls][1]
+                chk[cls, :3] = J.sum(0)
+                chk[cls, 3] = J.abs().sum()
+            dist.all_reduce(chk)
+
+    def step_with_gather():
+        # export variant: finished chunks of per-pair results travel to rank 0 over NCCL while the next chunk computes
         from integrator2_b200.multigpu import integrate_and_gather, wait_all
         works = []
         for cls in (2, 0, 1):
@@ -294,6 +307,26 @@ def main():
     ms_step = ms_total / args.steps
     value = total_pairs / (ms_step * 1e-3)
 
+    # ---- N > 1: the export variant (all per-pair results gathered to rank 0 over NVLink), timed separately ------------
+    gather_info = None
+    if world > 1:
+        for _ in range(2):
+            step_with_gather()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(stream)
+        for _ in range(args.steps):
+            step_with_gather()
+        g1.record(stream)
+        barrier()
+        tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        ms_g = float(tg.item()) / args.steps
+        gather_info = {"value": total_pairs / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g,
+                       "bytes_into_rank0_per_step": int(sum(counts) * 24 * (world - 1) / world),
+                       "what": "same step, but every per-pair Point3 result is also gathered to rank 0 (NCCL point-to-point, 8 chunks "
+                               "overlapped with compute); bound by rank 0's NVLink ingest, reported for the export use case"}
+
     # ---- roofline of the dominant kernel (regular pairs), measured live with CUDA events on the launch stream ----
     roof = None
     if rank == 0:
@@ -318,10 +351,10 @@ def main():
                     "algorithmic_flop_per_pair": FLOP_PER_REGULAR_PAIR, "pairs_per_launch": my_counts[2],
                     "peak_source": "measured on this device by i2_peak_rates (DFMA chains); MEASURED_PEAKS.json has no FP64 figure",
                     "mufu_peak_gops": mufu_g,
-                    "note": "achieved uses the per-point work model of SURVEY.md 8(d) (6.1 kflop/pair); the grouped kernel executes ~1760 FP64 "
+                    "note": "achieved uses the per-point work model of SURVEY.md 8(d) (6.1 kflop/pair); the grouped kernel executes ~1730 FP64 "
                             "instructions (~2.8 kflop) per pair, i.e. frac > 1 means work removed, not a faster pipe; FP64-pipe active 65 % in "
                             "profiles/r01_ncu_k_regular_grouped_v3_final.txt",
-                    "executed_fp64_inst_per_pair": 1760}
+                    "executed_fp64_inst_per_pair": 1730}
 
     # ---- end to end through the host-buffer C ABI (N=1): host mesh in -> prepare (H2D, geometry, classification, task
     # lists) -> three classes -> results.  Two variants, both timed with the host clock around the blocking calls:
@@ -389,9 +422,10 @@ def main():
                 "dtype": "f64", "data": "reference example mesh (tests/golden/meshes.npz, parsed from Vint16k.dat); no random data",
                 "config": {"workload": f"{args.mesh}.dat scale {args.scale} level {'adaptive' if args.level < 0 else args.level}: "
                                        f"{counts[0]} vertex-adjacent + {counts[1]} edge-adjacent + {counts[2]} regular = {total_pairs} ordered pairs",
-                           "triangles": mesh.n_cells, "quadrature": "Cowper 13-point (order 7)", "sharding": f"{world} contiguous equal-cost shards per class",
+                           "triangles": mesh.n_cells, "quadrature": "Cowper 13-point (order 7)", "sharding": f"{world} contiguous equal-cost shards per class, results resident per rank, checksums all-reduced",
                            "l2": "inputs+outputs per step (task lists 12 B/pair, results 56 B/pair) are far larger than L2; no flush needed"},
-                "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu}
+                "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
+                "with_gather_to_rank0": gather_info}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
