@@ -2,7 +2,9 @@
 #include "../../include/integrator2/evaluators/evaluator3d.cuh"
 #include "host_context.h"
 
-#include <fstream>
+#include <algorithm>
+#include <cstdio>
+#include <string>
 
 Evaluator3D::Evaluator3D(const Mesh3D &mesh_, NumericalIntegrator3D &numIntegrator_) : mesh(mesh_), numIntegrator(numIntegrator_) {}
 
@@ -138,29 +140,49 @@ bool Evaluator3D::outputResultsToFile(neighbour_type_enum neighborType, output_f
     }
     checkCudaErrors(cudaDeviceSynchronize());
 
-    std::ofstream out(filename.c_str());
-    if (!out.is_open()) {
+    FILE *out = fopen(filename.c_str(), "w");
+    if (!out) {
         printf("Error while opening the file\n");
         return false;
     }
     if (outputFormat == output_format_enum::csv) {
-        out << "\"TaskI\";\"TaskJ\";\"IntegralX\";\"IntegralY\";\"IntegralZ\"";
-        if (withErrors) out << ";\"Error\"";
-        out << std::endl;
+        fputs("\"TaskI\";\"TaskJ\";\"IntegralX\";\"IntegralY\";\"IntegralZ\"", out);
+        if (withErrors) fputs(";\"Error\"", out);
+        fputc('\n', out);
     }
-    for (int t = 0; t < n; ++t) {
-        const int3 task = hostTasks[t];
-        const Point3 J = hostResults[t];
-        if (outputFormat == output_format_enum::csv) {
-            out << task.x << ";" << task.y << ";" << J.x << ";" << J.y << ";" << J.z;
-            if (withErrors) out << ";" << hostErrors[t];
-        } else {
-            out << "(" << task.x << ", " << task.y << "): [" << J.x << ", " << J.y << ", " << J.z << "]";
-            if (withErrors) out << ", error = " << hostErrors[t];
+    // The reference streams every row through `ofstream << double << std::endl` (default precision: "%g", 6 digits) and
+    // flushes per row; the same bytes are produced here by formatting blocks of rows in parallel into strings that are
+    // written in order (2.9e8 rows on Vint16k: the formatting, not the GPU, is the export's cost).
+    const int block = 1 << 16;
+    const int nBlocks = (n + block - 1) / block;
+    const int wave = 64;   // blocks formatted concurrently, then written in order
+    std::vector<std::string> text(wave);
+    for (int b0 = 0; b0 < nBlocks; b0 += wave) {
+        const int nb = std::min(wave, nBlocks - b0);
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int b = 0; b < nb; ++b) {
+            std::string &dst = text[b];
+            dst.clear();
+            char line[256];
+            const int lo = (b0 + b) * block, hi = std::min(n, lo + block);
+            for (int t = lo; t < hi; ++t) {
+                const int3 task = hostTasks[t];
+                const Point3 J = hostResults[t];
+                int len;
+                if (outputFormat == output_format_enum::csv) {
+                    len = snprintf(line, sizeof(line), "%d;%d;%g;%g;%g", task.x, task.y, J.x, J.y, J.z);
+                    if (withErrors) len += snprintf(line + len, sizeof(line) - len, ";%g", hostErrors[t]);
+                } else {
+                    len = snprintf(line, sizeof(line), "(%d, %d): [%g, %g, %g]", task.x, task.y, J.x, J.y, J.z);
+                    if (withErrors) len += snprintf(line + len, sizeof(line) - len, ", error = %g", hostErrors[t]);
+                }
+                line[len++] = '\n';
+                dst.append(line, len);
+            }
         }
-        out << std::endl;
+        for (int b = 0; b < nb; ++b) fwrite(text[b].data(), 1, text[b].size(), out);
     }
-    out.close();
+    fclose(out);
     printf("%d results saved to file %s\n", n, filename.c_str());
     return true;
 }
