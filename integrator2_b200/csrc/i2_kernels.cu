@@ -324,7 +324,16 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
     const double *__restrict__ tri = pm.tri;
     double *myM = smM + threadIdx.x;
 
-    for (long long base = warpId * groupsPerWarp; base < count; base += warpStride * groupsPerWarp) {
+    // A warp walks a contiguous chunk of kChunkIters x 32 tasks: lists are sorted by control panel i, so a lane meets the
+    // same i (and the same child) in consecutive iterations and its staged Gauss points are reused (13 x 9 FP64 per task
+    // saved); chunks are dealt round-robin to the warps of the grid.
+    constexpr int kChunkIters = 16;
+    const long long chunkTasks = (long long)groupsPerWarp * kChunkIters;
+    int iStaged = -1;
+    for (long long chunk = warpId; chunk * chunkTasks < count; chunk += warpStride)
+    for (int it = 0; it < kChunkIters; ++it) {
+        const long long base = chunk * chunkTasks + (long long)it * groupsPerWarp;
+        if (base >= count) break;
         long long r = base + lane / G;
         const bool active = r < count;
         if (!active) r = count - 1;   // tail lanes recompute the last task (no write) so that warp votes stay full-mask
@@ -341,7 +350,7 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
 
         double s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;
         for (int k = 0; k < perLane; ++k) {
-            {
+            if (perLane > 1 || i != iStaged) {
                 d3 A = ld3(tri + PK_A * stride, stride, i), B = ld3(tri + PK_B * stride, stride, i), C = ld3(tri + PK_C * stride, stride, i);
                 descend(A, B, C, level, sub + G * k);
 #pragma unroll 1
@@ -349,6 +358,7 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
                     const d3 M = gauss_point(g, A, B, C);
                     myM[(3 * g + 0) * kThreads] = M.x; myM[(3 * g + 1) * kThreads] = M.y; myM[(3 * g + 2) * kThreads] = M.z;
                 }
+                iStaged = perLane > 1 ? -1 : i;
             }
             double a1, a2, a3, a4;
             grouped_eval<EDGELEN, RESID>(myM, ng, T, a1, a2, a3, a4);

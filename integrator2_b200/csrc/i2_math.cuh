@@ -1,5 +1,5 @@
 // Branch-free FP64 primitives for the regular-pair kernel (the FP64 pipe is the roofline, so every DFMA counts):
-//   fast_sqrt      MUFU.RSQ64H seed + one coupled Goldschmidt step + one residual correction   (7 FP64 ops)
+//   fast_sqrt      MUFU.RSQ64H seed + one Goldschmidt step + one residual correction           (6 FP64 ops)
 //   fast_rcp       MUFU.RCP64H seed + two Newton steps                                          (4 FP64 ops)
 //   log_ratio      ln(N/D) with the division folded into the atanh argument (N-D)/(N+D)        (~25 FP64 ops)
 //   atan2_fast     atan2(y,x) with a 5-entry argument reduction, one division                  (~26 FP64 ops)
@@ -79,11 +79,11 @@ I2_HD double rcp_seed(double x) {
 
 I2_HD double fast_sqrt(double x) {
     const double y = rsqrt_seed(x);
-    double g = x * y, h = 0.5 * y;
+    double g = x * y;
+    const double h = 0.5 * y;
     const double r = fma(-g, h, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
-    return fma(fma(-g, g, x), h, g);   // g + (x - g^2) * (1/(2 sqrt x))
+    g = fma(g, r, g);                  // relative error ~1.5 e0^2 (e0 = seed error, ~2^-22)
+    return fma(fma(-g, g, x), h, g);   // g + (x - g^2) * (1/(2 sqrt x)); h keeps the seed's error: residual ~e0^3, below 1 ulp
 }
 
 I2_HD double fast_rcp(double x) {
