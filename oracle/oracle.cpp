@@ -28,6 +28,7 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+#include <quadmath.h>
 
 namespace {
 
@@ -518,9 +519,86 @@ bool rungeUnconverged(V4 cur, V4 prev) {
     return norm1(divide(num, den)) > kEpsIntegration;
 }
 
+
+// ---- 113-bit ("truth") evaluation of the SAME formulas for regular pairs ------------------------------------------------
+// thetaPsi (src/evaluators/evaluatorJ3DK.cu:266-313) and the quadrature in __float128: with a 113-bit mantissa even the
+// worst cancellations of the formula (1/(1+cos) up to ~1e13) leave > 20 correct digits, so this is the exact value of what
+// the reference's expressions DEFINE for the given double inputs.  It measures how far the reference's own FP64 result,
+// the oracle and the product are from that value — the noise floor behind the conditioning-aware tolerance.
+typedef __float128 Q;
+struct Q3 { Q x, y, z; };
+inline Q3 qsub(Q3 a, Q3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline Q3 qadd(Q3 a, Q3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline Q3 qmul(Q s, Q3 a) { return {a.x * s, a.y * s, a.z * s}; }
+inline Q qdot(Q3 a, Q3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline Q3 qcross(Q3 a, Q3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+inline Q3 qunit(Q3 a) { const Q l = sqrtq(qdot(a, a)); return {a.x / l, a.y / l, a.z / l}; }
+inline Q3 toQ(V3 a) { return {(Q)a.x, (Q)a.y, (Q)a.z}; }
+
+void thetaPsiQ(Q3 pt, Q3 A, Q3 B, Q3 C, Q out[4]) {
+    Q3 oa = qsub(pt, A), ob = qsub(pt, B), oc = qsub(pt, C);
+    const Q la = sqrtq(qdot(oa, oa)), lb = sqrtq(qdot(ob, ob)), lc = sqrtq(qdot(oc, oc));
+    oa = qmul(1 / la, oa); ob = qmul(1 / lb, ob); oc = qmul(1 / lc, oc);
+    const Q3 ta = qunit(qsub(C, B)), tb = qunit(qsub(A, C)), tc = qunit(qsub(B, A));
+    const Q rac = qdot(oa, tc), rbc = qdot(ob, tc), rba = qdot(ob, ta), rca = qdot(oc, ta), rcb = qdot(oc, tb), rab = qdot(oa, tb);
+    const Q eps = (Q)(0.5 * kEpsPsiTheta2);
+    const Q t1 = fabsq(rbc + 1) < eps ? logq(lb / la) : logq((la * (1 + rac)) / (lb * (1 + rbc)));
+    const Q t2 = fabsq(rca + 1) < eps ? logq(lc / lb) : logq((lb * (1 + rba)) / (lc * (1 + rca)));
+    const Q t3 = fabsq(rab + 1) < eps ? logq(la / lc) : logq((lc * (1 + rcb)) / (la * (1 + rab)));
+    out[0] = t1 * tc.x + t2 * ta.x + t3 * tb.x;
+    out[1] = t1 * tc.y + t2 * ta.y + t3 * tb.y;
+    out[2] = t1 * tc.z + t2 * ta.z + t3 * tb.z;
+    out[3] = 2 * atan2q(qdot(qcross(oa, ob), oc), 1 + qdot(oa, ob) + qdot(ob, oc) + qdot(oc, oa));
+}
+
+void sumChildrenQ(Q3 A, Q3 B, Q3 C, Q measure, int level, Q3 JA, Q3 JB, Q3 JC, Q acc[4]) {
+    if (level == 0) {
+        Q part[4] = {0, 0, 0, 0};
+        for (int g = 0; g < g_qf.n; ++g) {
+            const Q3 p = qadd(qadd(qmul((Q)g_qf.L[g].x, A), qmul((Q)g_qf.L[g].y, B)), qmul((Q)g_qf.L[g].z, C));
+            Q f[4];
+            thetaPsiQ(p, JA, JB, JC, f);
+            for (int c = 0; c < 4; ++c) part[c] += (Q)g_qf.w[g] * f[c];
+        }
+        for (int c = 0; c < 4; ++c) acc[c] += measure * part[c];
+        return;
+    }
+    const Q half = (Q)0.5;
+    const Q3 ma = qmul(half, qadd(B, C)), mb = qmul(half, qadd(C, A)), mc = qmul(half, qadd(A, B));
+    const Q q = measure / 4;
+    sumChildrenQ(mc, B, ma, q, level - 1, JA, JB, JC, acc);
+    sumChildrenQ(ma, C, mb, q, level - 1, JA, JB, JC, acc);
+    sumChildrenQ(mb, A, mc, q, level - 1, JA, JB, JC, acc);
+    sumChildrenQ(ma, mb, mc, q, level - 1, JA, JB, JC, acc);
+}
+
 }  // namespace
 
 extern "C" {
+
+// regular-pair results J (Point3) of n tasks in 113-bit arithmetic, rounded to double at the very end
+void orc_regular_results_quad(const void *h, const int *tasks, long long n, int level, double *results) {
+    const Mesh *m = (const Mesh *)h;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (long long t = 0; t < n; ++t) {
+        const int i = tasks[3 * t], j = tasks[3 * t + 1];
+        const Tri ti = m->cells[i], tj = m->cells[j];
+        const Q3 IA = toQ(m->verts[ti.a]), IB = toQ(m->verts[ti.b]), IC = toQ(m->verts[ti.c]);
+        const Q3 JA = toQ(m->verts[tj.a]), JB = toQ(m->verts[tj.b]), JC = toQ(m->verts[tj.c]);
+        const Q3 nI = qcross(qsub(IB, IA), qsub(IC, IA));
+        const Q Si = sqrtq(qdot(nI, nI)) / 2;
+        Q acc[4] = {0, 0, 0, 0};
+        sumChildrenQ(IA, IB, IC, Si, level, JA, JB, JC, acc);
+        const Q3 nj = qunit(qcross(qsub(JB, JA), qsub(JC, JA)));
+        const Q3 psi = {acc[0], acc[1], acc[2]};
+        const Q3 pxn = qcross(psi, nj);
+        const Q k = (Q)kRecipFourPi;
+        results[3 * t] = (double)(k * (acc[3] * nj.x + pxn.x));
+        results[3 * t + 1] = (double)(k * (acc[3] * nj.y + pxn.y));
+        results[3 * t + 2] = (double)(k * (acc[3] * nj.z + pxn.z));
+    }
+}
+
 
 // quadrature rule: xy = n pairs (L_x, L_y); L_z = 1 - L_x - L_y (src/NumericalIntegrator3d.cu:202-206)
 int orc_set_quadrature(const double *xy, const double *w, int n, int order) {

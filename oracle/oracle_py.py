@@ -57,6 +57,7 @@ def lib():
         L.orc_singular_part.argtypes = [vp, C.c_int, dp, C.c_int, C.c_int, dp]
         L.orc_integrate_singular.argtypes = [vp, C.c_int, C.c_int, C.c_int, dp]
         L.orc_regular_integrals.argtypes = [vp, C.c_int, ip, ll, C.c_int, dp]
+        L.orc_regular_results_quad.argtypes = [vp, ip, ll, C.c_int, dp]
         L.orc_run_class.argtypes = [vp, C.c_int, ip, ll, C.c_int, dp, dp, C.POINTER(C.c_ubyte), C.POINTER(ll)]
         L.orc_run_class.restype = C.c_int
         L.orc_symmetry_error.argtypes = [dp, ll, dp]
@@ -157,6 +158,13 @@ class OracleMesh:
         tasks = np.ascontiguousarray(tasks, dtype=np.int32)
         out = np.empty((tasks.shape[0], 4))
         lib().orc_regular_integrals(self._h, cls, _ip(tasks), tasks.shape[0], int(level), _dp(out))
+        return out
+
+    def regular_results_quad(self, tasks, level=0):
+        """J of regular tasks evaluated with the reference's formulas in 113-bit arithmetic (the 'exact' value)."""
+        tasks = np.ascontiguousarray(tasks, dtype=np.int32)
+        out = np.empty((tasks.shape[0], 3))
+        lib().orc_regular_results_quad(self._h, _ip(tasks), tasks.shape[0], int(level), _dp(out))
         return out
 
     def run_class(self, cls, tasks, level=0):

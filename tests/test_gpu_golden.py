@@ -85,3 +85,22 @@ def test_gpu_adaptive_rounds_match_reference(ctx, name):
             assert d <= max(3, 2e-4 * unconv), (name, cn, k, r["stats"], rounds)
         ref = G[f"{name}.refinements"][c]
         assert (r["refinements"].cpu().numpy() != ref).sum() <= 2 * ties, (name, cn)
+
+
+@pytest.mark.parametrize("name", ["G1_r0", "s5m_r0", "Vint16k_r0", "cubehole_r0", "ellipsoid2000_r0"])
+def test_gpu_is_as_accurate_as_the_reference_against_exact(ctx, oracle, name):
+    """Distance to the EXACT value of the reference's formulas (113-bit evaluation in the oracle): the product's regular-pair
+    kernel (hoisted, grouped, branch-free primitives) must not be noisier than the reference's own CUDA results."""
+    m = dump_mesh(name)
+    ctx.set_mesh(m.vertices, m.cells)
+    r, J, t = _run(ctx, name, 2, 0)
+    om = oracle.OracleMesh(m.vertices, m.cells)
+    exact = om.regular_results_quad(t, 0)
+    scale = np.abs(exact).sum(1)
+    e_gpu = np.abs(J - exact).sum(1) / scale
+    e_ref = np.abs(G[f"{name}.not.J"] - exact).sum(1) / scale
+    print(name, "median gpu %.2e ref %.2e | p99 gpu %.2e ref %.2e | max gpu %.2e ref %.2e" %
+          (np.median(e_gpu), np.median(e_ref), np.quantile(e_gpu, .99), np.quantile(e_ref, .99), e_gpu.max(), e_ref.max()))
+    assert np.median(e_gpu) <= 1.5 * np.median(e_ref) + 1e-15
+    assert np.quantile(e_gpu, 0.99) <= 3.0 * np.quantile(e_ref, 0.99) + 1e-14
+    assert np.quantile(e_gpu, 0.999) <= 5.0 * np.quantile(e_ref, 0.999) + 1e-13
