@@ -262,11 +262,12 @@ static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, c
 #pragma unroll 1
     for (int g = 0; g < ng; ++g) {
         const d3 M = {myM[(3 * g + 0) * kThreads], myM[(3 * g + 1) * kThreads], myM[(3 * g + 2) * kThreads]};
-        const PointTerms t = point_terms<EDGELEN>(M, T);
+        PointTerms t = point_terms_raw<EDGELEN>(M, T);
+        if (__any_sync(0xffffffffu, eps_screen(t))) eps_fixup(t);   // warp-uniform; the screen runs on the integer pipe
         pn1 *= t.N1; pd1 *= t.D1; pn2 *= t.N2; pd2 *= t.D2; pn3 *= t.N3; pd3 *= t.D3;
         const double nr = fma(zr, t.den, -(zi * t.num)), ni = fma(zr, t.num, zi * t.den);
         zr = nr; zi = ni;
-        safe = safe && (fabs(t.num) <= 0.5 * t.den);
+        safe = safe && angle_small(t);
         if (c_groupEnd[g]) {
             const double w = c_gauss[4 * g + 3];
             a1 = fma(w, log_ratio<RESID>(pn1, pd1), a1);

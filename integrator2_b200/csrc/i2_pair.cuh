@@ -100,28 +100,55 @@ I2_HD LogTheta theta_psi_fast(d3 M, const TriJ &T) {
 // partial angle sums stay inside (-pi, pi); every point checks |y_g| <= x_g / 2 (|angle| < pi/6, groups have <= 6
 // points) and a group that fails the check anywhere in the WARP is redone point by point (warp-uniform branch).
 struct PointTerms {
-    double N1, D1, N2, D2, N3, D3;   // log arguments after the epsilon selects
+    double N1, D1, N2, D2, N3, D3;   // log arguments (after the epsilon selects)
     double num, den;                 // Theta_g = 2 atan2(num, den)
+    double la, lb, lc;               // |M-A|, |M-B|, |M-C|
 };
 
 // EDGELEN: d_b·t_c = d_a·t_c - |AB| etc. (d_b = d_a - AB): three dot products become three subtractions.
+// The log arguments are returned WITHOUT the epsilon fallback; eps_screen / eps_fixup apply it.
+template <bool EDGELEN = false>
+I2_HD PointTerms point_terms_raw(d3 M, const TriJ &T) {
+    const d3 da = M - T.A, db = M - T.B, dc = M - T.C;
+    PointTerms r;
+    r.la = fast_sqrt(norm2(da)); r.lb = fast_sqrt(norm2(db)); r.lc = fast_sqrt(norm2(dc));
+    const double pa = dot(da, T.tc), pb = dot(db, T.ta), pc = dot(dc, T.tb);
+    r.N1 = r.la + pa; r.D1 = r.lb + (EDGELEN ? pa - T.Lc : dot(db, T.tc));
+    r.N2 = r.lb + pb; r.D2 = r.lc + (EDGELEN ? pb - T.La : dot(dc, T.ta));
+    r.N3 = r.lc + pc; r.D3 = r.la + (EDGELEN ? pc - T.Lb : dot(da, T.tb));
+    r.num = dot(da, T.Nu);
+    r.den = r.la * r.lb * r.lc + dot(da, db) * r.lc + dot(db, dc) * r.la + dot(dc, da) * r.lb;
+    return r;
+}
+
+// Integer-pipe screen for the reference's fallback test |o_b·t_c + 1| < 0.5e-12  <=>  |D| < 0.5e-12 l: positive doubles
+// order like their bit patterns, so "high word of |D| < high word of l minus 40 exponent steps" (|D| < ~2^-40 l) is a
+// superset of the exact condition (0.5e-12 = 2^-40.86) that costs no FP64 issue slot.  Almost never true.
+I2_HD bool eps_screen(const PointTerms &r) {
+    const int k = 40 << 20;
+    return ((hi_word(r.D1) & 0x7fffffff) < hi_word(r.lb) - k) | ((hi_word(r.D2) & 0x7fffffff) < hi_word(r.lc) - k) |
+           ((hi_word(r.D3) & 0x7fffffff) < hi_word(r.la) - k);
+}
+// exact fallback selects (slow path, taken by a whole warp when any lane passes the screen)
+I2_HD void eps_fixup(PointTerms &r) {
+    const bool f1 = fabs(r.D1) < 0.5 * EPS_PSI_THETA2 * r.lb;
+    const bool f2 = fabs(r.D2) < 0.5 * EPS_PSI_THETA2 * r.lc;
+    const bool f3 = fabs(r.D3) < 0.5 * EPS_PSI_THETA2 * r.la;
+    r.N1 = f1 ? r.lb : r.N1; r.D1 = f1 ? r.la : r.D1;
+    r.N2 = f2 ? r.lc : r.N2; r.D2 = f2 ? r.lb : r.D2;
+    r.N3 = f3 ? r.la : r.N3; r.D3 = f3 ? r.lc : r.D3;
+}
+// |num| < den/2 and den > 0 on the integer pipe (conservative in the low word): the point's half solid angle is below pi/6
+I2_HD bool angle_small(const PointTerms &r) {
+    const int hd = hi_word(r.den);
+    return (hd > 0) & ((hi_word(r.num) & 0x7fffffff) < hd - (1 << 20));
+}
+
+// reference-order variant used by host-side emulation and the diagnostics: selects applied unconditionally
 template <bool EDGELEN = false>
 I2_HD PointTerms point_terms(d3 M, const TriJ &T) {
-    const d3 da = M - T.A, db = M - T.B, dc = M - T.C;
-    const double la = fast_sqrt(norm2(da)), lb = fast_sqrt(norm2(db)), lc = fast_sqrt(norm2(dc));
-    const double pa = dot(da, T.tc), pb = dot(db, T.ta), pc = dot(dc, T.tb);
-    const double n1 = la + pa, q1 = lb + (EDGELEN ? pa - T.Lc : dot(db, T.tc));
-    const double n2 = lb + pb, q2 = lc + (EDGELEN ? pb - T.La : dot(dc, T.ta));
-    const double n3 = lc + pc, q3 = la + (EDGELEN ? pc - T.Lb : dot(da, T.tb));
-    const bool f1 = fabs(q1) < 0.5 * EPS_PSI_THETA2 * lb;
-    const bool f2 = fabs(q2) < 0.5 * EPS_PSI_THETA2 * lc;
-    const bool f3 = fabs(q3) < 0.5 * EPS_PSI_THETA2 * la;
-    PointTerms r;
-    r.N1 = f1 ? lb : n1; r.D1 = f1 ? la : q1;
-    r.N2 = f2 ? lc : n2; r.D2 = f2 ? lb : q2;
-    r.N3 = f3 ? la : n3; r.D3 = f3 ? lc : q3;
-    r.num = dot(da, T.Nu);
-    r.den = la * lb * lc + dot(da, db) * lc + dot(db, dc) * la + dot(dc, da) * lb;
+    PointTerms r = point_terms_raw<EDGELEN>(M, T);
+    eps_fixup(r);
     return r;
 }
 

@@ -63,11 +63,12 @@ void emu_regular(const double *v, const int *cells, const double *measures, cons
             bool safe = true;
             int gStart = 0;
             for (int g = 0; g < g_n; ++g) {
-                const PointTerms t = (var & 1) ? point_terms<true>(gp(g, I.A, I.B, I.C), T) : point_terms<false>(gp(g, I.A, I.B, I.C), T);
+                PointTerms t = (var & 1) ? point_terms_raw<true>(gp(g, I.A, I.B, I.C), T) : point_terms_raw<false>(gp(g, I.A, I.B, I.C), T);
+                if (eps_screen(t)) eps_fixup(t);
                 pn1 *= t.N1; pd1 *= t.D1; pn2 *= t.N2; pd2 *= t.D2; pn3 *= t.N3; pd3 *= t.D3;
                 const double nr = fma(zr, t.den, -(zi * t.num)), ni = fma(zr, t.num, zi * t.den);
                 zr = nr; zi = ni;
-                safe = safe && (fabs(t.num) <= 0.5 * t.den);
+                safe = safe && angle_small(t);
                 const bool last = (g == g_n - 1) || (g_w[g + 1] != g_w[g]) || (g - gStart == 5);
                 if (last) {
                     const double w = g_w[g];
