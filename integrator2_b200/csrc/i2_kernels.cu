@@ -170,11 +170,12 @@ k_integrate(PackedMesh pm, const int *__restrict__ tasks, const int *__restrict_
     const double *__restrict__ tri = pm.tri;
 
     for (long long base = warpId * groupsPerWarp; base < count; base += warpStride * groupsPerWarp) {
-        const long long r = base + lane / G;
+        long long r = base + lane / G;
         const bool active = r < count;
+        if (!active) r = count - 1;   // tail lanes recompute the last task (no write): warp votes in the prologues stay full-mask
         d4 total = {0.0, 0.0, 0.0, 0.0};
         int slot = 0;
-        if (active) {
+        {
             slot = list ? __ldg(list + r) : (int)r;
             const int i = __ldg(tasks + 3 * (long long)slot), j = __ldg(tasks + 3 * (long long)slot + 1);
             double Si = __ldg(tri + PK_S * stride + i);
@@ -614,8 +615,9 @@ template <int CLS>
 __global__ void __launch_bounds__(128)
 k_finalize(PackedMesh pm, const double *__restrict__ verts, const int *__restrict__ tasks, long long n, double *bufA,
            const double *__restrict__ bufB, const QueueState *__restrict__ qs, double *__restrict__ results, QueueState *qsMut) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n) return;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = t < n;
+    if (!active) t = n - 1;   // tail lanes redo the last task without storing: the warp votes inside the closed forms stay full-mask
     // result-buffer ping-pong of the reference's adaptive loop (src/evaluators/evaluatorJ3DK.cu:976): after L rounds
     // the live buffer is A for even L, B for odd L; slots whose task converged earlier keep what that buffer last held.
     const double *src = (qs->lastRound & 1) ? bufB : bufA;
@@ -637,7 +639,7 @@ k_finalize(PackedMesh pm, const double *__restrict__ verts, const int *__restric
             bool bad = false;
             I = I + integral_singular_vertex(ldv(verts, ri.a), ldv(verts, ri.b), ldv(verts, ri.c), ldv(verts, rj.a), ldv(verts, rj.b),
                                              ldv(verts, rj.c), ni, nj, Si, &bad);
-            if (bad) {
+            if (bad && active) {
                 printf("Orientation is incorrect for pair (%d, %d)\n", i, j);  // same text as the reference (:701-702)
                 atomicAdd(&qsMut->orientationWarnings, 1);
             }
@@ -647,6 +649,7 @@ k_finalize(PackedMesh pm, const double *__restrict__ verts, const int *__restric
         }
     }
     const d3 J = assemble_J(I, nj, Si, CLS == 0);
+    if (!active) return;
     double2 *op = reinterpret_cast<double2 *>(bufA + 4 * t);
     op[0] = make_double2(I.x, I.y);
     op[1] = make_double2(I.z, I.w);

@@ -40,13 +40,11 @@ I2_HD d4 theta_psi_strict(d3 M, d3 A, d3 B, d3 C) {
     const d3 ta = unit(C - B), tb = unit(A - C), tc = unit(B - A);
     const double rac = dot(oa, tc), rbc = dot(ob, tc), rba = dot(ob, ta);
     const double rca = dot(oc, ta), rcb = dot(oc, tb), rab = dot(oa, tb);
-    double t1, t2, t3;
-    if (fabs(rbc + 1.0) < 0.5 * EPS_PSI_THETA2) t1 = log(lb / la);
-    else t1 = log((la * (1.0 + rac)) / (lb * (1.0 + rbc)));
-    if (fabs(rca + 1.0) < 0.5 * EPS_PSI_THETA2) t2 = log(lc / lb);
-    else t2 = log((lb * (1.0 + rba)) / (lc * (1.0 + rca)));
-    if (fabs(rab + 1.0) < 0.5 * EPS_PSI_THETA2) t3 = log(la / lc);
-    else t3 = log((lc * (1.0 + rcb)) / (la * (1.0 + rab)));
+    // epsilon fallback of the reference as selects on the log argument (same expressions, no divergence)
+    const bool f1 = fabs(rbc + 1.0) < 0.5 * EPS_PSI_THETA2, f2 = fabs(rca + 1.0) < 0.5 * EPS_PSI_THETA2, f3 = fabs(rab + 1.0) < 0.5 * EPS_PSI_THETA2;
+    const double t1 = log(f1 ? lb / la : (la * (1.0 + rac)) / (lb * (1.0 + rbc)));
+    const double t2 = log(f2 ? lc / lb : (lb * (1.0 + rba)) / (lc * (1.0 + rca)));
+    const double t3 = log(f3 ? la / lc : (lc * (1.0 + rcb)) / (la * (1.0 + rab)));
     d4 r = vec4(t1 * tc + t2 * ta + t3 * tb);
     r.w = 2.0 * atan2(dot(cross(oa, ob), oc), 1.0 + dot(oa, ob) + dot(ob, oc) + dot(oc, oa));
     return r;
@@ -207,18 +205,24 @@ struct VertexFrame {
         db = atan2(dot(cross(dir, tb), nj), dot(dir, tb));
     }
     I2_HD void init(d3 ni, d3 nj, d3 ta, d3 tb) {
-        e = cross(ni, nj);
-        if (norm2(e) < EPS_ZERO2) e = tb;
-        else e = unit(e);
+        const d3 c = cross(ni, nj);
+        const bool coplanar = norm2(c) < EPS_ZERO2;
+        const d3 u = unit(c);                       // garbage for coplanar pairs, discarded by the select
+        e = {coplanar ? tb.x : u.x, coplanar ? tb.y : u.y, coplanar ? tb.z : u.z};
         deltas(e, ta, tb, nj);
-        if ((PI - fabs(da) < EPS_ZERO) || (PI - fabs(db) < EPS_ZERO)) {
-            e = -1.0 * e;
-            deltas(e, ta, tb, nj);
-        }
-        if ((da * db < 0) && (fabs(da - db) > PI)) {
-            e = -1.0 * e;
-            deltas(e, ta, tb, nj);
-        }
+        // the two conditional flips of the reference, each evaluated by the whole warp only if some lane needs it
+        const bool flip1 = (PI - fabs(da) < EPS_ZERO) || (PI - fabs(db) < EPS_ZERO);
+        if (I2_WARP_ANY(flip1)) flip(flip1, ta, tb, nj);
+        const bool flip2 = (da * db < 0) && (fabs(da - db) > PI);
+        if (I2_WARP_ANY(flip2)) flip(flip2, ta, tb, nj);
+    }
+    I2_HD void flip(bool mine, d3 ta, d3 tb, d3 nj) {
+        VertexFrame f;
+        f.e = -1.0 * e;
+        f.deltas(f.e, ta, tb, nj);
+        e = {mine ? f.e.x : e.x, mine ? f.e.y : e.y, mine ? f.e.z : e.z};
+        da = mine ? f.da : da;
+        db = mine ? f.db : db;
     }
 };
 
@@ -324,11 +328,13 @@ I2_HD d4 integral_singular_edge(d3 IA, d3 IB, d3 IC, d3 JA, d3 JB, d3 JC, d3 ni,
     const double qab = nu.s * log(tan(0.5 * alpha) * tan(0.5 * nuA)) / be.s +
                        nu.s * log(tan(0.5 * beta) * tan(0.5 * nuA)) / al.s +
                        log(tan(0.5 * alpha) * tan(0.5 * beta));
-    q2 qa, qb;
-    if ((fabs(xiA) < EPS_ZERO) && (fabs(beta - gamma) < EPS_ZERO)) qa = q_edge_coplanar(be, nu, al.s);
-    else qa = q_edge(al, be, ga, nu, xi, cosMu, cosLambda);
-    if ((fabs(xiA) < EPS_ZERO) && (fabs(alpha - delta) < EPS_ZERO)) qb = q_edge_coplanar(al, nu, be.s);
-    else qb = q_edge(be, al, de, nu, xi, cosSigma, cosTheta);
+    // general formula for every lane; the coplanar limit is evaluated warp-wide only when some lane needs it
+    q2 qa = q_edge(al, be, ga, nu, xi, cosMu, cosLambda);
+    q2 qb = q_edge(be, al, de, nu, xi, cosSigma, cosTheta);
+    const bool copA = (fabs(xiA) < EPS_ZERO) && (fabs(beta - gamma) < EPS_ZERO);
+    const bool copB = (fabs(xiA) < EPS_ZERO) && (fabs(alpha - delta) < EPS_ZERO);
+    if (I2_WARP_ANY(copA)) { const q2 z = q_edge_coplanar(be, nu, al.s); qa.theta = copA ? z.theta : qa.theta; qa.psi = copA ? z.psi : qa.psi; }
+    if (I2_WARP_ANY(copB)) { const q2 z = q_edge_coplanar(al, nu, be.s); qb.theta = copB ? z.theta : qb.theta; qb.psi = copB ? z.psi : qb.psi; }
     d4 r = vec4(Si * (qa.psi * tb + qb.psi * ta - qab * tc));
     r.w = Si * (qa.theta + qb.theta);
     return r;
@@ -375,40 +381,49 @@ I2_HD q2 q_vertex(const VertexAngles &g, double delta, sc de, double cosLambda, 
     const double mulPsi = sgn_dz(g.xi.s * g.psi.s);
     const double mulDelta = sgn_dz(g.xi.s * de.s);
 
-    if ((fabs(g.xi.s) < EPS_ZERO) && (1.0 - fabs(cosSigma) < 0.5 * EPS_ZERO2) && (fabs(g.psi.s) > EPS_ZERO)) {
+    // The reference tests four special cases in a fixed order and falls through to the general formula; here the general
+    // value is the default and each special case is evaluated by the whole warp only if some lane is in it.
+    const bool planar = fabs(g.xi.s) < EPS_ZERO, psiOk = fabs(g.psi.s) > EPS_ZERO;
+    const bool c1 = planar && (1.0 - fabs(cosSigma) < 0.5 * EPS_ZERO2) && psiOk;
+    const bool c2 = !c1 && planar && psiOk;
+    const bool c34 = !c1 && !c2 && (fabs(sin(g.psiA)) < EPS_ZERO);
+    const bool c3 = c34 && (fabs(delta) > EPS_ZERO), c4 = c34 && !(fabs(delta) > EPS_ZERO);
+    r.theta = gent;
+    r.psi = gens;
+    if (I2_WARP_ANY(c1)) {
         const double ara = arg_dz(sin(0.5 * (g.nuA + g.psiA)) * cosSigma);
         const double arb = arg_dz(cos(0.5 * (g.muA - g.psiA)) * cosSigma);
-        r.theta = 2.0 * mulPsi * cosSigma * g.xi.c / (g.sinKappa * g.psi.s) * (g.mu.s * g.sinNuPsi * ara - g.nu.s * g.sinMuPsi * arb);
-        r.psi = 0.5 * (1.0 - log(2.0)) - 0.5 * log((1.0 - cosSigma * g.mu.c) * (1.0 + cosSigma * g.nu.c) / g.sinKappa) +
-                cosSigma * (g.mu.s - g.nu.s + 0.5 * sin(g.muA - g.nuA) * Lambda2) / g.sinKappa;
-        return r;
+        const double th = 2.0 * mulPsi * cosSigma * g.xi.c / (g.sinKappa * g.psi.s) * (g.mu.s * g.sinNuPsi * ara - g.nu.s * g.sinMuPsi * arb);
+        const double ps = 0.5 * (1.0 - log(2.0)) - 0.5 * log((1.0 - cosSigma * g.mu.c) * (1.0 + cosSigma * g.nu.c) / g.sinKappa) +
+                          cosSigma * (g.mu.s - g.nu.s + 0.5 * sin(g.muA - g.nuA) * Lambda2) / g.sinKappa;
+        r.theta = c1 ? th : r.theta;
+        r.psi = c1 ? ps : r.psi;
     }
-    if ((fabs(g.xi.s) < EPS_ZERO) && (fabs(g.psi.s) > EPS_ZERO)) {
+    if (I2_WARP_ANY(c2)) {
         const double are = arg_dz(sin(0.5 * (g.nuA + g.muA)) + sin(0.5 * (g.muA - g.nuA) - g.psiA + delta * g.xi.c));
         const double arc = arg_dz(1.0 / tan(0.5 * (g.nuA + g.psiA)) + tan(0.5 * delta) * g.xi.c);
         const double ard = arg_dz(tan(0.5 * (g.muA - g.psiA)) + tan(0.5 * delta) * g.xi.c);
-        r.theta = 2.0 * mulDelta * (de.s * g.mu.s * g.nu.s / cosChi * g.xi.c * are +
-                                    g.mu.s * g.sinNuPsi * arc - g.nu.s * g.sinMuPsi * ard) / (g.sinKappa * g.psi.s);
-        r.psi = gens;
-        return r;
+        const double th = 2.0 * mulDelta * (de.s * g.mu.s * g.nu.s / cosChi * g.xi.c * are +
+                                            g.mu.s * g.sinNuPsi * arc - g.nu.s * g.sinMuPsi * ard) / (g.sinKappa * g.psi.s);
+        r.theta = c2 ? th : r.theta;      // psi stays the general value
     }
-    if (fabs(sin(g.psiA)) < EPS_ZERO) {
-        if (fabs(delta) > EPS_ZERO) {
-            r.theta = 2.0 * (g.mu.s * g.nu.s * (W * de.c * g.xi.c - 0.5 * (Lambda1 - Lambda2 * cosSigma) * g.xi.s) / de.s +
-                             (Anu + mulDelta * arg_dz(sin(0.5 * (g.nuA + g.psiA)))) * g.mu.s * g.nu.c +
-                             (Amu + mulDelta * arg_dz(cos(0.5 * (g.muA - g.psiA)))) * g.mu.c * g.nu.s) / g.sinKappa;
-            r.psi = 0.5 * (3.0 - log(2.0)) -
-                    0.5 * (log((1.0 + cosLambda) * (1.0 + cosTheta) / g.sinKappa) - sin(g.muA - g.nuA) / g.sinKappa * Lambda1) -
-                    g.mu.s * g.nu.s * ((Lambda1 * de.c - Lambda2 * g.psi.c) * g.xi.c + 2.0 * W * g.xi.s) / (g.sinKappa * de.s);
-            return r;
-        }
-        r.theta = 2.0 * arg_dz(g.psi.c);
-        r.psi = 0.5 * (1.0 - log(2.0)) - 0.5 * log((1.0 - g.psi.c * g.mu.c) * (1.0 + g.psi.c * g.nu.c) / g.sinKappa) +
-                (0.5 * sin(g.muA - g.nuA) * Lambda1 + g.psi.c * (g.mu.s - g.nu.s)) / g.sinKappa;
-        return r;
+    if (I2_WARP_ANY(c3)) {
+        const double th = 2.0 * (g.mu.s * g.nu.s * (W * de.c * g.xi.c - 0.5 * (Lambda1 - Lambda2 * cosSigma) * g.xi.s) / de.s +
+                                 (Anu + mulDelta * arg_dz(sin(0.5 * (g.nuA + g.psiA)))) * g.mu.s * g.nu.c +
+                                 (Amu + mulDelta * arg_dz(cos(0.5 * (g.muA - g.psiA)))) * g.mu.c * g.nu.s) / g.sinKappa;
+        const double ps = 0.5 * (3.0 - log(2.0)) -
+                          0.5 * (log((1.0 + cosLambda) * (1.0 + cosTheta) / g.sinKappa) - sin(g.muA - g.nuA) / g.sinKappa * Lambda1) -
+                          g.mu.s * g.nu.s * ((Lambda1 * de.c - Lambda2 * g.psi.c) * g.xi.c + 2.0 * W * g.xi.s) / (g.sinKappa * de.s);
+        r.theta = c3 ? th : r.theta;
+        r.psi = c3 ? ps : r.psi;
     }
-    r.theta = gent;
-    r.psi = gens;
+    if (I2_WARP_ANY(c4)) {
+        const double th = 2.0 * arg_dz(g.psi.c);
+        const double ps = 0.5 * (1.0 - log(2.0)) - 0.5 * log((1.0 - g.psi.c * g.mu.c) * (1.0 + g.psi.c * g.nu.c) / g.sinKappa) +
+                          (0.5 * sin(g.muA - g.nuA) * Lambda1 + g.psi.c * (g.mu.s - g.nu.s)) / g.sinKappa;
+        r.theta = c4 ? th : r.theta;
+        r.psi = c4 ? ps : r.psi;
+    }
     return r;
 }
 
@@ -459,11 +474,11 @@ I2_HD d4 integral_singular_vertex(d3 IA, d3 IB, d3 IC, d3 JA, d3 JB, d3 JC, d3 n
 //      vertex-adjacent pairs (src/evaluators/evaluatorJ3DK.cu:224-264) -----------------------------------------
 I2_HD d3 assemble_J(d4 I, d3 nj, double Si, bool wrapTheta) {
     double theta = I.w;
-    if (wrapTheta) {
-        int p = 0;
+    if (wrapTheta) {   // compile-time class property, not data dependent
         const double ref = TWO_PI * Si;
-        if (theta > ref) p = -((int)trunc((theta - ref) / (2.0 * ref)) + 1);
-        else if (theta < -ref) p = ((int)trunc((-ref - theta) / (2.0 * ref)) + 1);
+        const int pHi = -((int)trunc((theta - ref) / (2.0 * ref)) + 1);
+        const int pLo = ((int)trunc((-ref - theta) / (2.0 * ref)) + 1);
+        const int p = theta > ref ? pHi : (theta < -ref ? pLo : 0);
         theta = theta + 2.0 * p * ref;
     }
     const d3 psi = {I.x, I.y, I.z};

@@ -11,6 +11,15 @@
 #define I2_D inline
 #endif
 
+// Warp-uniform control flow: a rare, data-dependent alternative is evaluated by the WHOLE warp when any lane needs it
+// and selected per lane afterwards; on the host (tests/host_emu) the vote degenerates to the lane's own predicate.
+// Callers on the device must have all 32 lanes of the warp active.
+#if defined(__CUDA_ARCH__)
+#define I2_WARP_ANY(pred) (__any_sync(0xffffffffu, (pred)) != 0)
+#else
+#define I2_WARP_ANY(pred) (pred)
+#endif
+
 namespace i2 {
 
 // thresholds and constants, bit-identical to the reference (src/common/constants.h:11-65):
@@ -52,14 +61,13 @@ I2_HD double l1(d4 a) { return fabs(a.x) + fabs(a.y) + fabs(a.z) + fabs(a.w); }
 I2_HD double sgn_dz(double x) { return fabs(x) < DOUBLE_MIN ? 0.0 : (x > DOUBLE_MIN ? 1.0 : -1.0); }
 I2_HD double arg_dz(double x) { return x > DOUBLE_MIN ? 0.0 : PI; }
 
-// angle between two vectors (src/common/cuda_math.cu:14-27)
+// angle between two vectors (src/common/cuda_math.cu:14-27): 0 for degenerate input, cosine clamped to [-1, 1]
+// (acos(1) = 0 and acos(-1) = pi exactly, which are the reference's early-return values) — branch-free
 I2_HD double angle_between(d3 a, d3 b) {
     const double den = sqrt(norm2(a) * norm2(b));
-    if (den < EPS_ZERO) return 0.0;
-    const double c = dot(a, b) / den;
-    if (c >= 1.0) return 0.0;
-    if (c <= -1.0) return PI;
-    return acos(c);
+    const double c = fmin(fmax(dot(a, b) / den, -1.0), 1.0);
+    const double r = acos(c);
+    return den < EPS_ZERO ? 0.0 : r;
 }
 
 struct tri3 { int a, b, c; };

@@ -131,4 +131,43 @@ void emu_regular_level(const double *v, const int *cells, const double *measures
     }
 }
 
+
+// closed-form integral of the singular part (cls 0 vertex-adjacent, 1 edge-adjacent) for n tasks; out double4[n]
+void emu_singular_integral(int cls, const double *v, const int *cells, const double *normals, const double *measures, const int *tasks,
+                           long long n, double *out) {
+    auto V = [&](int k) { return d3{v[3 * k], v[3 * k + 1], v[3 * k + 2]}; };
+    auto N = [&](int c) { return d3{normals[3 * c], normals[3 * c + 1], normals[3 * c + 2]}; };
+    for (long long t = 0; t < n; ++t) {
+        const int i = tasks[3 * t], j = tasks[3 * t + 1];
+        const tri3 ti = {cells[3 * i], cells[3 * i + 1], cells[3 * i + 2]}, tj = {cells[3 * j], cells[3 * j + 1], cells[3 * j + 2]};
+        int si, sj;
+        if (cls == 0) shifts_vertex(ti, tj, si, sj); else shifts_edge(ti, tj, si, sj);
+        const tri3 ri = rot_left(ti, si), rj = rot_left(tj, sj);
+        bool bad = false;
+        const d4 r = cls == 0 ? integral_singular_vertex(V(ri.a), V(ri.b), V(ri.c), V(rj.a), V(rj.b), V(rj.c), N(i), N(j), measures[i], &bad)
+                              : integral_singular_edge(V(ri.a), V(ri.b), V(ri.c), V(rj.a), V(rj.b), V(rj.c), N(i), N(j), measures[i]);
+        out[4 * t] = r.x; out[4 * t + 1] = r.y; out[4 * t + 2] = r.z; out[4 * t + 3] = r.w;
+    }
+}
+
+// singular part at the centroid-ish points of triangle i (regular part integrand of the adjacent classes), strict order
+void emu_singular_point(int cls, const double *v, const int *cells, const double *normals, const double *measures, const int *tasks,
+                        long long n, double *out) {
+    auto V = [&](int k) { return d3{v[3 * k], v[3 * k + 1], v[3 * k + 2]}; };
+    auto N = [&](int c) { return d3{normals[3 * c], normals[3 * c + 1], normals[3 * c + 2]}; };
+    for (long long t = 0; t < n; ++t) {
+        const int i = tasks[3 * t], j = tasks[3 * t + 1];
+        const tri3 ti = {cells[3 * i], cells[3 * i + 1], cells[3 * i + 2]}, tj = {cells[3 * j], cells[3 * j + 1], cells[3 * j + 2]};
+        int si, sj;
+        if (cls == 0) shifts_vertex(ti, tj, si, sj); else shifts_edge(ti, tj, si, sj);
+        const tri3 rj = rot_left(tj, sj);
+        const d3 M = gp(1, V(ti.a), V(ti.b), V(ti.c));
+        d4 r;
+        if (cls == 0) { VertexSingular vs; vs.init(V(rj.a), V(rj.b), V(rj.c), N(i), N(j), measures[i]); r = vs.at(M); }
+        else { EdgeSingular es; es.init(V(rj.a), V(rj.b), V(rj.c)); r = es.at(M); }
+        const d4 tp = theta_psi_strict(M, V(tj.a), V(tj.b), V(tj.c));
+        out[4 * t] = tp.x - r.x; out[4 * t + 1] = tp.y - r.y; out[4 * t + 2] = tp.z - r.z; out[4 * t + 3] = tp.w - r.w;
+    }
+}
+
 }  // extern "C"
