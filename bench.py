@@ -232,8 +232,14 @@ def main():
     counts = [int(t.shape[0]) for t in tasks_full]
     total_pairs = sum(counts)
     # equal-cost contiguous shard of every class for this rank
-    from integrator2_b200.multigpu import shard_bounds
-    bounds = [shard_bounds(n, world)[rank] for n in counts]
+    from integrator2_b200.multigpu import adaptive_task_cost, cost_balanced_bounds, shard_bounds
+    if args.level < 0 and world > 1:
+        # adaptive error control: shards of equal PREDICTED cost (class weight x expected refinement depth from the
+        # centroid-distance / panel-size ratio), still contiguous so that all descendants of a task stay on its rank
+        all_bounds = [cost_balanced_bounds(adaptive_task_cost(mesh.vertices, mesh.cells, t, cls), world) for cls, t in enumerate(tasks_full)]
+    else:
+        all_bounds = [shard_bounds(n, world) for n in counts]
+    bounds = [b[rank] for b in all_bounds]
     tasks = [t[lo:hi].contiguous() for t, (lo, hi) in zip(tasks_full, bounds)]
     if world > 1:
         del tasks_full
@@ -269,7 +275,7 @@ def main():
         works = []
         for cls in (2, 0, 1):
             works += integrate_and_gather(ctx, cls, tasks[cls], args.level, outs[cls], gathered[cls] if rank == 0 else None,
-                                          shard_bounds(counts[cls], world), rank, world, side, chunks=8 if cls == 2 else 1)
+                                          all_bounds[cls], rank, world, side, chunks=8 if cls == 2 else 1)
         wait_all(works, side)
 
     def barrier():

@@ -118,3 +118,54 @@ def wait_all(works, side_stream=None):
         w.wait()
     if side_stream is not None:
         torch.cuda.current_stream().wait_stream(side_stream)
+
+
+# Probability that a regular task is still unconverged after the first refinement round, as a function of
+# rho = |c_i - c_j| / sqrt(max(S_i, S_j)) (centroid distance over panel size), measured with the CPU oracle on the
+# reference's s5m.dat airplane (scale 0.0005; tools' calibration in DESIGN.md section 7).  Far pairs never refine twice.
+_RHO_EDGES = (1.0, 1.5, 2.0, 3.0, 4.0, 6.0, 10.0)
+_P_UNCONVERGED = (0.69, 0.42, 0.13, 0.031, 0.0066, 0.0020, 0.0006, 0.0)
+# expected child integrations of a task that survives round 1: 16 + 0.33 (64 + 0.23 (256 + 0.13 * 1024))
+_TAIL_COST = 66.7
+_BASE_COST = 5.0     # rounds 0 and 1 are unconditional: 1 + 4 child integrations
+
+
+def adaptive_task_cost(vertices, cells, tasks, cls=2):
+    """Predicted cost (in level-0 pair integrations) of every task under adaptive error control: class weight x
+    (5 + 66.7 * P(rho)).  Works on numpy arrays or on torch tensors (any device); returns the same kind."""
+    is_torch = type(tasks).__module__.startswith("torch")     # (numpy >= 2 arrays also have a .device attribute)
+    if is_torch:
+        import torch
+        v = torch.as_tensor(vertices, device=tasks.device, dtype=torch.float64)
+        c = torch.as_tensor(cells, device=tasks.device).long()
+        tri = v[c]                                              # [nc, 3, 3]
+        cent = tri.mean(1)
+        area = 0.5 * torch.linalg.norm(torch.linalg.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]), dim=1)
+        i, j = tasks[:, 0].long(), tasks[:, 1].long()
+        rho = torch.linalg.norm(cent[i] - cent[j], dim=1) / torch.sqrt(torch.maximum(area[i], area[j]))
+        idx = torch.bucketize(rho, torch.tensor(_RHO_EDGES, device=tasks.device, dtype=torch.float64), right=True)
+        p = torch.tensor(_P_UNCONVERGED, device=tasks.device, dtype=torch.float64)[idx]
+        return CLASS_COST[cls] * (_BASE_COST + _TAIL_COST * p)
+    import numpy as np
+    tri = np.asarray(vertices)[np.asarray(cells)]
+    cent = tri.mean(1)
+    area = 0.5 * np.linalg.norm(np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]), axis=1)
+    i, j = tasks[:, 0], tasks[:, 1]
+    rho = np.linalg.norm(cent[i] - cent[j], axis=1) / np.sqrt(np.maximum(area[i], area[j]))
+    p = np.asarray(_P_UNCONVERGED)[np.searchsorted(np.asarray(_RHO_EDGES), rho, side="right")]
+    return CLASS_COST[cls] * (_BASE_COST + _TAIL_COST * p)
+
+
+def cost_balanced_bounds(cost, world):
+    """shard_bounds for a per-task cost vector that may live on the GPU (torch) or on the host (numpy)."""
+    if type(cost).__module__.startswith("torch"):
+        import torch
+        n = int(cost.shape[0])
+        c = torch.cumsum(cost.double(), 0)
+        total = float(c[-1]) if n else 0.0
+        targets = torch.tensor([total * r / world for r in range(1, world)], device=cost.device, dtype=torch.float64)
+        cuts = [0] + [int(x) for x in torch.searchsorted(c, targets).tolist()] + [n]
+        for r in range(1, world + 1):
+            cuts[r] = max(cuts[r], cuts[r - 1])
+        return [(cuts[r], cuts[r + 1]) for r in range(world)]
+    return shard_bounds(len(cost), world, cost)

@@ -204,3 +204,28 @@ def test_full_size_properties_vint16k(ctx, oracle):
     ref = om.run_class(2, ts, 0)
     st = check_regular_parity(m.vertices, m.cells, ts, J[idx.cuda()].cpu().numpy(), ref["results"], "Vint16k sample")
     print("Vint16k", st)
+
+
+def test_cost_balanced_adaptive_sharding(ctx, oracle):
+    """Adaptive work per shard (child integrations actually executed, from the device queue's statistics) for 4 contiguous
+    shards of the regular class of s5m: split by predicted cost (integrator2_b200.multigpu.adaptive_task_cost) vs split
+    by task count."""
+    import torch
+    from integrator2_b200.multigpu import adaptive_task_cost, cost_balanced_bounds, shard_bounds
+    m, om = _setup(ctx, oracle, "s5m", 0.0005)
+    tasks = torch.as_tensor(om.tasks(2)).cuda()
+    n = int(tasks.shape[0])
+
+    def work(bounds):
+        out = []
+        for lo, hi in bounds:
+            st = ctx.integrate_class(2, tasks[lo:hi].contiguous(), -1)["stats"]
+            out.append(sum(st["integrated"][: st["last_round"] + 1]))
+        return np.array(out, dtype=np.float64)
+
+    w_count = work(shard_bounds(n, 4))
+    w_cost = work(cost_balanced_bounds(adaptive_task_cost(m.vertices, m.cells, tasks), 4))
+    assert abs(w_count.sum() - w_cost.sum()) <= 1e-3 * w_count.sum()       # same total work (ties aside)
+    imb_count, imb_cost = w_count.max() / w_count.mean(), w_cost.max() / w_cost.mean()
+    print("adaptive shard imbalance: by count %.4f, by predicted cost %.4f" % (imb_count, imb_cost))
+    assert imb_cost < 1.03 and imb_cost <= imb_count + 0.005

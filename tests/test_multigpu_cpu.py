@@ -55,3 +55,24 @@ def test_gather_two_ranks_gloo(tmp_path):
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                           "--master-port", "29611", str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert "GATHER_OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_adaptive_cost_model_orders_near_before_far():
+    """Predicted adaptive cost: near pairs (small centroid distance / panel size) cost several times a far pair; numpy and
+    torch paths agree; cost-balanced bounds cover the list."""
+    import torch
+    from integrator2_b200.meshio import load_fixture
+    from integrator2_b200.multigpu import adaptive_task_cost, cost_balanced_bounds
+    from oracle import oracle_py as O
+    m = load_fixture("s5m", 0.0005)
+    om = O.OracleMesh(m.vertices, m.cells)
+    t = om.tasks(2)[::50]
+    c_np = adaptive_task_cost(m.vertices, m.cells, t)
+    c_t = adaptive_task_cost(m.vertices, m.cells, torch.as_tensor(t)).numpy()
+    assert np.allclose(c_np, c_t)
+    assert c_np.min() == 5.0 and c_np.max() > 40.0
+    b = cost_balanced_bounds(torch.as_tensor(c_np), 4)
+    assert b[0][0] == 0 and b[-1][1] == t.shape[0] and all(b[r][1] == b[r + 1][0] for r in range(3))
+    per = np.array([c_np[lo:hi].sum() for lo, hi in b])
+    assert per.max() / per.mean() < 1.02
+    assert b == shard_bounds(t.shape[0], 4, c_np) or abs(b[1][0] - shard_bounds(t.shape[0], 4, c_np)[1][0]) <= 1
