@@ -1,8 +1,10 @@
 #!/bin/bash
+# Full single-GPU session (run with: gpurun -- bash tools/gpu_session.sh): kernel timing, GPU test suite, bench (both arms),
+# ncu launch list of the bench command and one ncu --set full capture of the regular-pair kernel.  Outputs in gpurun_out/.
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out; rm -f gpurun_out/variants.log
-I2_VARIANT=3 timeout 300 python tools/gpu_variants.py >> gpurun_out/variants.log 2>&1
+timeout 300 python tools/gpu_variants.py >> gpurun_out/variants.log 2>&1
 cat gpurun_out/variants.log
 echo "== pytest gpu"; timeout 2400 python -m pytest tests -m gpu -q --timeout 1200 > gpurun_out/pytest_gpu_all.log 2>&1; tail -6 gpurun_out/pytest_gpu_all.log
 echo "== bench"; timeout 1200 python bench.py > gpurun_out/bench_ours.log 2>&1; tail -1 gpurun_out/bench_ours.log | cut -c1-600
