@@ -347,6 +347,7 @@ def main():
                     t_int.append(ctx.profile_last()[0])
         ctx.set_profiling(False)
         dfma_tf, mufu_g = ctx.peak_rates()
+        dfma3_tf = ctx.peak_dfma_three_operand()
         if t_int:
             ms_k = sum(t_int) / len(t_int)
             flops = FLOP_PER_REGULAR_PAIR * my_counts[2] * (4 ** max(args.level, 0))
@@ -359,8 +360,10 @@ def main():
                     "algorithmic_flop_per_pair": FLOP_PER_REGULAR_PAIR, "pairs_per_launch": my_counts[2],
                     "peak_source": "measured on this device by i2_peak_rates (DFMA chains); MEASURED_PEAKS.json has no FP64 figure",
                     "mufu_peak_gops": mufu_g,
+                    "peak_three_register_operands": dfma3_tf,
                     "note": "achieved uses the per-point work model of SURVEY.md 8(d) (6.1 kflop/pair); the grouped kernel executes ~1640 FP64 "
-                            "instructions (~2.6 kflop) per pair, i.e. frac > 1 means work removed, not a faster pipe; FP64-pipe active 65 % in "
+                            "instructions (~2.6 kflop) per pair, i.e. frac > 1 means work removed, not a faster pipe; peak_three_register_operands is the DFMA rate when every "
+                            "instruction reads three distinct registers (the practical ceiling of real code, ~75 % of peak); FP64-pipe active 65 % in "
                             "profiles/r01_ncu_k_regular_grouped_v4_final.txt",
                     "executed_fp64_inst_per_pair": 1640}
 

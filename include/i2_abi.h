@@ -146,6 +146,8 @@ int i2_selftest_math(i2_context *ctx, int op, const double *d_a, const double *d
 
 /* ---- measured roofline denominators: FP64-pipe DFMA rate and XU-pipe MUFU rate of this device ---------- */
 int i2_peak_rates(i2_context *ctx, double *dfma_tflops, double *mufu_gops);
+/* DFMA rate when every instruction reads three distinct 64-bit register operands (register-file bandwidth included) */
+int i2_peak_dfma_three_operand(i2_context *ctx, double *tflops);
 
 #ifdef __cplusplus
 }

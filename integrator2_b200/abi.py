@@ -48,7 +48,7 @@ EXPORTS = [
     "i2_create", "i2_destroy", "i2_set_stream", "i2_synchronize", "i2_set_math_mode", "i2_error_string",
     "i2_set_quadrature", "i2_mesh_geometry", "i2_set_mesh", "i2_classify_count", "i2_classify_fill",
     "i2_add_reversed_pairs", "i2_integrate_class", "i2_symmetry_error", "i2_host_prepare", "i2_host_run",
-    "i2_host_device_views", "i2_host_checksums", "i2_peak_rates", "i2_refine_mesh_once", "i2_launch_count", "i2_set_profiling", "i2_profile_last", "i2_selftest_math", "i2_apply_regular",
+    "i2_host_device_views", "i2_host_checksums", "i2_peak_rates", "i2_peak_dfma_three_operand", "i2_refine_mesh_once", "i2_launch_count", "i2_set_profiling", "i2_profile_last", "i2_selftest_math", "i2_apply_regular",
 ]
 
 _lib = None
@@ -93,6 +93,7 @@ def load_library():
     L.i2_launch_count.argtypes = [C.POINTER(ll)]
     L.i2_set_profiling.argtypes = [vp, i32]
     L.i2_profile_last.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.i2_peak_dfma_three_operand.argtypes = [vp, C.POINTER(C.c_double)]
     L.i2_peak_rates.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     for name in EXPORTS:
         if name != "i2_error_string":
@@ -254,6 +255,11 @@ class Context:
         a, b = C.c_double(), C.c_double()
         _check(self.L.i2_peak_rates(self.h, C.byref(a), C.byref(b)))
         return float(a.value), float(b.value)
+
+    def peak_dfma_three_operand(self):
+        a = C.c_double()
+        _check(self.L.i2_peak_dfma_three_operand(self.h, C.byref(a)))
+        return float(a.value)
 
     # ---- host-buffer API (end-to-end) ------------------------------------------------------------------
     def host_prepare(self, vertices, cells):

@@ -522,6 +522,33 @@ int i2_profile_last(i2_context *c, float *msIntegrate, float *msFinalize) {
     return 0;
 }
 
+int i2_peak_dfma_three_operand(i2_context *c, double *tflops) {
+    if (!c || !tflops) return I2_E_BADARG;
+    I2_CUDA(cudaSetDevice(c->device));
+    double *buf = nullptr;
+    I2_CUDA(cudaMalloc((void **)&buf, sizeof(double) * 17));
+    double seed[16];
+    for (int k = 0; k < 16; ++k) seed[k] = (k < 8 ? 1.0000001 : 0.9999999) + 1e-9 * k;   // |b c| ~ 1: no overflow over the loop
+    I2_CUDA(cudaMemcpyAsync(buf + 1, seed, sizeof(seed), cudaMemcpyHostToDevice, c->stream));
+    cudaEvent_t e0, e1;
+    I2_CUDA(cudaEventCreate(&e0));
+    I2_CUDA(cudaEventCreate(&e1));
+    const int blocks = c->numSMs * 8, iters = 10000;
+    float ms = 0.f;
+    for (int rep = 0; rep < 3; ++rep) {
+        I2_CUDA(cudaEventRecord(e0, c->stream));
+        launch_peak_dfma3(buf, buf + 1, iters, blocks, c->stream);
+        I2_CUDA(cudaEventRecord(e1, c->stream));
+        I2_CUDA(cudaEventSynchronize(e1));
+        I2_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    }
+    *tflops = (double)blocks * 256.0 * iters * 16.0 * 2.0 / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    return 0;
+}
+
 int i2_peak_rates(i2_context *c, double *dfmaTflops, double *mufuGops) {
     if (!c) return I2_E_BADARG;
     I2_CUDA(cudaSetDevice(c->device));

@@ -254,7 +254,7 @@ k_integrate(PackedMesh pm, const int *__restrict__ tasks, const int *__restrict_
 // Grouped evaluation of one (child) control panel against triangle T: on return a1..a3 = sum_g w_g ln(N/D) per edge,
 // a4 = sum_g w_g Theta_g.  myM points at this thread's staged Gauss points ([point][component], stride kThreads).
 // Must be called by all 32 lanes of a warp (one __all_sync per group of equal weights).
-template <bool EDGELEN, bool RESID>
+template <bool EDGELEN, bool RESID, bool DERIVE = false>
 static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, const TriJ &T, double &a1, double &a2, double &a3, double &a4) {
     a1 = 0.0; a2 = 0.0; a3 = 0.0; a4 = 0.0;
     double pn1 = 1.0, pd1 = 1.0, pn2 = 1.0, pd2 = 1.0, pn3 = 1.0, pd3 = 1.0, zr = 1.0, zi = 0.0;
@@ -263,7 +263,7 @@ static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, c
 #pragma unroll 1
     for (int g = 0; g < ng; ++g) {
         const d3 M = {myM[(3 * g + 0) * kThreads], myM[(3 * g + 1) * kThreads], myM[(3 * g + 2) * kThreads]};
-        PointTerms t = point_terms_raw<EDGELEN>(M, T);
+        PointTerms t = point_terms_raw<EDGELEN, DERIVE>(M, T);
         if (__any_sync(0xffffffffu, eps_screen(t))) eps_fixup(t);   // warp-uniform; the screen runs on the integer pipe
         pn1 *= t.N1; pd1 *= t.D1; pn2 *= t.N2; pd2 *= t.D2; pn3 *= t.N3; pd3 *= t.D3;
         const double nr = fma(zr, t.den, -(zi * t.num)), ni = fma(zr, t.num, zi * t.den);
@@ -281,7 +281,7 @@ static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, c
                 th = 0.0;
                 for (int h = gStart; h <= g; ++h) {
                     const d3 Mh = {myM[(3 * h + 0) * kThreads], myM[(3 * h + 1) * kThreads], myM[(3 * h + 2) * kThreads]};
-                    const PointTerms u = point_terms<EDGELEN>(Mh, T);
+                    const PointTerms u = point_terms_raw<EDGELEN, DERIVE>(Mh, T);
                     th += atan2_fast<RESID>(u.num, u.den);
                 }
             }
@@ -311,7 +311,7 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
                   long long countHost, int level, double *__restrict__ out, double *__restrict__ results) {
     __shared__ double smM[MAX_GAUSS_POINTS * 3 * kThreads];
     const long long count = countDev ? (long long)*countDev : countHost;
-    constexpr bool EDGELEN = (VAR & 1) != 0, RESID = (VAR & 2) == 0, LEVEL0 = (VAR & 4) != 0;
+    constexpr bool EDGELEN = (VAR & 1) != 0, RESID = (VAR & 2) == 0, LEVEL0 = (VAR & 4) != 0, DERIVE = (VAR & 8) != 0 && EDGELEN;
     if (LEVEL0) level = 0;
     const int children = 1 << (2 * level);
     const int G = children < 32 ? children : 32;
@@ -345,7 +345,8 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
         for (int l = 0; l < level; ++l) Si *= 0.25;
 
         TriJ T;
-        T.A = ld3(tri + PK_A * stride, stride, j); T.B = ld3(tri + PK_B * stride, stride, j); T.C = ld3(tri + PK_C * stride, stride, j);
+        T.A = ld3(tri + PK_A * stride, stride, j);
+        if (!DERIVE) { T.B = ld3(tri + PK_B * stride, stride, j); T.C = ld3(tri + PK_C * stride, stride, j); }
         T.ta = ld3(tri + PK_TA * stride, stride, j); T.tb = ld3(tri + PK_TB * stride, stride, j); T.tc = ld3(tri + PK_TC * stride, stride, j);
         T.Nu = ld3(tri + PK_NU * stride, stride, j);
         if (EDGELEN) { const d3 L = ld3(tri + PK_L * stride, stride, j); T.La = L.x; T.Lb = L.y; T.Lc = L.z; }
@@ -363,7 +364,7 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
                 iStaged = perLane > 1 ? -1 : i;
             }
             double a1, a2, a3, a4;
-            grouped_eval<EDGELEN, RESID>(myM, ng, T, a1, a2, a3, a4);
+            grouped_eval<EDGELEN, RESID, DERIVE>(myM, ng, T, a1, a2, a3, a4);
             if (LEVEL0) { s1 = Si * a1; s2 = Si * a2; s3 = Si * a3; s4 = Si * a4; }
             else { s1 = fma(Si, a1, s1); s2 = fma(Si, a2, s2); s3 = fma(Si, a3, s3); s4 = fma(Si, a4, s4); }
         }
@@ -452,12 +453,12 @@ k_apply_regular(PackedMesh pm, int rowLo, int rowHi, int colLo, int colHi, int c
         for (int jj = 0; jj < nj; ++jj) {
             const double *t = smT + jj * kTileStride;
             TriJ T;
-            T.A = {t[0], t[1], t[2]}; T.B = {t[3], t[4], t[5]}; T.C = {t[6], t[7], t[8]};
+            T.A = {t[0], t[1], t[2]};   // B and C are derived from A, the tangents and the edge lengths (DERIVE)
             T.ta = {t[9], t[10], t[11]}; T.tb = {t[12], t[13], t[14]}; T.tc = {t[15], t[16], t[17]};
             T.Nu = {t[18], t[19], t[20]};
             T.La = t[21]; T.Lb = t[22]; T.Lc = t[23];
             double a1, a2, a3, a4;
-            grouped_eval<true, false>(myM, ng, T, a1, a2, a3, a4);
+            grouped_eval<true, false, true>(myM, ng, T, a1, a2, a3, a4);
             const int ja = smId[3 * jj], jb = smId[3 * jj + 1], jc = smId[3 * jj + 2];
             const bool skip = (tile + jj == i) || ci.a == ja || ci.a == jb || ci.a == jc || ci.b == ja || ci.b == jb || ci.b == jc ||
                               ci.c == ja || ci.c == jb || ci.c == jc;
@@ -498,7 +499,7 @@ void launch_apply_regular(const PackedMesh &pm, int rowLo, int rowHi, int colLo,
 
 // tuning knob (env I2_MINBLOCKS = 3|4|5): resident CTAs per SM the regular kernel is compiled for
 static int g_minBlocks = [] { const char *e = getenv("I2_MINBLOCKS"); return e ? atoi(e) : 4; }();
-static int g_variant = [] { const char *e = getenv("I2_VARIANT"); return e ? atoi(e) : 3; }();
+static int g_variant = [] { const char *e = getenv("I2_VARIANT"); return e ? atoi(e) : 11; }();
 
 void launch_integrate(int cls, int mathMode, const PackedMesh &pm, const int *tasks, const int *list, const int *countDev,
                       long long countHost, int level, double *out4, double *fusedResults3, int numSMs, cudaStream_t s) {
@@ -519,9 +520,10 @@ void launch_integrate(int cls, int mathMode, const PackedMesh &pm, const int *ta
     else if (mathMode == MATH_FAST_LIBDEVICE) { ++g_launchCount; k_integrate<2, MATH_FAST_LIBDEVICE, 4><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4); }
     else if (mathMode == MATH_FAST_POINTWISE) { ++g_launchCount; k_integrate<2, MATH_FAST_POINTWISE, 4><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4); }
     else {
-        // tuning knobs: I2_MINBLOCKS (3|4|5 resident CTAs/SM), I2_VARIANT (bit0 edge-length trick, bit1 no residual correction);
+        // tuning knobs: I2_MINBLOCKS (3|4|5 resident CTAs/SM), I2_VARIANT (bit0 edge-length identity, bit1 no residual correction,
+        // bit3 derive d_b, d_c from d_a instead of reading B and C; default 11 = all three);
         // the LEVEL0 specialisation (bit 2) is chosen automatically
-        const int var = (g_variant & 3) | (level == 0 ? 4 : 0);
+        const int var = (g_variant & 3) | (level == 0 ? 4 : 0) | (g_variant & 8);
         ++g_launchCount;
 #define I2_LAUNCH_GROUPED(MB, V) k_regular_grouped<MB, V><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4, fusedResults3)
 #define I2_PICK_VAR(MB)                                                                                              \
@@ -529,7 +531,9 @@ void launch_integrate(int cls, int mathMode, const PackedMesh &pm, const int *ta
         case 0: I2_LAUNCH_GROUPED(MB, 0); break; case 1: I2_LAUNCH_GROUPED(MB, 1); break;                       \
         case 2: I2_LAUNCH_GROUPED(MB, 2); break; case 3: I2_LAUNCH_GROUPED(MB, 3); break;                       \
         case 4: I2_LAUNCH_GROUPED(MB, 4); break; case 5: I2_LAUNCH_GROUPED(MB, 5); break;                       \
-        case 6: I2_LAUNCH_GROUPED(MB, 6); break; default: I2_LAUNCH_GROUPED(MB, 7); break;                      \
+        case 6: I2_LAUNCH_GROUPED(MB, 6); break; case 7: I2_LAUNCH_GROUPED(MB, 7); break;                       \
+        case 11: I2_LAUNCH_GROUPED(MB, 11); break; case 15: I2_LAUNCH_GROUPED(MB, 15); break;                   \
+        default: I2_LAUNCH_GROUPED(MB, 7); break;                                                                \
         }
         if (g_minBlocks == 3) { I2_PICK_VAR(3) }
         else if (g_minBlocks == 5) { I2_PICK_VAR(5) }
@@ -549,8 +553,8 @@ cudaError_t preload_kernels() {
 #define I2_TOUCH(...) do { e = cudaFuncGetAttributes(&a, (const void *)(__VA_ARGS__)); if (e != cudaSuccess) return e; } while (0)
     I2_TOUCH(k_integrate<0, MATH_STRICT, 3>);
     I2_TOUCH(k_integrate<1, MATH_STRICT, 3>);
-    I2_TOUCH(k_regular_grouped<4, 7>);
-    I2_TOUCH(k_regular_grouped<4, 3>);
+    I2_TOUCH(k_regular_grouped<4, 15>);
+    I2_TOUCH(k_regular_grouped<4, 11>);
     I2_TOUCH(k_apply_regular<4>);
 #undef I2_TOUCH
     return cudaSuccess;
@@ -811,6 +815,23 @@ __global__ void __launch_bounds__(256) k_peak_dfma(double *sink, int iters) {
     const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
     if (r == 123.456) sink[0] = r;
 }
+// same, but every DFMA reads three DISTINCT 64-bit register operands (the pattern of real code: dot products, Horner
+// steps with register coefficients), which exercises the register-file operand bandwidth as well as the pipe
+__global__ void __launch_bounds__(256) k_peak_dfma3(double *sink, const double *seed, int iters) {
+    double a[8], b[8], c[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a[k] = threadIdx.x * 1e-9 + k; b[k] = seed[k] + threadIdx.x * 1e-12; c[k] = seed[8 + k] - threadIdx.x * 1e-12; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = fma(b[k], c[(k + 3) & 7], a[k]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) b[k] = fma(a[k], c[k], b[(k + 5) & 7]);
+    }
+    double r = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r += a[k] + b[k];
+    if (r == 123.456) sink[0] = r;
+}
 __global__ void __launch_bounds__(256) k_peak_mufu(double *sink, int iters) {
     double a0 = 1.5 + threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
     for (int k = 0; k < iters; ++k) {
@@ -850,6 +871,7 @@ cudaError_t preload_rest() {
 }
 
 void launch_peak_dfma(double *sink, int iters, int blocks, cudaStream_t s) { ++g_launchCount; k_peak_dfma<<<blocks, 256, 0, s>>>(sink, iters); }
+void launch_peak_dfma3(double *sink, const double *seed, int iters, int blocks, cudaStream_t s) { ++g_launchCount; k_peak_dfma3<<<blocks, 256, 0, s>>>(sink, seed, iters); }
 void launch_peak_mufu(double *sink, int iters, int blocks, cudaStream_t s) { ++g_launchCount; k_peak_mufu<<<blocks, 256, 0, s>>>(sink, iters); }
 
 }  // namespace i2

@@ -74,6 +74,7 @@ cudaError_t preload_kernels();
 cudaError_t upload_quadrature(const double *Lxyzw, int n, double pow2p, cudaStream_t s);
 // FP64-pipe / MUFU peak micro-benchmarks: returns elapsed ms for `iters` dependent-chain iterations
 void launch_peak_dfma(double *sink, int iters, int blocks, cudaStream_t s);
+void launch_peak_dfma3(double *sink, const double *seed, int iters, int blocks, cudaStream_t s);
 void launch_peak_mufu(double *sink, int iters, int blocks, cudaStream_t s);
 
 }  // namespace i2

@@ -63,7 +63,7 @@ void emu_regular(const double *v, const int *cells, const double *measures, cons
             bool safe = true;
             int gStart = 0;
             for (int g = 0; g < g_n; ++g) {
-                PointTerms t = (var & 1) ? point_terms_raw<true>(gp(g, I.A, I.B, I.C), T) : point_terms_raw<false>(gp(g, I.A, I.B, I.C), T);
+                PointTerms t = (var & 4) ? point_terms_raw<true, true>(gp(g, I.A, I.B, I.C), T) : ((var & 1) ? point_terms_raw<true>(gp(g, I.A, I.B, I.C), T) : point_terms_raw<false>(gp(g, I.A, I.B, I.C), T));
                 if (eps_screen(t)) eps_fixup(t);
                 pn1 *= t.N1; pd1 *= t.D1; pn2 *= t.N2; pd2 *= t.D2; pn3 *= t.N3; pd3 *= t.D3;
                 const double nr = fma(zr, t.den, -(zi * t.num)), ni = fma(zr, t.num, zi * t.den);

@@ -31,4 +31,6 @@ for rep in range(3):
     ts.append(ctx.profile_last()[0])
 out["level1_ms_per_8th"] = min(ts[1:])
 out["checksum"] = float(buf[1][: n // 8].abs().sum())
+out["peak_dfma_tflops"], out["peak_mufu_gops"] = ctx.peak_rates()
+out["peak_dfma3_tflops"] = ctx.peak_dfma_three_operand()
 print(json.dumps(out))
