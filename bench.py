@@ -352,7 +352,7 @@ def main():
             ms_k = sum(t_int) / len(t_int)
             flops = FLOP_PER_REGULAR_PAIR * my_counts[2] * (4 ** max(args.level, 0))
             achieved = flops / (ms_k * 1e-3) / 1e12
-            # dram__bytes_read+write of this kernel from the ncu --set full capture in profiles/r01_ncu_k_regular_grouped_v4_final.txt:
+            # dram__bytes_read+write of this kernel from the ncu --set full capture in profiles/r01_ncu_k_regular_grouped_v5_final.txt:
             # 19.453 GB for 286 403 650 pairs = 67.92 B/pair (algorithmic: 12 B task + 32 B integrals + 24 B result = 68 B)
             traffic = 67.92 * my_counts[2] if args.level == 0 else None
             roof = {"bound": "fp64", "achieved": achieved, "peak": dfma_tf, "unit": "TFLOP/s", "frac": achieved / dfma_tf,
@@ -361,11 +361,11 @@ def main():
                     "peak_source": "measured on this device by i2_peak_rates (DFMA chains); MEASURED_PEAKS.json has no FP64 figure",
                     "mufu_peak_gops": mufu_g,
                     "peak_three_register_operands": dfma3_tf,
-                    "note": "achieved uses the per-point work model of SURVEY.md 8(d) (6.1 kflop/pair); the grouped kernel executes ~1640 FP64 "
-                            "instructions (~2.6 kflop) per pair, i.e. frac > 1 means work removed, not a faster pipe; peak_three_register_operands is the DFMA rate when every "
-                            "instruction reads three distinct registers (the practical ceiling of real code, ~75 % of peak); FP64-pipe active 65 % in "
-                            "profiles/r01_ncu_k_regular_grouped_v4_final.txt",
-                    "executed_fp64_inst_per_pair": 1640}
+                    "note": "achieved uses the per-point work model of SURVEY.md 8(d) (6.1 kflop/pair); the grouped kernel executes ~1530 FP64 "
+                            "instructions (~2.45 kflop) per pair, i.e. frac > 1 means work removed, not a faster pipe; peak_three_register_operands is the DFMA rate when every "
+                            "instruction reads three distinct registers (the practical ceiling of real code, ~75 % of peak); FP64-pipe active 62 % (83 % of the three-operand ceiling) in "
+                            "profiles/r01_ncu_k_regular_grouped_v5_final.txt",
+                    "executed_fp64_inst_per_pair": 1530}
 
     # ---- end to end through the host-buffer C ABI (N=1): host mesh in -> prepare (H2D, geometry, classification, task
     # lists) -> three classes -> results.  Two variants, both timed with the host clock around the blocking calls:
