@@ -139,7 +139,7 @@ def run_reference(args, mesh, n_pairs_total):
             value = n_pairs_total / (ms_step * 1e-3)
             line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
                     "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-                    "data": "reference example mesh (Vint16k.dat), no random data", "config": cfg,
+                    "data": f"reference example mesh ({args.mesh}.dat), no random data", "config": cfg,
                     "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
                                      "sample": "whole workload; the reference is CUDA-only (no CPU path): its unmodified sources compiled for sm_100, "
                                                "1 host thread + this B200, time window = its own three 'Time for ... integration' lines"},
@@ -430,7 +430,7 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f64", "data": "reference example mesh (tests/golden/meshes.npz, parsed from Vint16k.dat); no random data",
+                "dtype": "f64", "data": f"reference example mesh (tests/golden/meshes.npz, parsed from {args.mesh}.dat); no random data",
                 "config": {"workload": f"{args.mesh}.dat scale {args.scale} level {'adaptive' if args.level < 0 else args.level}: "
                                        f"{counts[0]} vertex-adjacent + {counts[1]} edge-adjacent + {counts[2]} regular = {total_pairs} ordered pairs",
                            "triangles": mesh.n_cells, "quadrature": "Cowper 13-point (order 7)", "sharding": f"{world} contiguous equal-cost shards per class, results resident per rank (no data-path collective)",
