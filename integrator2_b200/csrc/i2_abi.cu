@@ -115,28 +115,29 @@ const char *i2_error_string(int code) {
     }
 }
 
+int i2_destroy(i2_context *c);
+
 int i2_create(i2_context **out, int device) {
     if (!out) return I2_E_BADARG;
     *out = nullptr;
     I2_CUDA(cudaSetDevice(device));
     i2_context *c = new i2_context;
     c->device = device;
+    c->ownStream = true;
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
-    if (e != cudaSuccess) { delete c; return (int)e; }
-    c->numSMs = prop.multiProcessorCount;
-    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) { delete c; return (int)e; }
-    c->ownStream = true;
-    e = cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) { delete c; return (int)e; }
-    for (int k = 0; k < 2; ++k) cudaEventCreateWithFlags(&c->chunkDone[k], cudaEventDisableTiming);
-    e = cudaMalloc((void **)&c->qs, sizeof(QueueState));
-    if (e != cudaSuccess) { delete c; return (int)e; }
-    e = upload_math_tables(c->stream);
+    if (e == cudaSuccess) c->numSMs = prop.multiProcessorCount;
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking);
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&c->chunkDone[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->qs, sizeof(QueueState));
+    if (e == cudaSuccess) e = upload_math_tables(c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e == cudaSuccess) e = preload_kernels();
-    if (e != cudaSuccess) { delete c; return (int)e; }
+    if (e != cudaSuccess) {
+        i2_destroy(c);   // releases whatever was created so far
+        return (int)e;
+    }
     *out = c;
     return 0;
 }
@@ -144,7 +145,7 @@ int i2_create(i2_context **out, int device) {
 int i2_destroy(i2_context *c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     freeHostState(c);
     if (c->tri) cudaFree(c->tri);
     if (c->bufB) cudaFree(c->bufB);
