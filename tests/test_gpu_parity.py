@@ -229,3 +229,20 @@ def test_cost_balanced_adaptive_sharding(ctx, oracle):
     imb_count, imb_cost = w_count.max() / w_count.mean(), w_cost.max() / w_cost.mean()
     print("adaptive shard imbalance: by count %.4f, by predicted cost %.4f" % (imb_count, imb_cost))
     assert imb_cost < 1.03 and imb_cost <= imb_count + 0.005
+
+
+@pytest.mark.parametrize("scale", [1e-9, 1e-6, 1e-3, 1e3, 1e6, 1e9])
+def test_regular_pairs_scale_invariance(ctx, oracle, scale):
+    """J(K_i,K_j) scales with the square of the mesh scale; the grouped kernel multiplies up to six
+    lengths / six solid-angle terms per group, so this also checks that nothing over- or underflows for coordinates
+    between 1e-8 and 1e10."""
+    import torch
+    m = load_fixture("G1")
+    om = oracle.OracleMesh(m.vertices, m.cells)
+    tasks = torch.as_tensor(om.tasks(2)).cuda()
+    ctx.set_mesh(m.vertices, m.cells)
+    base = ctx.integrate_class(2, tasks, 1)["results"].cpu().numpy()
+    ctx.set_mesh(m.vertices * scale, m.cells)
+    scaled = ctx.integrate_class(2, tasks, 1)["results"].cpu().numpy()
+    rel = np.abs(scaled / scale ** 2 - base).sum(1) / np.abs(base).sum(1)
+    assert np.isfinite(scaled).all() and rel.max() < 1e-12, (scale, rel.max())
