@@ -81,10 +81,11 @@ def test_gpu_adaptive_rounds_match_reference(ctx, name):
         ties = 0
         for k, (checked, conv, unconv) in enumerate(rounds, start=1):
             d = abs(r["stats"]["unconverged"][k] - unconv)
-            ties = max(ties, d)
+            ties += d
             assert d <= max(5, 2e-3 * unconv), (name, cn, k, r["stats"], rounds)
         ref = G[f"{name}.refinements"][c]
-        assert (r["refinements"].cpu().numpy() != ref).sum() <= 4 * ties + 2, (name, cn)
+        # every flipped borderline decision can change the counter of its control panel in that and the following rounds
+        assert (r["refinements"].cpu().numpy() != ref).sum() <= 2 * ties + 2, (name, cn)
 
 
 @pytest.mark.parametrize("name", ["G1_r0", "s5m_r0", "Vint16k_r0", "cubehole_r0", "ellipsoid2000_r0"])
