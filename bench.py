@@ -148,29 +148,13 @@ def run_reference(args, mesh, n_pairs_total):
     # fallback: CPU oracle port on all host cores, bounded sample
     from oracle import oracle_py as O
     om = O.OracleMesh(mesh.vertices, mesh.cells)
-    v, c, sample = cpu_oracle_rate(O, om, args.level, budget_s=12.0)
+    v, c, sample = cpu_oracle_rate_from_mesh(O, om, mesh, args.level, budget_s=15.0)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": n_pairs_total / v * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "reference example mesh", "config": cfg,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": c, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
-
-
-def cpu_oracle_rate(O, om, level, budget_s=12.0):
-    """OpenMP CPU oracle on a bounded, strided sample of the regular task list (about budget_s seconds of CPU work)."""
-    import numpy as np
-    tasks = om.tasks(2)
-    probe = tasks[:: max(1, tasks.shape[0] // 20000)][:20000]
-    t0 = time.time()
-    om.run_class(2, probe, level)
-    dt = max(time.time() - t0, 1e-3)
-    n = int(min(tasks.shape[0], max(20000, probe.shape[0] * budget_s / dt)))
-    sample = tasks[:: max(1, tasks.shape[0] // n)][:n]
-    t0 = time.time()
-    om.run_class(2, np.ascontiguousarray(sample), level)
-    dt = time.time() - t0
-    return sample.shape[0] / dt, O.num_threads(), f"{sample.shape[0]} regular pairs (every {max(1, tasks.shape[0] // n)}-th task of the list), {dt:.1f} s"
 
 
 def main():
