@@ -61,3 +61,21 @@ def test_two_contexts_share_the_process_wide_quadrature(oracle):
     assert torch.equal(ra, rb)                                   # deterministic, bit-identical between contexts
     a.close()
     b.close()
+
+
+def test_results_are_bitwise_reproducible(ctx, oracle):
+    """No atomics on the value path (the reference sums refined results with FP64 atomicAdd in arbitrary order): two runs of
+    the same call give identical bits, in fixed and in adaptive mode."""
+    import torch
+    from integrator2_b200.meshio import load_fixture
+    m = load_fixture("s5m", 0.0005)
+    ctx.set_mesh(m.vertices, m.cells)
+    om = oracle.OracleMesh(m.vertices, m.cells)
+    for cls in (0, 2):
+        t = torch.as_tensor(om.tasks(cls)).cuda()
+        for level in (2, -1):
+            r1 = ctx.integrate_class(cls, t, level)
+            r2 = ctx.integrate_class(cls, t, level)
+            assert torch.equal(r1["results"], r2["results"]) and torch.equal(r1["integrals"], r2["integrals"])
+            if level < 0:
+                assert r1["stats"] == r2["stats"] and torch.equal(r1["refinements"], r2["refinements"])
