@@ -152,101 +152,141 @@ static __device__ __forceinline__ d3 gauss_point(int g, d3 A, d3 B, d3 C) {
     return p;
 }
 
+// Lane layout shared by the integrate kernels.  A task at refinement level L has 4^L children:
+//   G = min(4^L, 128) lanes cooperate on one task, each lane sums 4^L / G children;
+//   G <= 32 : the G lanes sit inside one warp (32/G tasks per warp), reduction by shuffles;
+//   G  > 32 : the lanes of one task span G/32 warps of the CTA (128/G tasks per CTA), reduction by shuffles + one
+//             pass through shared memory in warp order.  Deep adaptive rounds have few tasks with many children, so
+//             spreading a task over the whole CTA divides their serial tail by four.
+// Both reductions run in a fixed order: results are bitwise reproducible.
+struct LaneLayout {
+    int children, G, perLane;
+    __device__ explicit LaneLayout(int level) {
+        children = 1 << (2 * level);
+        G = children < kThreads ? children : kThreads;
+        perLane = children / G;
+    }
+};
+
+static __device__ __forceinline__ d4 warp_sum(d4 v, int lanes) {
+    for (int off = lanes >> 1; off > 0; off >>= 1) {
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, off);
+        v.y += __shfl_xor_sync(0xffffffffu, v.y, off);
+        v.z += __shfl_xor_sync(0xffffffffu, v.z, off);
+        v.w += __shfl_xor_sync(0xffffffffu, v.w, off);
+    }
+    return v;
+}
+
 template <int CLS, int MODE, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB)
 k_integrate(PackedMesh pm, const int *__restrict__ tasks, const int *__restrict__ list, const int *__restrict__ countDev,
             long long countHost, int level, double *__restrict__ out) {
+    __shared__ double red[kThreads / 32][4];
     const long long count = countDev ? (long long)*countDev : countHost;
-    const int children = 1 << (2 * level);
-    const int G = children < 32 ? children : 32;  // lanes that share one task
-    const int perLane = children / G;
-    const int lane = threadIdx.x & 31;
-    const int sub = lane & (G - 1);
-    const int groupsPerWarp = 32 / G;
-    const long long warpId = ((long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
-    const long long warpStride = ((long long)gridDim.x * kThreads) >> 5;
+    const LaneLayout lay(level);
+    const int G = lay.G, perLane = lay.perLane;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ng = c_ngauss;
     const int stride = pm.stride;
     const double *__restrict__ tri = pm.tri;
 
-    for (long long base = warpId * groupsPerWarp; base < count; base += warpStride * groupsPerWarp) {
-        long long r = base + lane / G;
-        const bool active = r < count;
-        if (!active) r = count - 1;   // tail lanes recompute the last task (no write): warp votes in the prologues stay full-mask
+    // per-lane partial sum of task slot `slot` over this lane's children (sub, sub + G, ...)
+    auto lane_work = [&](int slot, int sub) -> d4 {
         d4 total = {0.0, 0.0, 0.0, 0.0};
-        int slot = 0;
-        {
-            slot = list ? __ldg(list + r) : (int)r;
-            const int i = __ldg(tasks + 3 * (long long)slot), j = __ldg(tasks + 3 * (long long)slot + 1);
-            double Si = __ldg(tri + PK_S * stride + i);
-            for (int l = 0; l < level; ++l) Si *= 0.25;  // child area = parent/4 per level (exact)
+        const int i = __ldg(tasks + 3 * (long long)slot), j = __ldg(tasks + 3 * (long long)slot + 1);
+        double Si = __ldg(tri + PK_S * stride + i);
+        for (int l = 0; l < level; ++l) Si *= 0.25;  // child area = parent/4 per level (exact)
 
-            if (CLS == 2 && MODE != MATH_STRICT) {
-                TriJ T;
-                T.A = ld3(tri + PK_A * stride, stride, j); T.B = ld3(tri + PK_B * stride, stride, j); T.C = ld3(tri + PK_C * stride, stride, j);
-                T.ta = ld3(tri + PK_TA * stride, stride, j); T.tb = ld3(tri + PK_TB * stride, stride, j); T.tc = ld3(tri + PK_TC * stride, stride, j);
-                T.Nu = ld3(tri + PK_NU * stride, stride, j);
-                double s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;  // sums over children of S_child * sum_g w_g (t1,t2,t3,theta)
-                for (int k = 0; k < perLane; ++k) {
-                    // control-panel vertices are re-read per child (L1-resident) to keep them out of the live register set
-                    d3 A = ld3(tri + PK_A * stride, stride, i), B = ld3(tri + PK_B * stride, stride, i), C = ld3(tri + PK_C * stride, stride, i);
-                    descend(A, B, C, level, sub + G * k);
-                    double a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0;
+        if (CLS == 2 && MODE != MATH_STRICT) {
+            TriJ T;
+            T.A = ld3(tri + PK_A * stride, stride, j); T.B = ld3(tri + PK_B * stride, stride, j); T.C = ld3(tri + PK_C * stride, stride, j);
+            T.ta = ld3(tri + PK_TA * stride, stride, j); T.tb = ld3(tri + PK_TB * stride, stride, j); T.tc = ld3(tri + PK_TC * stride, stride, j);
+            T.Nu = ld3(tri + PK_NU * stride, stride, j);
+            double s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;  // sums over children of S_child * sum_g w_g (t1,t2,t3,theta)
+            for (int k = 0; k < perLane; ++k) {
+                // control-panel vertices are re-read per child (L1-resident) to keep them out of the live register set
+                d3 A = ld3(tri + PK_A * stride, stride, i), B = ld3(tri + PK_B * stride, stride, i), C = ld3(tri + PK_C * stride, stride, i);
+                descend(A, B, C, level, sub + G * k);
+                double a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0;
 #pragma unroll 1
-                    for (int g = 0; g < ng; ++g) {
-                        const LogTheta v = theta_psi_fast<MODE == MATH_FAST_POINTWISE>(gauss_point(g, A, B, C), T);
-                        const double w = c_gauss[4 * g + 3];
-                        a1 = fma(w, v.t1, a1); a2 = fma(w, v.t2, a2); a3 = fma(w, v.t3, a3); a4 = fma(w, v.theta, a4);
-                    }
-                    s1 = fma(Si, a1, s1); s2 = fma(Si, a2, s2); s3 = fma(Si, a3, s3); s4 = fma(Si, a4, s4);
+                for (int g = 0; g < ng; ++g) {
+                    const LogTheta v = theta_psi_fast<MODE == MATH_FAST_POINTWISE>(gauss_point(g, A, B, C), T);
+                    const double w = c_gauss[4 * g + 3];
+                    a1 = fma(w, v.t1, a1); a2 = fma(w, v.t2, a2); a3 = fma(w, v.t3, a3); a4 = fma(w, v.theta, a4);
                 }
-                const d3 psi = s1 * T.tc + s2 * T.ta + s3 * T.tb;
-                total = vec4(psi, s4);
-            } else {
-                const d3 JA = ld3(tri + PK_A * stride, stride, j), JB = ld3(tri + PK_B * stride, stride, j), JC = ld3(tri + PK_C * stride, stride, j);
-                EdgeSingular es;
-                VertexSingular vs;
-                if (CLS == 1) {
-                    int si, sj;
-                    shifts_edge(ldtri(pm.cells, i), ldtri(pm.cells, j), si, sj);
-                    const d3 RA = sj == 0 ? JA : (sj == 1 ? JB : JC), RB = sj == 0 ? JB : (sj == 1 ? JC : JA), RC = sj == 0 ? JC : (sj == 1 ? JA : JB);
-                    es.init(RA, RB, RC);
-                }
-                if (CLS == 0) {
-                    int si, sj;
-                    shifts_vertex(ldtri(pm.cells, i), ldtri(pm.cells, j), si, sj);
-                    const d3 RA = sj == 0 ? JA : (sj == 1 ? JB : JC), RB = sj == 0 ? JB : (sj == 1 ? JC : JA), RC = sj == 0 ? JC : (sj == 1 ? JA : JB);
-                    vs.init(RA, RB, RC, ld3(tri + PK_N * stride, stride, i), ld3(tri + PK_N * stride, stride, j), __ldg(tri + PK_S * stride + i));
-                }
-                for (int k = 0; k < perLane; ++k) {
-                    // control-panel vertices are re-read per child (L1-resident) to keep them out of the live register set
-                    d3 A = ld3(tri + PK_A * stride, stride, i), B = ld3(tri + PK_B * stride, stride, i), C = ld3(tri + PK_C * stride, stride, i);
-                    descend(A, B, C, level, sub + G * k);
-                    d4 acc = {0.0, 0.0, 0.0, 0.0};
+                s1 = fma(Si, a1, s1); s2 = fma(Si, a2, s2); s3 = fma(Si, a3, s3); s4 = fma(Si, a4, s4);
+            }
+            const d3 psi = s1 * T.tc + s2 * T.ta + s3 * T.tb;
+            total = vec4(psi, s4);
+        } else {
+            const d3 JA = ld3(tri + PK_A * stride, stride, j), JB = ld3(tri + PK_B * stride, stride, j), JC = ld3(tri + PK_C * stride, stride, j);
+            EdgeSingular es;
+            VertexSingular vs;
+            if (CLS == 1) {
+                int si, sj;
+                shifts_edge(ldtri(pm.cells, i), ldtri(pm.cells, j), si, sj);
+                const d3 RA = sj == 0 ? JA : (sj == 1 ? JB : JC), RB = sj == 0 ? JB : (sj == 1 ? JC : JA), RC = sj == 0 ? JC : (sj == 1 ? JA : JB);
+                es.init(RA, RB, RC);
+            }
+            if (CLS == 0) {
+                int si, sj;
+                shifts_vertex(ldtri(pm.cells, i), ldtri(pm.cells, j), si, sj);
+                const d3 RA = sj == 0 ? JA : (sj == 1 ? JB : JC), RB = sj == 0 ? JB : (sj == 1 ? JC : JA), RC = sj == 0 ? JC : (sj == 1 ? JA : JB);
+                vs.init(RA, RB, RC, ld3(tri + PK_N * stride, stride, i), ld3(tri + PK_N * stride, stride, j), __ldg(tri + PK_S * stride + i));
+            }
+            for (int k = 0; k < perLane; ++k) {
+                d3 A = ld3(tri + PK_A * stride, stride, i), B = ld3(tri + PK_B * stride, stride, i), C = ld3(tri + PK_C * stride, stride, i);
+                descend(A, B, C, level, sub + G * k);
+                d4 acc = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
-                    for (int g = 0; g < ng; ++g) {
-                        const d3 M = gauss_point(g, A, B, C);
-                        d4 f = theta_psi_strict(M, JA, JB, JC);
-                        if (CLS == 1) f = f - es.at(M);
-                        if (CLS == 0) f = f - vs.at(M);
-                        const double w = c_gauss[4 * g + 3];
-                        acc.x = fma(w, f.x, acc.x); acc.y = fma(w, f.y, acc.y); acc.z = fma(w, f.z, acc.z); acc.w = fma(w, f.w, acc.w);
-                    }
-                    total = total + Si * acc;
+                for (int g = 0; g < ng; ++g) {
+                    const d3 M = gauss_point(g, A, B, C);
+                    d4 f = theta_psi_strict(M, JA, JB, JC);
+                    if (CLS == 1) f = f - es.at(M);
+                    if (CLS == 0) f = f - vs.at(M);
+                    const double w = c_gauss[4 * g + 3];
+                    acc.x = fma(w, f.x, acc.x); acc.y = fma(w, f.y, acc.y); acc.z = fma(w, f.z, acc.z); acc.w = fma(w, f.w, acc.w);
                 }
+                total = total + Si * acc;
             }
         }
-        // deterministic tree reduction over the G lanes of the task
-        for (int off = G >> 1; off > 0; off >>= 1) {
-            total.x += __shfl_xor_sync(0xffffffffu, total.x, off);
-            total.y += __shfl_xor_sync(0xffffffffu, total.y, off);
-            total.z += __shfl_xor_sync(0xffffffffu, total.z, off);
-            total.w += __shfl_xor_sync(0xffffffffu, total.w, off);
+        return total;
+    };
+    auto store = [&](int slot, d4 total) {
+        double2 *o = reinterpret_cast<double2 *>(out + 4 * (long long)slot);
+        o[0] = make_double2(total.x, total.y);
+        o[1] = make_double2(total.z, total.w);
+    };
+
+    if (G <= 32) {
+        const int groupsPerWarp = 32 / G, sub = lane & (G - 1);
+        const long long warpId = ((long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
+        const long long warpStride = ((long long)gridDim.x * kThreads) >> 5;
+        for (long long base = warpId * groupsPerWarp; base < count; base += warpStride * groupsPerWarp) {
+            long long r = base + lane / G;
+            const bool active = r < count;
+            if (!active) r = count - 1;   // tail lanes recompute the last task (no write): warp votes in the prologues stay full-mask
+            const int slot = list ? __ldg(list + r) : (int)r;
+            const d4 total = warp_sum(lane_work(slot, sub), G);
+            if (active && sub == 0) store(slot, total);
         }
-        if (active && sub == 0) {
-            double2 *o = reinterpret_cast<double2 *>(out + 4 * (long long)slot);
-            o[0] = make_double2(total.x, total.y);
-            o[1] = make_double2(total.z, total.w);
+    } else {
+        const int tasksPerCTA = kThreads / G, sub = threadIdx.x & (G - 1), tIdx = threadIdx.x / G, warpsPerTask = G / 32;
+        for (long long base = (long long)blockIdx.x * tasksPerCTA; base < count; base += (long long)gridDim.x * tasksPerCTA) {
+            long long r = base + tIdx;
+            const bool active = r < count;
+            if (!active) r = count - 1;
+            const int slot = list ? __ldg(list + r) : (int)r;
+            const d4 part = warp_sum(lane_work(slot, sub), 32);
+            if (lane == 0) { red[warp][0] = part.x; red[warp][1] = part.y; red[warp][2] = part.z; red[warp][3] = part.w; }
+            __syncthreads();
+            if (active && sub == 0) {
+                d4 total = {0.0, 0.0, 0.0, 0.0};
+                for (int w = 0; w < warpsPerTask; ++w) { total.x += red[warp + w][0]; total.y += red[warp + w][1]; total.z += red[warp + w][2]; total.w += red[warp + w][3]; }
+                store(slot, total);
+            }
+            __syncthreads();
         }
     }
 }
@@ -313,44 +353,25 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
     const long long count = countDev ? (long long)*countDev : countHost;
     constexpr bool EDGELEN = (VAR & 1) != 0, RESID = (VAR & 2) == 0, LEVEL0 = (VAR & 4) != 0, DERIVE = (VAR & 8) != 0 && EDGELEN;
     if (LEVEL0) level = 0;
-    const int children = 1 << (2 * level);
-    const int G = children < 32 ? children : 32;
-    const int perLane = children / G;
-    const int lane = threadIdx.x & 31;
-    const int sub = lane & (G - 1);
-    const int groupsPerWarp = 32 / G;
-    const long long warpId = ((long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
-    const long long warpStride = ((long long)gridDim.x * kThreads) >> 5;
+    const LaneLayout lay(level);
+    const int G = lay.G, perLane = lay.perLane;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ng = c_ngauss;
     const int stride = pm.stride;
     const double *__restrict__ tri = pm.tri;
     double *myM = smM + threadIdx.x;
+    __shared__ double red[kThreads / 32][4];
 
-    // A warp walks a contiguous chunk of kChunkIters x 32 tasks: lists are sorted by control panel i, so a lane meets the
-    // same i (and the same child) in consecutive iterations and its staged Gauss points are reused (13 x 9 FP64 per task
-    // saved); chunks are dealt round-robin to the warps of the grid.
-    constexpr int kChunkIters = 16;
-    const long long chunkTasks = (long long)groupsPerWarp * kChunkIters;
-    int iStaged = -1;
-    for (long long chunk = warpId; chunk * chunkTasks < count; chunk += warpStride)
-    for (int it = 0; it < kChunkIters; ++it) {
-        const long long base = chunk * chunkTasks + (long long)it * groupsPerWarp;
-        if (base >= count) break;
-        long long r = base + lane / G;
-        const bool active = r < count;
-        if (!active) r = count - 1;   // tail lanes recompute the last task (no write) so that warp votes stay full-mask
-        const int slot = list ? __ldg(list + r) : (int)r;
-        const int i = __ldg(tasks + 3 * (long long)slot), j = __ldg(tasks + 3 * (long long)slot + 1);
+    // per-lane partial (Psi, Theta) of task (i, j) over this lane's children; iStaged remembers whose Gauss points sit in smem
+    auto lane_work = [&](int i, int j, int sub, int &iStaged) -> d4 {
         double Si = __ldg(tri + PK_S * stride + i);
         for (int l = 0; l < level; ++l) Si *= 0.25;
-
         TriJ T;
         T.A = ld3(tri + PK_A * stride, stride, j);
         if (!DERIVE) { T.B = ld3(tri + PK_B * stride, stride, j); T.C = ld3(tri + PK_C * stride, stride, j); }
         T.ta = ld3(tri + PK_TA * stride, stride, j); T.tb = ld3(tri + PK_TB * stride, stride, j); T.tc = ld3(tri + PK_TC * stride, stride, j);
         T.Nu = ld3(tri + PK_NU * stride, stride, j);
         if (EDGELEN) { const d3 L = ld3(tri + PK_L * stride, stride, j); T.La = L.x; T.Lb = L.y; T.Lc = L.z; }
-
         double s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;
         for (int k = 0; k < perLane; ++k) {
             if (perLane > 1 || i != iStaged) {
@@ -368,21 +389,59 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
             if (LEVEL0) { s1 = Si * a1; s2 = Si * a2; s3 = Si * a3; s4 = Si * a4; }
             else { s1 = fma(Si, a1, s1); s2 = fma(Si, a2, s2); s3 = fma(Si, a3, s3); s4 = fma(Si, a4, s4); }
         }
-        d4 total = vec4(s1 * T.tc + s2 * T.ta + s3 * T.tb, s4);
-        for (int off = G >> 1; off > 0; off >>= 1) {
-            total.x += __shfl_xor_sync(0xffffffffu, total.x, off);
-            total.y += __shfl_xor_sync(0xffffffffu, total.y, off);
-            total.z += __shfl_xor_sync(0xffffffffu, total.z, off);
-            total.w += __shfl_xor_sync(0xffffffffu, total.w, off);
+        return vec4(s1 * T.tc + s2 * T.ta + s3 * T.tb, s4);
+    };
+    auto store = [&](int slot, int j, d4 total) {
+        double2 *o = reinterpret_cast<double2 *>(out + 4 * (long long)slot);
+        o[0] = make_double2(total.x, total.y);
+        o[1] = make_double2(total.z, total.w);
+        if (results) {   // fixed level: final assembly fused (no second pass over the integrals)
+            const d3 J = assemble_J(total, ld3(tri + PK_N * stride, stride, j), 0.0, false);
+            results[3 * (long long)slot] = J.x; results[3 * (long long)slot + 1] = J.y; results[3 * (long long)slot + 2] = J.z;
         }
-        if (active && sub == 0) {
-            double2 *o = reinterpret_cast<double2 *>(out + 4 * (long long)slot);
-            o[0] = make_double2(total.x, total.y);
-            o[1] = make_double2(total.z, total.w);
-            if (results) {   // fixed level: final assembly fused (no second pass over the integrals)
-                const d3 J = assemble_J(total, ld3(tri + PK_N * stride, stride, j), 0.0, false);
-                results[3 * (long long)slot] = J.x; results[3 * (long long)slot + 1] = J.y; results[3 * (long long)slot + 2] = J.z;
+    };
+
+    if (G <= 32) {
+        // A warp walks a contiguous chunk of kChunkIters x (32/G) tasks: lists are sorted by control panel i, so a lane meets
+        // the same i (and the same child) in consecutive iterations and its staged Gauss points are reused (13 x 9 FP64 per
+        // task saved); chunks are dealt round-robin to the warps of the grid.
+        constexpr int kChunkIters = 16;
+        const int groupsPerWarp = 32 / G, sub = lane & (G - 1);
+        const long long warpId = ((long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
+        const long long warpStride = ((long long)gridDim.x * kThreads) >> 5;
+        const long long chunkTasks = (long long)groupsPerWarp * kChunkIters;
+        int iStaged = -1;
+        for (long long chunk = warpId; chunk * chunkTasks < count; chunk += warpStride)
+            for (int it = 0; it < kChunkIters; ++it) {
+                const long long base = chunk * chunkTasks + (long long)it * groupsPerWarp;
+                if (base >= count) break;
+                long long r = base + lane / G;
+                const bool active = r < count;
+                if (!active) r = count - 1;   // tail lanes recompute the last task (no write) so that warp votes stay full-mask
+                const int slot = list ? __ldg(list + r) : (int)r;
+                const int i = __ldg(tasks + 3 * (long long)slot), j = __ldg(tasks + 3 * (long long)slot + 1);
+                const d4 total = warp_sum(lane_work(i, j, sub, iStaged), G);
+                if (active && sub == 0) store(slot, j, total);
             }
+    } else {
+        // deep refinement: the lanes of one task span G/32 warps of the CTA (see LaneLayout)
+        const int tasksPerCTA = kThreads / G, sub = threadIdx.x & (G - 1), tIdx = threadIdx.x / G, warpsPerTask = G / 32;
+        for (long long base = (long long)blockIdx.x * tasksPerCTA; base < count; base += (long long)gridDim.x * tasksPerCTA) {
+            long long r = base + tIdx;
+            const bool active = r < count;
+            if (!active) r = count - 1;
+            const int slot = list ? __ldg(list + r) : (int)r;
+            const int i = __ldg(tasks + 3 * (long long)slot), j = __ldg(tasks + 3 * (long long)slot + 1);
+            int iStaged = -1;
+            const d4 part = warp_sum(lane_work(i, j, sub, iStaged), 32);
+            if (lane == 0) { red[warp][0] = part.x; red[warp][1] = part.y; red[warp][2] = part.z; red[warp][3] = part.w; }
+            __syncthreads();
+            if (active && sub == 0) {
+                d4 total = {0.0, 0.0, 0.0, 0.0};
+                for (int w = 0; w < warpsPerTask; ++w) { total.x += red[warp + w][0]; total.y += red[warp + w][1]; total.z += red[warp + w][2]; total.w += red[warp + w][3]; }
+                store(slot, j, total);
+            }
+            __syncthreads();
         }
     }
 }
@@ -505,7 +564,7 @@ void launch_integrate(int cls, int mathMode, const PackedMesh &pm, const int *ta
                       long long countHost, int level, double *out4, double *fusedResults3, int numSMs, cudaStream_t s) {
     if (!countDev && countHost <= 0) return;
     const int children = 1 << (2 * level);
-    const int G = children < 32 ? children : 32;
+    const int G = children < kThreads ? children : kThreads;   // LaneLayout
     long long blocks;
     const long long persistent = (long long)numSMs * 4 * 8;  // a few waves of 4 CTAs/SM; the kernel grid-strides
     if (countDev) blocks = persistent;

@@ -246,3 +246,18 @@ def test_regular_pairs_scale_invariance(ctx, oracle, scale):
     scaled = ctx.integrate_class(2, tasks, 1)["results"].cpu().numpy()
     rel = np.abs(scaled / scale ** 2 - base).sum(1) / np.abs(base).sum(1)
     assert np.isfinite(scaled).all() and rel.max() < 1e-12, (scale, rel.max())
+
+
+@pytest.mark.parametrize("level", [4, 5])
+def test_deep_fixed_levels_all_classes_G1(ctx, oracle, level):
+    """Levels 4 and 5 (256 / 1024 children per task): the lanes of one task span the whole CTA (LaneLayout, G = 128),
+    partial sums meet in shared memory in warp order."""
+    import torch
+    m, om = _setup(ctx, oracle, "G1")
+    for cls in (0, 1, 2):
+        tasks = om.tasks(cls)[:: (1 if cls < 2 else 8)]
+        tasks = np.ascontiguousarray(tasks)
+        r = ctx.integrate_class(cls, torch.as_tensor(tasks).cuda(), level)
+        ref = om.run_class(cls, tasks, level)
+        rel = np.abs(r["results"].cpu().numpy() - ref["results"]).sum(1) / np.abs(ref["results"]).sum(1)
+        assert rel.max() < 2e-12, (cls, level, rel.max())

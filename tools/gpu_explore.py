@@ -43,6 +43,7 @@ if what == "time":
     print(json.dumps(out))
 elif what == "adaptive":
     for cls in (0, 1, 2):
+        ctx.integrate_class(cls, tasks[cls], -1)     # warm-up (allocations, kernel images)
         torch.cuda.synchronize()
         t0 = time.time()
         r = ctx.integrate_class(cls, tasks[cls], -1)
