@@ -294,7 +294,7 @@ k_integrate(PackedMesh pm, const int *__restrict__ tasks, const int *__restrict_
 // Grouped evaluation of one (child) control panel against triangle T: on return a1..a3 = sum_g w_g ln(N/D) per edge,
 // a4 = sum_g w_g Theta_g.  myM points at this thread's staged Gauss points ([point][component], stride kThreads).
 // Must be called by all 32 lanes of a warp (one __all_sync per group of equal weights).
-template <bool EDGELEN, bool RESID, bool DERIVE = false>
+template <bool EDGELEN, bool RESID, bool DERIVE = false, bool PROJ = false>
 static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, const TriJ &T, double &a1, double &a2, double &a3, double &a4) {
     a1 = 0.0; a2 = 0.0; a3 = 0.0; a4 = 0.0;
     double pn1 = 1.0, pd1 = 1.0, pn2 = 1.0, pd2 = 1.0, pn3 = 1.0, pd3 = 1.0, zr = 1.0, zi = 0.0;
@@ -303,7 +303,14 @@ static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, c
 #pragma unroll 1
     for (int g = 0; g < ng; ++g) {
         const d3 M = {myM[(3 * g + 0) * kThreads], myM[(3 * g + 1) * kThreads], myM[(3 * g + 2) * kThreads]};
-        PointTerms t = point_terms_raw<EDGELEN, DERIVE>(M, T);
+        PointTerms t;
+        if (PROJ) {
+            bool nearVertex;
+            t = point_terms_proj(M, T, &nearVertex);
+            if (__any_sync(0xffffffffu, nearVertex)) t = point_terms_raw<true, true>(M, T);   // rare: keep full accuracy next to a vertex
+        } else {
+            t = point_terms_raw<EDGELEN, DERIVE>(M, T);
+        }
         if (__any_sync(0xffffffffu, eps_screen(t))) eps_fixup(t);   // warp-uniform; the screen runs on the integer pipe
         pn1 *= t.N1; pd1 *= t.D1; pn2 *= t.N2; pd2 *= t.D2; pn3 *= t.N3; pd3 *= t.D3;
         const double nr = fma(zr, t.den, -(zi * t.num)), ni = fma(zr, t.num, zi * t.den);
@@ -311,12 +318,21 @@ static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, c
         safe = safe && angle_small(t);
         if (c_groupEnd[g]) {
             const double w = c_gauss[4 * g + 3];
-            a1 = fma(w, log_ratio<RESID>(pn1, pd1), a1);
-            a2 = fma(w, log_ratio<RESID>(pn2, pd2), a2);
-            a3 = fma(w, log_ratio<RESID>(pn3, pd3), a3);
+            // far-field shortcut, taken by the whole warp: all three ratios within [1/sqrt2, sqrt2] -> no mantissa surgery
+            const double sa = pn1 + pd1, da_ = pn1 - pd1, sb = pn2 + pd2, db_ = pn2 - pd2, sc_ = pn3 + pd3, dc_ = pn3 - pd3;
+            if (__all_sync(0xffffffffu, ratio_near1(sa, da_) && ratio_near1(sb, db_) && ratio_near1(sc_, dc_))) {
+                a1 = fma(w, log_ratio_near1<RESID>(sa, da_), a1);
+                a2 = fma(w, log_ratio_near1<RESID>(sb, db_), a2);
+                a3 = fma(w, log_ratio_near1<RESID>(sc_, dc_), a3);
+            } else {
+                a1 = fma(w, log_ratio<RESID>(pn1, pd1), a1);
+                a2 = fma(w, log_ratio<RESID>(pn2, pd2), a2);
+                a3 = fma(w, log_ratio<RESID>(pn3, pd3), a3);
+            }
             double th;
             if (__all_sync(0xffffffffu, safe)) {
-                th = atan2_fast<RESID>(zi, zr);
+                if (__all_sync(0xffffffffu, angle_tiny(zi, zr))) th = atan2_small<RESID>(zi, zr);
+                else th = atan2_fast<RESID>(zi, zr);
             } else {  // some lane of the warp sees triangle j under a large solid angle: add the angles one by one
                 th = 0.0;
                 for (int h = gStart; h <= g; ++h) {
@@ -352,6 +368,7 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
     __shared__ double smM[MAX_GAUSS_POINTS * 3 * kThreads];
     const long long count = countDev ? (long long)*countDev : countHost;
     constexpr bool EDGELEN = (VAR & 1) != 0, RESID = (VAR & 2) == 0, LEVEL0 = (VAR & 4) != 0, DERIVE = (VAR & 8) != 0 && EDGELEN;
+    constexpr bool PROJ = (VAR & 16) != 0 && DERIVE;
     if (LEVEL0) level = 0;
     const LaneLayout lay(level);
     const int G = lay.G, perLane = lay.perLane;
@@ -372,6 +389,7 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
         T.ta = ld3(tri + PK_TA * stride, stride, j); T.tb = ld3(tri + PK_TB * stride, stride, j); T.tc = ld3(tri + PK_TC * stride, stride, j);
         T.Nu = ld3(tri + PK_NU * stride, stride, j);
         if (EDGELEN) { const d3 L = ld3(tri + PK_L * stride, stride, j); T.La = L.x; T.Lb = L.y; T.Lc = L.z; }
+        if (PROJ) { T.c1 = T.Lc * dot(T.tc, T.ta); T.c2 = T.Lc * T.Lb * dot(T.tc, T.tb); }
         double s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;
         for (int k = 0; k < perLane; ++k) {
             if (perLane > 1 || i != iStaged) {
@@ -385,7 +403,7 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
                 iStaged = perLane > 1 ? -1 : i;
             }
             double a1, a2, a3, a4;
-            grouped_eval<EDGELEN, RESID, DERIVE>(myM, ng, T, a1, a2, a3, a4);
+            grouped_eval<EDGELEN, RESID, DERIVE, PROJ>(myM, ng, T, a1, a2, a3, a4);
             if (LEVEL0) { s1 = Si * a1; s2 = Si * a2; s3 = Si * a3; s4 = Si * a4; }
             else { s1 = fma(Si, a1, s1); s2 = fma(Si, a2, s2); s3 = fma(Si, a3, s3); s4 = fma(Si, a4, s4); }
         }
@@ -516,8 +534,9 @@ k_apply_regular(PackedMesh pm, int rowLo, int rowHi, int colLo, int colHi, int c
             T.ta = {t[9], t[10], t[11]}; T.tb = {t[12], t[13], t[14]}; T.tc = {t[15], t[16], t[17]};
             T.Nu = {t[18], t[19], t[20]};
             T.La = t[21]; T.Lb = t[22]; T.Lc = t[23];
+            T.c1 = T.Lc * dot(T.tc, T.ta); T.c2 = T.Lc * T.Lb * dot(T.tc, T.tb);
             double a1, a2, a3, a4;
-            grouped_eval<true, false, true>(myM, ng, T, a1, a2, a3, a4);
+            grouped_eval<true, false, true, true>(myM, ng, T, a1, a2, a3, a4);
             const int ja = smId[3 * jj], jb = smId[3 * jj + 1], jc = smId[3 * jj + 2];
             const bool skip = (tile + jj == i) || ci.a == ja || ci.a == jb || ci.a == jc || ci.b == ja || ci.b == jb || ci.b == jc ||
                               ci.c == ja || ci.c == jb || ci.c == jc;
@@ -558,7 +577,7 @@ void launch_apply_regular(const PackedMesh &pm, int rowLo, int rowHi, int colLo,
 
 // tuning knob (env I2_MINBLOCKS = 3|4|5): resident CTAs per SM the regular kernel is compiled for
 static int g_minBlocks = [] { const char *e = getenv("I2_MINBLOCKS"); return e ? atoi(e) : 4; }();
-static int g_variant = [] { const char *e = getenv("I2_VARIANT"); return e ? atoi(e) : 11; }();
+static int g_variant = [] { const char *e = getenv("I2_VARIANT"); return e ? atoi(e) : 27; }();
 
 void launch_integrate(int cls, int mathMode, const PackedMesh &pm, const int *tasks, const int *list, const int *countDev,
                       long long countHost, int level, double *out4, double *fusedResults3, int numSMs, cudaStream_t s) {
@@ -580,9 +599,9 @@ void launch_integrate(int cls, int mathMode, const PackedMesh &pm, const int *ta
     else if (mathMode == MATH_FAST_POINTWISE) { ++g_launchCount; k_integrate<2, MATH_FAST_POINTWISE, 4><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4); }
     else {
         // tuning knobs: I2_MINBLOCKS (3|4|5 resident CTAs/SM), I2_VARIANT (bit0 edge-length identity, bit1 no residual correction,
-        // bit3 derive d_b, d_c from d_a instead of reading B and C; default 11 = all three);
+        // bit3 derive d_b, d_c from d_a instead of reading B and C, bit4 projection form of the lengths/dots; default 27 = all);
         // the LEVEL0 specialisation (bit 2) is chosen automatically
-        const int var = (g_variant & 3) | (level == 0 ? 4 : 0) | (g_variant & 8);
+        const int var = (g_variant & 3) | (level == 0 ? 4 : 0) | (g_variant & 24);
         ++g_launchCount;
 #define I2_LAUNCH_GROUPED(MB, V) k_regular_grouped<MB, V><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4, fusedResults3)
 #define I2_PICK_VAR(MB)                                                                                              \
@@ -592,6 +611,7 @@ void launch_integrate(int cls, int mathMode, const PackedMesh &pm, const int *ta
         case 4: I2_LAUNCH_GROUPED(MB, 4); break; case 5: I2_LAUNCH_GROUPED(MB, 5); break;                       \
         case 6: I2_LAUNCH_GROUPED(MB, 6); break; case 7: I2_LAUNCH_GROUPED(MB, 7); break;                       \
         case 11: I2_LAUNCH_GROUPED(MB, 11); break; case 15: I2_LAUNCH_GROUPED(MB, 15); break;                   \
+        case 27: I2_LAUNCH_GROUPED(MB, 27); break; case 31: I2_LAUNCH_GROUPED(MB, 31); break;                   \
         default: I2_LAUNCH_GROUPED(MB, 7); break;                                                                \
         }
         if (g_minBlocks == 3) { I2_PICK_VAR(3) }
@@ -612,8 +632,8 @@ cudaError_t preload_kernels() {
 #define I2_TOUCH(...) do { e = cudaFuncGetAttributes(&a, (const void *)(__VA_ARGS__)); if (e != cudaSuccess) return e; } while (0)
     I2_TOUCH(k_integrate<0, MATH_STRICT, 3>);
     I2_TOUCH(k_integrate<1, MATH_STRICT, 3>);
-    I2_TOUCH(k_regular_grouped<4, 15>);
-    I2_TOUCH(k_regular_grouped<4, 11>);
+    I2_TOUCH(k_regular_grouped<4, 31>);
+    I2_TOUCH(k_regular_grouped<4, 27>);
     I2_TOUCH(k_apply_regular<4>);
 #undef I2_TOUCH
     return cudaSuccess;

@@ -135,6 +135,52 @@ I2_HD double log_ratio(double N, double D) {
     return fma(ed, I2_K(19), fma(ed, I2_K(20), lg));   // ln2 split hi/lo
 }
 
+// Far-field shortcuts, used when a whole warp qualifies (the caller votes):
+//   log_ratio_near1: N/D within [1/sqrt2, sqrt2] — f = (N-D)/(N+D) is scale invariant, so no exponent / mantissa surgery;
+//   atan2_small    : x > 0 and |y| < x/8 — no octant logic, no argument reduction.
+// Same series, same accuracy as the general versions; they only drop the integer-pipe bookkeeping (~20 issue slots each).
+I2_HD bool ratio_near1(double s, double d) { return fabs(d) <= 0.1715 * s; }   // s = N + D > 0, d = N - D
+template <bool RESID = true>
+I2_HD double log_ratio_near1(double s, double d) {
+    const double r = fast_rcp(s);
+    double f = d * r;
+    if (RESID) f = fma(fma(-f, s, d), r, f);
+    const double z = f * f;
+    double p = I2_K(9);
+    p = fma(p, z, I2_K(8));
+    p = fma(p, z, I2_K(7));
+    p = fma(p, z, I2_K(6));
+    p = fma(p, z, I2_K(5));
+    p = fma(p, z, I2_K(4));
+    p = fma(p, z, I2_K(3));
+    p = fma(p, z, I2_K(2));
+    p = fma(p, z, I2_K(1));
+    p = fma(p, z, I2_K(0));
+    return fma(f * z, p, f + f);
+}
+// positive doubles order like their bit patterns: "high word of |y| below the high word of x/8" (conservative in the low word)
+I2_HD bool angle_tiny(double y, double x) {
+    const int hx = hi_word(x);
+    return (hx > 0) & ((hi_word(y) & 0x7fffffff) < hx - (3 << 20));
+}
+template <bool RESID = true>
+I2_HD double atan2_small(double y, double x) {
+    const double r = fast_rcp(x);
+    double t = y * r;
+    if (RESID) t = fma(fma(-t, x, y), r, t);
+    const double z = t * t;
+    double p = I2_K(18);
+    p = fma(p, z, I2_K(17));
+    p = fma(p, z, I2_K(16));
+    p = fma(p, z, I2_K(15));
+    p = fma(p, z, I2_K(14));
+    p = fma(p, z, I2_K(13));
+    p = fma(p, z, I2_K(12));
+    p = fma(p, z, I2_K(11));
+    p = fma(p, z, I2_K(10));
+    return fma(t * z, p, t);
+}
+
 // atan2(y, x) for finite arguments, not both zero.  t = min/max in [0,1]; c = nearest of {0, 1/4, 1/2, 3/4, 1};
 // atan t = atan c + atan((t-c)/(1+tc)) = atan c + atan((mn - c mx)/(mx + c mn)), |arg| <= 0.1244: odd series to ^19.
 template <bool RESID = true>

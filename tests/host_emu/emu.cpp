@@ -19,6 +19,7 @@ static TriJ make_tri(const double *v, const int *cells, int j) {
     T.ta = unit(T.C - T.B); T.tb = unit(T.A - T.C); T.tc = unit(T.B - T.A);
     T.Nu = cross(T.B - T.A, T.C - T.A);
     T.La = norm(T.C - T.B); T.Lb = norm(T.A - T.C); T.Lc = norm(T.B - T.A);
+    T.c1 = T.Lc * dot(T.tc, T.ta); T.c2 = T.Lc * T.Lb * dot(T.tc, T.tb);
     return T;
 }
 
@@ -63,7 +64,9 @@ void emu_regular(const double *v, const int *cells, const double *measures, cons
             bool safe = true;
             int gStart = 0;
             for (int g = 0; g < g_n; ++g) {
-                PointTerms t = (var & 4) ? point_terms_raw<true, true>(gp(g, I.A, I.B, I.C), T) : ((var & 1) ? point_terms_raw<true>(gp(g, I.A, I.B, I.C), T) : point_terms_raw<false>(gp(g, I.A, I.B, I.C), T));
+                bool nearV = false;
+                PointTerms t = (var & 8) ? point_terms_proj(gp(g, I.A, I.B, I.C), T, &nearV) : (var & 4) ? point_terms_raw<true, true>(gp(g, I.A, I.B, I.C), T) : ((var & 1) ? point_terms_raw<true>(gp(g, I.A, I.B, I.C), T) : point_terms_raw<false>(gp(g, I.A, I.B, I.C), T));
+                if (nearV) t = point_terms_raw<true, true>(gp(g, I.A, I.B, I.C), T);
                 if (eps_screen(t)) eps_fixup(t);
                 pn1 *= t.N1; pd1 *= t.D1; pn2 *= t.N2; pd2 *= t.D2; pn3 *= t.N3; pd3 *= t.D3;
                 const double nr = fma(zr, t.den, -(zi * t.num)), ni = fma(zr, t.num, zi * t.den);
@@ -72,10 +75,13 @@ void emu_regular(const double *v, const int *cells, const double *measures, cons
                 const bool last = (g == g_n - 1) || (g_w[g + 1] != g_w[g]) || (g - gStart == 5);
                 if (last) {
                     const double w = g_w[g];
-                    if (var & 2) { a1 = fma(w, log_ratio<false>(pn1, pd1), a1); a2 = fma(w, log_ratio<false>(pn2, pd2), a2); a3 = fma(w, log_ratio<false>(pn3, pd3), a3); }
+                    const double sa = pn1 + pd1, da_ = pn1 - pd1, sb = pn2 + pd2, db_ = pn2 - pd2, sc_ = pn3 + pd3, dc_ = pn3 - pd3;
+                    if ((var & 8) && ratio_near1(sa, da_) && ratio_near1(sb, db_) && ratio_near1(sc_, dc_)) { a1 = fma(w, log_ratio_near1<false>(sa, da_), a1); a2 = fma(w, log_ratio_near1<false>(sb, db_), a2); a3 = fma(w, log_ratio_near1<false>(sc_, dc_), a3); }
+                    else if (var & 2) { a1 = fma(w, log_ratio<false>(pn1, pd1), a1); a2 = fma(w, log_ratio<false>(pn2, pd2), a2); a3 = fma(w, log_ratio<false>(pn3, pd3), a3); }
                     else { a1 = fma(w, log_ratio<true>(pn1, pd1), a1); a2 = fma(w, log_ratio<true>(pn2, pd2), a2); a3 = fma(w, log_ratio<true>(pn3, pd3), a3); }
                     double th;
-                    if (safe) th = (var & 2) ? atan2_fast<false>(zi, zr) : atan2_fast<true>(zi, zr);
+                    if (safe && (var & 8) && angle_tiny(zi, zr)) th = atan2_small<false>(zi, zr);
+                    else if (safe) th = (var & 2) ? atan2_fast<false>(zi, zr) : atan2_fast<true>(zi, zr);
                     else { th = 0; for (int h = gStart; h <= g; ++h) { const PointTerms u = point_terms(gp(h, I.A, I.B, I.C), T); th += atan2_fast(u.num, u.den); } }
                     a4 = fma(w, th + th, a4);
                     pn1 = pd1 = pn2 = pd2 = pn3 = pd3 = zr = 1.0; zi = 0.0; safe = true; gStart = g + 1;

@@ -55,8 +55,20 @@ def test_apply_regular_equals_list_kernel_on_vint16k(ctx):
     lo, hi = 4000, 9000
     got = ctx.apply_regular(lo, hi)
     ref = rowsum[lo:hi]
-    rel = (got - ref).abs().sum(1) / ref.abs().sum(1).mean()
-    assert float(rel.max()) < 1e-11
+    # the two kernels group lanes differently (32 consecutive tasks vs 32 columns of a tile), so their warps vote
+    # differently on the far-field shortcuts and round ill-conditioned pairs differently: allow 1e-12 |J| plus the summed
+    # conditioning bound of the row's pairs (helpers.reference_noise_bound), like the oracle comparison above
+    t = tasks.cpu().numpy()
+    sel = (t[:, 0] >= lo) & (t[:, 0] < hi)
+    noise = np.zeros(m.n_cells)
+    np.add.at(noise, t[sel, 0], reference_noise_bound(m.vertices, m.cells, np.ascontiguousarray(t[sel])))
+    absJ = torch.zeros(m.n_cells, dtype=torch.float64, device="cuda")
+    absJ.index_add_(0, tasks[:, 0].long(), J.abs().sum(1))
+    tol = 1e-12 * absJ[lo:hi] + 8.0 * torch.as_tensor(noise[lo:hi]).cuda()
+    err = (got - ref).abs().sum(1)
+    assert bool((err <= tol).all()), float((err / tol).max())
+    rel = err / ref.abs().sum(1).mean()
+    assert float(rel.median()) < 1e-13 and float(rel.max()) < 1e-9
 
 
 def test_apply_regular_beyond_the_reference_limit(ctx):
