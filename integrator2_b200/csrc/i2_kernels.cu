@@ -27,6 +27,8 @@ long long g_launchCount = 0;
 __constant__ double c_gauss[MAX_GAUSS_POINTS * 4];
 __constant__ int c_ngauss;
 __constant__ int c_groupEnd[MAX_GAUSS_POINTS];   // 1 = last point of a run of equal weights (grouped evaluation)
+__constant__ int c_ngroups;                      // the same runs as [c_groupStart[k], c_groupStart[k + 1])
+__constant__ int c_groupStart[MAX_GAUSS_POINTS + 1];
 __constant__ double c_pow2p;
 
 cudaError_t upload_math_tables(cudaStream_t s) {
@@ -39,15 +41,21 @@ cudaError_t upload_quadrature(const double *Lxyzw, int n, double pow2p, cudaStre
     e = cudaMemcpyToSymbolAsync(c_ngauss, &n, sizeof(int), 0, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) return e;
     // runs of equal weights (at most 6 points per run: the angle-sum argument of the grouped kernel needs <= 6)
-    static int groupEnd[MAX_GAUSS_POINTS];
+    static int groupEnd[MAX_GAUSS_POINTS], groupStart[MAX_GAUSS_POINTS + 1], ngroups;
     int run = 0;
+    ngroups = 0;
+    groupStart[0] = 0;
     for (int g = 0; g < n; ++g) {
         ++run;
         const bool last = (g == n - 1) || (Lxyzw[4 * (g + 1) + 3] != Lxyzw[4 * g + 3]) || run == 6;
         groupEnd[g] = last ? 1 : 0;
-        if (last) run = 0;
+        if (last) { run = 0; groupStart[++ngroups] = g + 1; }
     }
     e = cudaMemcpyToSymbolAsync(c_groupEnd, groupEnd, sizeof(int) * n, 0, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbolAsync(c_groupStart, groupStart, sizeof(int) * (ngroups + 1), 0, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbolAsync(c_ngroups, &ngroups, sizeof(int), 0, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) return e;
     return cudaMemcpyToSymbolAsync(c_pow2p, &pow2p, sizeof(double), 0, cudaMemcpyHostToDevice, s);
 }
@@ -291,61 +299,104 @@ k_integrate(PackedMesh pm, const int *__restrict__ tasks, const int *__restrict_
     }
 }
 
+// Sticky "this group needs the careful form" flag of grouped_eval, raised on the integer pipe: one chained predicate
+//   one-sided form : D_k below 2^-40 of its length (eps_screen)
+//   projection form: symmetric D_k below 2^-20 of its edge (near_edge) | |d_b|^2 or |d_c|^2 below |d_a|^2 / 16 (near_vertex)
+//   both           : half solid angle not provably below pi/6 (!angle_small; a non-positive den fails the compare by itself)
+// and one select.  Written in PTX because the compiler otherwise emits one select per condition.
+template <bool PROJ>
+static __device__ __forceinline__ int raise_flag(int flagged, const PointTerms &t, const TriJ &T, const double *sq) {
+    const int k = 40 << 20;
+    int e1 = hi_word(t.lb) - k, e2 = hi_word(t.lc) - k, e3 = hi_word(t.la) - k;
+    const int hn = hi_word(t.num) & 0x7fffffff, hd = hi_word(t.den) - (1 << 20);
+    if (PROJ) {
+        const int nv = hi_word(sq[0]) - (4 << 20);
+        e1 = T.s1; e2 = T.s2; e3 = T.s3;
+        asm("{\n\t.reg .pred p;\n\t"
+            "setp.lt.s32 p, %1, %2;\n\t"
+            "setp.lt.or.s32 p, %3, %4, p;\n\t"
+            "setp.lt.or.s32 p, %5, %6, p;\n\t"
+            "setp.ge.or.s32 p, %7, %8, p;\n\t"
+            "setp.lt.or.s32 p, %9, %11, p;\n\t"
+            "setp.lt.or.s32 p, %10, %11, p;\n\t"
+            "selp.s32 %0, 1, %0, p;\n\t}"
+            : "+r"(flagged)
+            : "r"(hi_word(t.D1)), "r"(e1), "r"(hi_word(t.D2)), "r"(e2), "r"(hi_word(t.D3)), "r"(e3), "r"(hn), "r"(hd),
+              "r"(hi_word(sq[1])), "r"(hi_word(sq[2])), "r"(nv));
+    } else {
+        asm("{\n\t.reg .pred p;\n\t"
+            "setp.lt.s32 p, %1, %2;\n\t"
+            "setp.lt.or.s32 p, %3, %4, p;\n\t"
+            "setp.lt.or.s32 p, %5, %6, p;\n\t"
+            "setp.ge.or.s32 p, %7, %8, p;\n\t"
+            "selp.s32 %0, 1, %0, p;\n\t}"
+            : "+r"(flagged)
+            : "r"(hi_word(t.D1)), "r"(e1), "r"(hi_word(t.D2)), "r"(e2), "r"(hi_word(t.D3)), "r"(e3), "r"(hn), "r"(hd));
+    }
+    return flagged;
+}
+
 // Grouped evaluation of one (child) control panel against triangle T: on return a1..a3 = sum_g w_g ln(N/D) per edge,
 // a4 = sum_g w_g Theta_g.  myM points at this thread's staged Gauss points ([point][component], stride kThreads).
-// Must be called by all 32 lanes of a warp (one __all_sync per group of equal weights).
+// Must be called by all 32 lanes of a warp.  The point loop carries no vote and no branch: every rare condition (a log
+// argument below the reference's epsilon, a large solid angle, a Gauss point next to a vertex of T in the projection form)
+// only raises a sticky flag, and ONE __all_sync per group of equal weights decides whether the warp redoes the group point
+// by point in the careful form.
 template <bool EDGELEN, bool RESID, bool DERIVE = false, bool PROJ = false>
 static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, const TriJ &T, double &a1, double &a2, double &a3, double &a4) {
     a1 = 0.0; a2 = 0.0; a3 = 0.0; a4 = 0.0;
-    double pn1 = 1.0, pd1 = 1.0, pn2 = 1.0, pd2 = 1.0, pn3 = 1.0, pd3 = 1.0, zr = 1.0, zi = 0.0;
-    bool safe = true;
-    int gStart = 0;
+    const int ngroups = c_ngroups;
+    int g = 0;
 #pragma unroll 1
-    for (int g = 0; g < ng; ++g) {
-        const d3 M = {myM[(3 * g + 0) * kThreads], myM[(3 * g + 1) * kThreads], myM[(3 * g + 2) * kThreads]};
-        PointTerms t;
-        if (PROJ) {
-            bool nearVertex;
-            t = point_terms_proj(M, T, &nearVertex);
-            if (__any_sync(0xffffffffu, nearVertex)) t = point_terms_raw<true, true>(M, T);   // rare: keep full accuracy next to a vertex
+    for (int grp = 0; grp < ngroups; ++grp) {
+        const int gStart = g, gEnd = c_groupStart[grp + 1];
+        double pn1 = 1.0, pd1 = 1.0, pn2 = 1.0, pd2 = 1.0, pn3 = 1.0, pd3 = 1.0, zr = 1.0, zi = 0.0;
+        int flagged = 0;
+        const double *pM = myM + 3 * kThreads * gStart, *const pEnd = myM + 3 * kThreads * gEnd;
+#pragma unroll 1
+        for (; pM != pEnd; pM += 3 * kThreads) {
+            const d3 M = {pM[0], pM[kThreads], pM[2 * kThreads]};
+            PointTerms t;
+            double sq[3];
+            if (PROJ) t = point_terms_proj(M, T, sq);
+            else t = point_terms_raw<EDGELEN, DERIVE>(M, T);
+            flagged = raise_flag<PROJ>(flagged, t, T, sq);
+            pn1 *= t.N1; pd1 *= t.D1; pn2 *= t.N2; pd2 *= t.D2; pn3 *= t.N3; pd3 *= t.D3;
+            const double zin = zi * t.num;   // complex product, updated in place
+            zi = zi * t.den;
+            zi = fma(zr, t.num, zi);
+            zr = fma(zr, t.den, -zin);
+        }
+        g = gEnd;
+        const double w = c_gauss[4 * gStart + 3];
+        double th;
+        if (__all_sync(0xffffffffu, !flagged)) {
+            if (__all_sync(0xffffffffu, angle_tiny(zi, zr))) th = atan2_small<RESID>(zi, zr);
+            else th = atan2_fast<RESID>(zi, zr);
         } else {
-            t = point_terms_raw<EDGELEN, DERIVE>(M, T);
-        }
-        if (__any_sync(0xffffffffu, eps_screen(t))) eps_fixup(t);   // warp-uniform; the screen runs on the integer pipe
-        pn1 *= t.N1; pd1 *= t.D1; pn2 *= t.N2; pd2 *= t.D2; pn3 *= t.N3; pd3 *= t.D3;
-        const double nr = fma(zr, t.den, -(zi * t.num)), ni = fma(zr, t.num, zi * t.den);
-        zr = nr; zi = ni;
-        safe = safe && angle_small(t);
-        if (c_groupEnd[g]) {
-            const double w = c_gauss[4 * g + 3];
-            // far-field shortcut, taken by the whole warp: all three ratios within [1/sqrt2, sqrt2] -> no mantissa surgery
-            const double sa = pn1 + pd1, da_ = pn1 - pd1, sb = pn2 + pd2, db_ = pn2 - pd2, sc_ = pn3 + pd3, dc_ = pn3 - pd3;
-            if (__all_sync(0xffffffffu, ratio_near1(sa, da_) && ratio_near1(sb, db_) && ratio_near1(sc_, dc_))) {
-                a1 = fma(w, log_ratio_near1<RESID>(sa, da_), a1);
-                a2 = fma(w, log_ratio_near1<RESID>(sb, db_), a2);
-                a3 = fma(w, log_ratio_near1<RESID>(sc_, dc_), a3);
-            } else {
-                a1 = fma(w, log_ratio<RESID>(pn1, pd1), a1);
-                a2 = fma(w, log_ratio<RESID>(pn2, pd2), a2);
-                a3 = fma(w, log_ratio<RESID>(pn3, pd3), a3);
+            // careful form for the whole warp: epsilon fallback applied, angles added one by one
+            pn1 = pd1 = pn2 = pd2 = pn3 = pd3 = 1.0;
+            th = 0.0;
+            for (int h = gStart; h < gEnd; ++h) {
+                const d3 Mh = {myM[(3 * h + 0) * kThreads], myM[(3 * h + 1) * kThreads], myM[(3 * h + 2) * kThreads]};
+                PointTerms u = point_terms_raw<EDGELEN, DERIVE>(Mh, T);
+                eps_fixup(u);
+                pn1 *= u.N1; pd1 *= u.D1; pn2 *= u.N2; pd2 *= u.D2; pn3 *= u.N3; pd3 *= u.D3;
+                th += atan2_fast<RESID>(u.num, u.den);
             }
-            double th;
-            if (__all_sync(0xffffffffu, safe)) {
-                if (__all_sync(0xffffffffu, angle_tiny(zi, zr))) th = atan2_small<RESID>(zi, zr);
-                else th = atan2_fast<RESID>(zi, zr);
-            } else {  // some lane of the warp sees triangle j under a large solid angle: add the angles one by one
-                th = 0.0;
-                for (int h = gStart; h <= g; ++h) {
-                    const d3 Mh = {myM[(3 * h + 0) * kThreads], myM[(3 * h + 1) * kThreads], myM[(3 * h + 2) * kThreads]};
-                    const PointTerms u = point_terms_raw<EDGELEN, DERIVE>(Mh, T);
-                    th += atan2_fast<RESID>(u.num, u.den);
-                }
-            }
-            a4 = fma(w, th + th, a4);
-            pn1 = pd1 = pn2 = pd2 = pn3 = pd3 = zr = 1.0; zi = 0.0;
-            safe = true;
-            gStart = g + 1;
         }
+        // far-field shortcut, taken by the whole warp: all three ratios within [1/sqrt2, sqrt2] -> no mantissa surgery
+        const double sa = pn1 + pd1, da_ = pn1 - pd1, sb = pn2 + pd2, db_ = pn2 - pd2, sc_ = pn3 + pd3, dc_ = pn3 - pd3;
+        if (__all_sync(0xffffffffu, ratio_near1(sa, da_) && ratio_near1(sb, db_) && ratio_near1(sc_, dc_))) {
+            a1 = fma(w, log_ratio_near1<RESID>(sa, da_), a1);
+            a2 = fma(w, log_ratio_near1<RESID>(sb, db_), a2);
+            a3 = fma(w, log_ratio_near1<RESID>(sc_, dc_), a3);
+        } else {
+            a1 = fma(w, log_ratio<RESID>(pn1, pd1), a1);
+            a2 = fma(w, log_ratio<RESID>(pn2, pd2), a2);
+            a3 = fma(w, log_ratio<RESID>(pn3, pd3), a3);
+        }
+        a4 = fma(w, th + th, a4);
     }
 }
 
@@ -389,7 +440,10 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
         T.ta = ld3(tri + PK_TA * stride, stride, j); T.tb = ld3(tri + PK_TB * stride, stride, j); T.tc = ld3(tri + PK_TC * stride, stride, j);
         T.Nu = ld3(tri + PK_NU * stride, stride, j);
         if (EDGELEN) { const d3 L = ld3(tri + PK_L * stride, stride, j); T.La = L.x; T.Lb = L.y; T.Lc = L.z; }
-        if (PROJ) { T.c1 = T.Lc * dot(T.tc, T.ta); T.c2 = T.Lc * T.Lb * dot(T.tc, T.tb); }
+        if (PROJ) {
+            T.c2 = T.Lc * T.Lb * dot(T.tc, T.tb);
+            T.s1 = hi_word(T.Lc) - kNearEdgeShift; T.s2 = hi_word(T.La) - kNearEdgeShift; T.s3 = hi_word(T.Lb) - kNearEdgeShift;
+        }
         double s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;
         for (int k = 0; k < perLane; ++k) {
             if (perLane > 1 || i != iStaged) {
@@ -534,7 +588,8 @@ k_apply_regular(PackedMesh pm, int rowLo, int rowHi, int colLo, int colHi, int c
             T.ta = {t[9], t[10], t[11]}; T.tb = {t[12], t[13], t[14]}; T.tc = {t[15], t[16], t[17]};
             T.Nu = {t[18], t[19], t[20]};
             T.La = t[21]; T.Lb = t[22]; T.Lc = t[23];
-            T.c1 = T.Lc * dot(T.tc, T.ta); T.c2 = T.Lc * T.Lb * dot(T.tc, T.tb);
+            T.c2 = T.Lc * T.Lb * dot(T.tc, T.tb);
+            T.s1 = hi_word(T.Lc) - kNearEdgeShift; T.s2 = hi_word(T.La) - kNearEdgeShift; T.s3 = hi_word(T.Lb) - kNearEdgeShift;
             double a1, a2, a3, a4;
             grouped_eval<true, false, true, true>(myM, ng, T, a1, a2, a3, a4);
             const int ja = smId[3 * jj], jb = smId[3 * jj + 1], jc = smId[3 * jj + 2];

@@ -29,7 +29,8 @@ struct TriJ {
     d3 ta, tb, tc;     // unit tangents (C-B)^, (A-C)^, (B-A)^
     d3 Nu;             // (B-A) x (C-A), not normalised:  (M-A)·Nu = (M-A)x(M-B)·(M-C)
     double La, Lb, Lc; // edge lengths |C-B|, |A-C|, |B-A| (only used by the EDGELEN variant of point_terms)
-    double c1, c2;     // Lc (tc·ta) and Lc Lb (tc·tb): only used by point_terms_proj
+    double c2;         // Lc Lb (tc·tb): only used by point_terms_proj
+    int s1, s2, s3;    // near_edge thresholds hi_word(Lc, La, Lb) - kNearEdgeShift (device kernels precompute them per task)
 };
 
 // ---- regular pairs: reference operation order ("strict") ------------------------------------------
@@ -124,40 +125,57 @@ I2_HD PointTerms point_terms_raw(d3 M, const TriJ &T) {
     return r;
 }
 
-// Projection form: every length and dot product of the point follows from d_a = M - A, |d_a|^2 and the three projections
-// q = d_a·(t_a, t_b, t_c), because d_b = d_a - Lc t_c and d_c = d_a + Lb t_b:
+// Projection form: every length and dot product of the point follows from d_a = M - A, |d_a|^2 and the two projections
+// q_b = d_a·t_b, q_c = d_a·t_c, because d_b = d_a - Lc t_c and d_c = d_a + Lb t_b:
 //   |d_b|^2 = |d_a|^2 + Lc (Lc - 2 q_c)      |d_c|^2 = |d_a|^2 + Lb (Lb + 2 q_b)
-//   d_b·t_a = q_a - Lc (t_c·t_a)             d_c·t_b = q_b + Lb
 //   d_a·d_b = |d_a|^2 - Lc q_c               d_c·d_a = |d_a|^2 + Lb q_b          d_b·d_c = d_c·d_a - Lc q_c - Lc Lb (t_c·t_b)
-// 25 FP64 operations instead of 36 for the same quantities.  The differences are exact in real arithmetic; in FP64 the
+// and the log arguments are taken in the symmetric form of the same segment potential,
+//   (l_a + d_a·t_c) / (l_b + d_b·t_c)  =  (l_a + l_b + Lc) / (l_a + l_b - Lc)
+// (multiply out with l^2 - (d·t)^2 = squared distance to the edge line, equal for both ends), which needs no projection
+// at all and has no cancellation away from the edge itself: N - D = 2 Lc exactly, so far pairs keep full relative
+// accuracy where the one-sided form loses log2(distance / edge) bits.  On the line beyond either end it equals the
+// reference's epsilon-fallback value l_b / l_a by itself; it differs from the reference only where D -> 0, i.e. within
+// ~1e-3 edge lengths of the edge segment, which near_edge() screens (superset of the reference's fallback condition for
+// points further than 2e-6 |d_b| from the vertices) and sends to the one-sided form + eps_fixup.
+// 60 FP64 operations per point instead of 71.  The differences are exact in real arithmetic; in FP64 the
 // squared lengths of B and C lose log2(|d_a|^2 / |d_b|^2) bits, so the caller uses this form only while |d_b|^2 and
-// |d_c|^2 stay above |d_a|^2 / 16 (*nearVertex reports the opposite; far pairs — the bulk — always qualify).
-I2_HD PointTerms point_terms_proj(d3 M, const TriJ &T, bool *nearVertex) {
+// |d_c|^2 stay above |d_a|^2 / 16 (near_vertex(sq) reports the opposite; far pairs — the bulk — always qualify).
+// sq receives (|d_a|^2, |d_b|^2, |d_c|^2).
+I2_HD bool near_vertex(const double *sq) {
+    return (hi_word(sq[1]) < hi_word(sq[0]) - (4 << 20)) | (hi_word(sq[2]) < hi_word(sq[0]) - (4 << 20));
+}
+constexpr int kNearEdgeShift = 20 << 20;   // D < 2^-20 L
+I2_HD PointTerms point_terms_proj(d3 M, const TriJ &T, double *sq) {
     const d3 da = M - T.A;
     const double la2 = norm2(da);
-    const double qa = dot(da, T.ta), qb = dot(da, T.tb), qc = dot(da, T.tc);
+    const double qb = dot(da, T.tb), qc = dot(da, T.tc);
     const double lb2 = fma(T.Lc, fma(-2.0, qc, T.Lc), la2);
     const double lc2 = fma(T.Lb, fma(2.0, qb, T.Lb), la2);
-    *nearVertex = (hi_word(lb2) < hi_word(la2) - (4 << 20)) | (hi_word(lc2) < hi_word(la2) - (4 << 20));
+    sq[0] = la2; sq[1] = lb2; sq[2] = lc2;
     PointTerms r;
     r.la = fast_sqrt(la2); r.lb = fast_sqrt(lb2); r.lc = fast_sqrt(lc2);
-    const double pb = qa - T.c1, pc = qb + T.Lb;
-    r.N1 = r.la + qc; r.D1 = r.lb + (qc - T.Lc);
-    r.N2 = r.lb + pb; r.D2 = r.lc + (pb - T.La);
-    r.N3 = r.lc + pc; r.D3 = r.la + (pc - T.Lb);
+    const double sab = r.la + r.lb, sbc = r.lb + r.lc, sca = r.lc + r.la;
+    r.N1 = sab + T.Lc; r.D1 = sab - T.Lc;
+    r.N2 = sbc + T.La; r.D2 = sbc - T.La;
+    r.N3 = sca + T.Lb; r.D3 = sca - T.Lb;
     r.num = dot(da, T.Nu);
     const double ab = fma(-T.Lc, qc, la2), ca = fma(T.Lb, qb, la2), bc = fma(-T.Lc, qc, ca - T.c2);
     r.den = r.la * r.lb * r.lc + ab * r.lc + bc * r.la + ca * r.lb;
     return r;
+}
+// symmetric-form D below 2^-20 of its edge (negative rounding noise included): the point is next to the edge segment
+I2_HD bool near_edge(const PointTerms &r, const TriJ &T) {
+    return (hi_word(r.D1) < hi_word(T.Lc) - kNearEdgeShift) | (hi_word(r.D2) < hi_word(T.La) - kNearEdgeShift) |
+           (hi_word(r.D3) < hi_word(T.Lb) - kNearEdgeShift);
 }
 
 // Integer-pipe screen for the reference's fallback test |o_b·t_c + 1| < 0.5e-12  <=>  |D| < 0.5e-12 l: positive doubles
 // order like their bit patterns, so "high word of |D| < high word of l minus 40 exponent steps" (|D| < ~2^-40 l) is a
 // superset of the exact condition (0.5e-12 = 2^-40.86) that costs no FP64 issue slot.  Almost never true.
 I2_HD bool eps_screen(const PointTerms &r) {
+    // signed compares: a (rounding-noise) negative D has a negative high word and is flagged as well
     const int k = 40 << 20;
-    return ((hi_word(r.D1) & 0x7fffffff) < hi_word(r.lb) - k) | ((hi_word(r.D2) & 0x7fffffff) < hi_word(r.lc) - k) |
-           ((hi_word(r.D3) & 0x7fffffff) < hi_word(r.la) - k);
+    return (hi_word(r.D1) < hi_word(r.lb) - k) | (hi_word(r.D2) < hi_word(r.lc) - k) | (hi_word(r.D3) < hi_word(r.la) - k);
 }
 // exact fallback selects (slow path, taken by a whole warp when any lane passes the screen)
 I2_HD void eps_fixup(PointTerms &r) {

@@ -19,7 +19,7 @@ static TriJ make_tri(const double *v, const int *cells, int j) {
     T.ta = unit(T.C - T.B); T.tb = unit(T.A - T.C); T.tc = unit(T.B - T.A);
     T.Nu = cross(T.B - T.A, T.C - T.A);
     T.La = norm(T.C - T.B); T.Lb = norm(T.A - T.C); T.Lc = norm(T.B - T.A);
-    T.c1 = T.Lc * dot(T.tc, T.ta); T.c2 = T.Lc * T.Lb * dot(T.tc, T.tb);
+    T.c2 = T.Lc * T.Lb * dot(T.tc, T.tb);
     return T;
 }
 
@@ -64,9 +64,9 @@ void emu_regular(const double *v, const int *cells, const double *measures, cons
             bool safe = true;
             int gStart = 0;
             for (int g = 0; g < g_n; ++g) {
-                bool nearV = false;
-                PointTerms t = (var & 8) ? point_terms_proj(gp(g, I.A, I.B, I.C), T, &nearV) : (var & 4) ? point_terms_raw<true, true>(gp(g, I.A, I.B, I.C), T) : ((var & 1) ? point_terms_raw<true>(gp(g, I.A, I.B, I.C), T) : point_terms_raw<false>(gp(g, I.A, I.B, I.C), T));
-                if (nearV) t = point_terms_raw<true, true>(gp(g, I.A, I.B, I.C), T);
+                double sq[3] = {1.0, 1.0, 1.0};
+                PointTerms t = (var & 8) ? point_terms_proj(gp(g, I.A, I.B, I.C), T, sq) : (var & 4) ? point_terms_raw<true, true>(gp(g, I.A, I.B, I.C), T) : ((var & 1) ? point_terms_raw<true>(gp(g, I.A, I.B, I.C), T) : point_terms_raw<false>(gp(g, I.A, I.B, I.C), T));
+                if ((var & 8) && (near_vertex(sq) || near_edge(t, T))) t = point_terms_raw<true, true>(gp(g, I.A, I.B, I.C), T);
                 if (eps_screen(t)) eps_fixup(t);
                 pn1 *= t.N1; pd1 *= t.D1; pn2 *= t.N2; pd2 *= t.D2; pn3 *= t.N3; pd3 *= t.D3;
                 const double nr = fma(zr, t.den, -(zi * t.num)), ni = fma(zr, t.num, zi * t.den);

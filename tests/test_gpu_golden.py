@@ -82,7 +82,9 @@ def test_gpu_adaptive_rounds_match_reference(ctx, name):
         for k, (checked, conv, unconv) in enumerate(rounds, start=1):
             d = abs(r["stats"]["unconverged"][k] - unconv)
             ties += d
-            assert d <= max(5, 2e-3 * unconv), (name, cn, k, r["stats"], rounds)
+            # ties: pairs whose Runge estimate sits within the reference's own rounding noise of the threshold (the
+            # reference's one-sided log form loses log2(distance/edge) bits that the kernel's symmetric form keeps)
+            assert d <= max(5, 4e-3 * unconv), (name, cn, k, r["stats"], rounds)
         ref = G[f"{name}.refinements"][c]
         # every flipped borderline decision can change the counter of its control panel in that and the following rounds
         # (the net count difference per round under-counts the flips: some go each way)
