@@ -350,16 +350,20 @@ static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, c
 #pragma unroll 1
     for (int grp = 0; grp < ngroups; ++grp) {
         const int gStart = g, gEnd = c_groupStart[grp + 1];
-        double pn1 = 1.0, pd1 = 1.0, pn2 = 1.0, pd2 = 1.0, pn3 = 1.0, pd3 = 1.0, zr = 1.0, zi = 0.0;
-        int flagged = 0;
         const double *pM = myM + 3 * kThreads * gStart, *const pEnd = myM + 3 * kThreads * gEnd;
-#pragma unroll 1
-        for (; pM != pEnd; pM += 3 * kThreads) {
+        double sq[3];
+        auto point = [&]() -> PointTerms {
             const d3 M = {pM[0], pM[kThreads], pM[2 * kThreads]};
-            PointTerms t;
-            double sq[3];
-            if (PROJ) t = point_terms_proj(M, T, sq);
-            else t = point_terms_raw<EDGELEN, DERIVE>(M, T);
+            pM += 3 * kThreads;
+            return PROJ ? point_terms_proj(M, T, sq) : point_terms_raw<EDGELEN, DERIVE>(M, T);
+        };
+        // first point of the group: the running products start from its terms (no multiplication by one)
+        PointTerms t = point();
+        double pn1 = t.N1, pd1 = t.D1, pn2 = t.N2, pd2 = t.D2, pn3 = t.N3, pd3 = t.D3, zr = t.den, zi = t.num;
+        int flagged = raise_flag<PROJ>(0, t, T, sq);
+#pragma unroll 1
+        while (pM != pEnd) {
+            t = point();
             flagged = raise_flag<PROJ>(flagged, t, T, sq);
             pn1 *= t.N1; pd1 *= t.D1; pn2 *= t.N2; pd2 *= t.D2; pn3 *= t.N3; pd3 *= t.D3;
             const double zin = zi * t.num;   // complex product, updated in place
