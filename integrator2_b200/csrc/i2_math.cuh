@@ -1,6 +1,6 @@
 // Branch-free FP64 primitives for the regular-pair kernel (the FP64 pipe is the roofline, so every DFMA counts):
-//   fast_sqrt      MUFU.RSQ64H seed + one Goldschmidt step + one residual correction           (6 FP64 ops)
-//   fast_rcp       MUFU.RCP64H seed + two Newton steps                                          (4 FP64 ops)
+//   fast_sqrt      MUFU.RSQ64H seed + one cubic (Halley-type) step                              (5 FP64 ops)
+//   fast_rcp       MUFU.RCP64H seed + one cubic step                                            (3 FP64 ops)
 //   log_ratio      ln(N/D) with the division folded into the atanh argument (N-D)/(N+D)        (~25 FP64 ops)
 //   atan2_fast     atan2(y,x) with a 5-entry argument reduction, one division                  (~26 FP64 ops)
 // libdevice spends ~17 (sqrt) / ~19 (div) / ~30 (log) / ~46 (atan2) FP64-pipe instructions on the same jobs and
@@ -78,20 +78,19 @@ I2_HD double rcp_seed(double x) {
 }
 
 I2_HD double fast_sqrt(double x) {
+    // one cubic step: sqrt x = g (1 - e)^(-1/2) with g = x y, e = 1 - x y^2 (|e| ~ 2^-19 for the 2^-20 seed):
+    // 1 + e/2 + 3 e^2/8, next term 5 e^3/16 < 2^-58.  The rounding of g is half compensated through e: <= 1 ulp.
     const double y = rsqrt_seed(x);
-    double g = x * y;
-    const double h = 0.5 * y;
-    const double r = fma(-g, h, 0.5);
-    g = fma(g, r, g);                  // relative error ~1.5 e0^2 (e0 = seed error, ~2^-22)
-    return fma(fma(-g, g, x), h, g);   // g + (x - g^2) * (1/(2 sqrt x)); h keeps the seed's error: residual ~e0^3, below 1 ulp
+    const double g = x * y;
+    const double e = fma(-g, y, 1.0);
+    const double q = e * fma(0.375, e, 0.5);
+    return fma(g, q, g);
 }
 
 I2_HD double fast_rcp(double x) {
-    double y = rcp_seed(x);
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    return fma(y, e, y);
+    const double y = rcp_seed(x);
+    const double e = fma(-x, y, 1.0);
+    return fma(y, fma(e, e, e), y);    // y (1 + e + e^2), next term e^3 < 2^-60
 }
 
 // ln(N/D), N, D > 0.  N = 2^eN mN, D = 2^eD mD with mN, mD in [1,2); the pair is rescaled by one more factor 2 if

@@ -79,12 +79,16 @@ def test_gpu_adaptive_rounds_match_reference(ctx, name):
         rounds = parse_rounds(META[name]["log"])[c]
         assert r["stats"]["last_round"] == len(rounds), (name, cn)
         ties = 0
+        carried = 0
         for k, (checked, conv, unconv) in enumerate(rounds, start=1):
             d = abs(r["stats"]["unconverged"][k] - unconv)
             ties += d
             # ties: pairs whose Runge estimate sits within the reference's own rounding noise of the threshold (the
-            # reference's one-sided log form loses log2(distance/edge) bits that the kernel's symmetric form keeps)
-            assert d <= max(5, 4e-3 * unconv), (name, cn, k, r["stats"], rounds)
+            # reference's one-sided log form loses log2(distance/edge) bits that the kernel's symmetric form keeps; the
+            # unconverged pairs are exactly the near, ill-conditioned ones).  A flip in round k also changes which pairs
+            # round k+1 sees, so the previous round's difference is carried.
+            assert d <= max(5, 4e-3 * unconv) + carried, (name, cn, k, r["stats"], rounds)
+            carried = d
         ref = G[f"{name}.refinements"][c]
         # every flipped borderline decision can change the counter of its control panel in that and the following rounds
         # (the net count difference per round under-counts the flips: some go each way)
