@@ -372,7 +372,7 @@ static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, c
             zr = fma(zr, t.den, -zin);
         }
         g = gEnd;
-        const double w = c_gauss[4 * gStart + 3];
+        const double w = c_gauss[4 * gStart + 3], w2 = w + w;
         double th;
         if (__all_sync(0xffffffffu, !flagged)) {
             if (__all_sync(0xffffffffu, angle_tiny(zi, zr))) th = atan2_small<RESID>(zi, zr);
@@ -392,15 +392,15 @@ static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, c
         // far-field shortcut, taken by the whole warp: all three ratios within [1/sqrt2, sqrt2] -> no mantissa surgery
         const double sa = pn1 + pd1, da_ = pn1 - pd1, sb = pn2 + pd2, db_ = pn2 - pd2, sc_ = pn3 + pd3, dc_ = pn3 - pd3;
         if (__all_sync(0xffffffffu, ratio_near1(sa, da_) && ratio_near1(sb, db_) && ratio_near1(sc_, dc_))) {
-            a1 = fma(w, log_ratio_near1<RESID>(sa, da_), a1);
-            a2 = fma(w, log_ratio_near1<RESID>(sb, db_), a2);
-            a3 = fma(w, log_ratio_near1<RESID>(sc_, dc_), a3);
+            a1 = fma(w2, atanh_near1<RESID>(sa, da_), a1);
+            a2 = fma(w2, atanh_near1<RESID>(sb, db_), a2);
+            a3 = fma(w2, atanh_near1<RESID>(sc_, dc_), a3);
         } else {
             a1 = fma(w, log_ratio<RESID>(pn1, pd1), a1);
             a2 = fma(w, log_ratio<RESID>(pn2, pd2), a2);
             a3 = fma(w, log_ratio<RESID>(pn3, pd3), a3);
         }
-        a4 = fma(w, th + th, a4);
+        a4 = fma(w2, th, a4);
     }
 }
 

@@ -24,8 +24,9 @@ namespace i2 {
 #define I2_MATH_TABLE_VALUES                                                                                                   \
     {2.0 / 3.0, 2.0 / 5.0, 2.0 / 7.0, 2.0 / 9.0, 2.0 / 11.0, 2.0 / 13.0, 2.0 / 15.0, 2.0 / 17.0, 2.0 / 19.0, 2.0 / 21.0,       /* atanh series  [0..9]  */ \
      -1.0 / 3.0, 1.0 / 5.0, -1.0 / 7.0, 1.0 / 9.0, -1.0 / 11.0, 1.0 / 13.0, -1.0 / 15.0, 1.0 / 17.0, -1.0 / 19.0,              /* atan series  [10..18] */ \
-     6.93147180369123816490e-01, 1.90821492927058770002e-10, 1.57079632679489655800e+00, 3.14159265358979311600e+00}          /* ln2 hi, ln2 lo, pi/2, pi [19..22] */
-constexpr int I2_MATH_TABLE_SIZE = 23;
+     6.93147180369123816490e-01, 1.90821492927058770002e-10, 1.57079632679489655800e+00, 3.14159265358979311600e+00,         /* ln2 hi, ln2 lo, pi/2, pi [19..22] */ \
+     1.0 / 3.0, 1.0 / 5.0, 1.0 / 7.0, 1.0 / 9.0, 1.0 / 11.0, 1.0 / 13.0, 1.0 / 15.0, 1.0 / 17.0, 1.0 / 19.0, 1.0 / 21.0}       /* atanh series, halved [23..32] */
+constexpr int I2_MATH_TABLE_SIZE = 33;
 #if defined(__CUDACC__)
 __constant__ double c_mathTable[I2_MATH_TABLE_SIZE];
 static const double h_mathTable[I2_MATH_TABLE_SIZE] = I2_MATH_TABLE_VALUES;
@@ -139,24 +140,27 @@ I2_HD double log_ratio(double N, double D) {
 //   atan2_small    : x > 0 and |y| < x/8 — no octant logic, no argument reduction.
 // Same series, same accuracy as the general versions; they only drop the integer-pipe bookkeeping (~20 issue slots each).
 I2_HD bool ratio_near1(double s, double d) { return fabs(d) <= 0.1715 * s; }   // s = N + D > 0, d = N - D
+// atanh(d/s) = ln(N/D) / 2: the caller folds the factor 2 into the quadrature weight
 template <bool RESID = true>
-I2_HD double log_ratio_near1(double s, double d) {
+I2_HD double atanh_near1(double s, double d) {
     const double r = fast_rcp(s);
     double f = d * r;
     if (RESID) f = fma(fma(-f, s, d), r, f);
     const double z = f * f;
-    double p = I2_K(9);
-    p = fma(p, z, I2_K(8));
-    p = fma(p, z, I2_K(7));
-    p = fma(p, z, I2_K(6));
-    p = fma(p, z, I2_K(5));
-    p = fma(p, z, I2_K(4));
-    p = fma(p, z, I2_K(3));
-    p = fma(p, z, I2_K(2));
-    p = fma(p, z, I2_K(1));
-    p = fma(p, z, I2_K(0));
-    return fma(f * z, p, f + f);
+    double p = I2_K(32);
+    p = fma(p, z, I2_K(31));
+    p = fma(p, z, I2_K(30));
+    p = fma(p, z, I2_K(29));
+    p = fma(p, z, I2_K(28));
+    p = fma(p, z, I2_K(27));
+    p = fma(p, z, I2_K(26));
+    p = fma(p, z, I2_K(25));
+    p = fma(p, z, I2_K(24));
+    p = fma(p, z, I2_K(23));
+    return fma(f * z, p, f);
 }
+template <bool RESID = true>
+I2_HD double log_ratio_near1(double s, double d) { const double h = atanh_near1<RESID>(s, d); return h + h; }
 // positive doubles order like their bit patterns: "high word of |y| below the high word of x/8" (conservative in the low word)
 I2_HD bool angle_tiny(double y, double x) {
     const int hx = hi_word(x);

@@ -148,3 +148,69 @@ def check_parity_perturbation(oracle, vertices, cells, cls, tasks, level, J_new,
     if bad.size:
         assert rel[bad].max() < 1e-5, f"{label}: outlier too large {stats}"
     return stats
+
+
+def near_singular_mesh(seed=0):
+    """Synthetic mesh of disjoint triangles in crafted (i, j) couples that are REGULAR by topology but nearly singular by
+    geometry: one Gauss point of i is placed next to an edge of j (distance 1e-2 .. 1e-9 edge lengths), on the line of an
+    edge beyond either end (where the reference's epsilon fallback fires), next to a vertex of j, or just above j's
+    interior (half solid angle near pi).  Returns (vertices, cells, couples[n][2], labels)."""
+    from oracle import oracle_py as O
+    rng = np.random.default_rng(seed)
+    L3 = np.column_stack([O.QF13_XY[:, 0], O.QF13_XY[:, 1], 1.0 - O.QF13_XY[:, 0] - O.QF13_XY[:, 1]])
+    verts, cells, couples, labels = [], [], [], []
+
+    def unit(v):
+        return v / np.linalg.norm(v)
+
+    def add(P_of, label):
+        m = len(couples)
+        origin = np.array([8.0 * (m % 16), 8.0 * (m // 16), 0.0])
+        tj = rng.normal(size=(3, 3))
+        tj = np.roll(tj, m % 3, axis=0)
+        P = P_of(tj)
+        ti = rng.normal(size=(3, 3)) * rng.choice([0.3, 1.0])
+        g = int(rng.choice([0, 1, 5, 9]))
+        ti = ti + (P - L3[g] @ ti)        # Gauss point g of i lands on P
+        base = len(verts)
+        verts.extend((ti + origin).tolist()); verts.extend((tj + origin).tolist())
+        cells.append([base, base + 1, base + 2]); cells.append([base + 3, base + 4, base + 5])
+        couples.append([2 * m, 2 * m + 1]); labels.append(label)
+
+    for delta in (1e-2, 1e-3, 1e-4, 1e-6, 1e-9, 0.0):
+        for rep in range(3):
+            def near_edge(tj, delta=delta):
+                A, B, C = tj
+                e = B - A
+                n = unit(np.cross(e, rng.normal(size=3)))
+                return A + rng.uniform(0.2, 0.8) * e + delta * np.linalg.norm(e) * n
+            add(near_edge, f"edge interior {delta:g}")
+
+            def beyond_b(tj, delta=delta):
+                A, B, C = tj
+                e = B - A
+                n = unit(np.cross(e, rng.normal(size=3)))
+                return A + rng.uniform(1.2, 2.0) * e + delta * np.linalg.norm(e) * n
+            add(beyond_b, f"beyond B {delta:g}")
+
+            def beyond_a(tj, delta=delta):
+                A, B, C = tj
+                e = B - A
+                n = unit(np.cross(e, rng.normal(size=3)))
+                return A - rng.uniform(0.2, 1.0) * e + delta * np.linalg.norm(e) * n
+            add(beyond_a, f"beyond A {delta:g}")
+    for delta in (1e-1, 1e-2, 1e-3, 1e-5):
+        for rep in range(3):
+            add(lambda tj, delta=delta: tj[0] + delta * np.linalg.norm(tj[1] - tj[0]) * unit(rng.normal(size=3)), f"vertex {delta:g}")
+            add(lambda tj, delta=delta: tj.mean(0) + delta * unit(np.cross(tj[1] - tj[0], tj[2] - tj[0])), f"above interior {delta:g}")
+            add(lambda tj, delta=delta: tj[0] + 1.7 * (tj[1] - tj[0]) + 0.9 * (tj[2] - tj[0]) + delta * 1e-3 * unit(np.cross(tj[1] - tj[0], tj[2] - tj[0])),
+                f"coplanar outside {delta * 1e-3:g}")
+    return np.array(verts), np.array(cells, dtype=np.int32), np.array(couples), labels
+
+
+def couple_tasks(om, couples):
+    """tasks of the regular class restricted to the crafted couples (both orders)."""
+    t = om.tasks(2)
+    keys = set(map(tuple, couples.tolist())) | set(map(tuple, couples[:, ::-1].tolist()))
+    sel = np.array([(int(a), int(b)) in keys for a, b in t[:, :2]])
+    return np.ascontiguousarray(t[sel])

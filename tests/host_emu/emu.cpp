@@ -31,6 +31,64 @@ static d3 gp(int g, d3 A, d3 B, d3 C) {
     return p;
 }
 
+// grouped evaluation of one control panel (A,B,C) against T: the same sequence as grouped_eval in i2_kernels.cu, with the
+// lane's own predicate in place of every warp vote
+static void grouped_panel(d3 A, d3 B, d3 C, const TriJ &T, int var, double *a) {
+    const bool proj = (var & 8) != 0, resid = (var & 2) == 0;
+    auto raw = [&](d3 M) {
+        return (var & 4) || proj ? point_terms_raw<true, true>(M, T) : ((var & 1) ? point_terms_raw<true>(M, T) : point_terms_raw<false>(M, T));
+    };
+    a[0] = a[1] = a[2] = a[3] = 0.0;
+    int g = 0;
+    while (g < g_n) {
+        int gEnd = g + 1;
+        while (gEnd < g_n && g_w[gEnd] == g_w[g] && gEnd - g < 6) ++gEnd;
+        double pn1 = 1, pd1 = 1, pn2 = 1, pd2 = 1, pn3 = 1, pd3 = 1, zr = 1, zi = 0;
+        bool flagged = false;
+        for (int h = g; h < gEnd; ++h) {
+            const d3 M = gp(h, A, B, C);
+            double sq[3];
+            PointTerms t;
+            if (proj) { t = point_terms_proj(M, T, sq); flagged |= near_vertex(sq) | near_edge(t, T); }
+            else { t = raw(M); flagged |= eps_screen(t); }
+            flagged |= !angle_small(t);
+            if (h == g) { pn1 = t.N1; pd1 = t.D1; pn2 = t.N2; pd2 = t.D2; pn3 = t.N3; pd3 = t.D3; zr = t.den; zi = t.num; continue; }
+            pn1 *= t.N1; pd1 *= t.D1; pn2 *= t.N2; pd2 *= t.D2; pn3 *= t.N3; pd3 *= t.D3;
+            const double zin = zi * t.num;
+            zi = zi * t.den;
+            zi = fma(zr, t.num, zi);
+            zr = fma(zr, t.den, -zin);
+        }
+        const double w = g_w[g], w2 = w + w;
+        double th;
+        if (!flagged) {
+            if (angle_tiny(zi, zr)) th = resid ? atan2_small<true>(zi, zr) : atan2_small<false>(zi, zr);
+            else th = resid ? atan2_fast<true>(zi, zr) : atan2_fast<false>(zi, zr);
+        } else {
+            pn1 = pd1 = pn2 = pd2 = pn3 = pd3 = 1.0;
+            th = 0.0;
+            for (int h = g; h < gEnd; ++h) {
+                PointTerms u = raw(gp(h, A, B, C));
+                eps_fixup(u);
+                pn1 *= u.N1; pd1 *= u.D1; pn2 *= u.N2; pd2 *= u.D2; pn3 *= u.N3; pd3 *= u.D3;
+                th += resid ? atan2_fast<true>(u.num, u.den) : atan2_fast<false>(u.num, u.den);
+            }
+        }
+        const double sa = pn1 + pd1, da_ = pn1 - pd1, sb = pn2 + pd2, db_ = pn2 - pd2, sc_ = pn3 + pd3, dc_ = pn3 - pd3;
+        if (ratio_near1(sa, da_) && ratio_near1(sb, db_) && ratio_near1(sc_, dc_)) {
+            a[0] = fma(w2, resid ? atanh_near1<true>(sa, da_) : atanh_near1<false>(sa, da_), a[0]);
+            a[1] = fma(w2, resid ? atanh_near1<true>(sb, db_) : atanh_near1<false>(sb, db_), a[1]);
+            a[2] = fma(w2, resid ? atanh_near1<true>(sc_, dc_) : atanh_near1<false>(sc_, dc_), a[2]);
+        } else {
+            a[0] = fma(w, resid ? log_ratio<true>(pn1, pd1) : log_ratio<false>(pn1, pd1), a[0]);
+            a[1] = fma(w, resid ? log_ratio<true>(pn2, pd2) : log_ratio<false>(pn2, pd2), a[1]);
+            a[2] = fma(w, resid ? log_ratio<true>(pn3, pd3) : log_ratio<false>(pn3, pd3), a[2]);
+        }
+        a[3] = fma(w2, th, a[3]);
+        g = gEnd;
+    }
+}
+
 extern "C" {
 
 void emu_fast_sqrt(const double *x, long long n, double *out) { for (long long k = 0; k < n; ++k) out[k] = fast_sqrt(x[k]); }
@@ -58,37 +116,11 @@ void emu_regular(const double *v, const int *cells, const double *measures, cons
             }
             res = measures[i] * acc;
         } else if ((mode & 7) == 3) {
-            const int var = mode >> 3;   // bit0 EDGELEN, bit1 no residual correction
-            // grouped evaluation, same sequence as k_regular_grouped (per-thread safety flag instead of the warp vote)
-            double a1 = 0, a2 = 0, a3 = 0, a4 = 0, pn1 = 1, pd1 = 1, pn2 = 1, pd2 = 1, pn3 = 1, pd3 = 1, zr = 1, zi = 0;
-            bool safe = true;
-            int gStart = 0;
-            for (int g = 0; g < g_n; ++g) {
-                double sq[3] = {1.0, 1.0, 1.0};
-                PointTerms t = (var & 8) ? point_terms_proj(gp(g, I.A, I.B, I.C), T, sq) : (var & 4) ? point_terms_raw<true, true>(gp(g, I.A, I.B, I.C), T) : ((var & 1) ? point_terms_raw<true>(gp(g, I.A, I.B, I.C), T) : point_terms_raw<false>(gp(g, I.A, I.B, I.C), T));
-                if ((var & 8) && (near_vertex(sq) || near_edge(t, T))) t = point_terms_raw<true, true>(gp(g, I.A, I.B, I.C), T);
-                if (eps_screen(t)) eps_fixup(t);
-                pn1 *= t.N1; pd1 *= t.D1; pn2 *= t.N2; pd2 *= t.D2; pn3 *= t.N3; pd3 *= t.D3;
-                const double nr = fma(zr, t.den, -(zi * t.num)), ni = fma(zr, t.num, zi * t.den);
-                zr = nr; zi = ni;
-                safe = safe && angle_small(t);
-                const bool last = (g == g_n - 1) || (g_w[g + 1] != g_w[g]) || (g - gStart == 5);
-                if (last) {
-                    const double w = g_w[g];
-                    const double sa = pn1 + pd1, da_ = pn1 - pd1, sb = pn2 + pd2, db_ = pn2 - pd2, sc_ = pn3 + pd3, dc_ = pn3 - pd3;
-                    if ((var & 8) && ratio_near1(sa, da_) && ratio_near1(sb, db_) && ratio_near1(sc_, dc_)) { a1 = fma(w, log_ratio_near1<false>(sa, da_), a1); a2 = fma(w, log_ratio_near1<false>(sb, db_), a2); a3 = fma(w, log_ratio_near1<false>(sc_, dc_), a3); }
-                    else if (var & 2) { a1 = fma(w, log_ratio<false>(pn1, pd1), a1); a2 = fma(w, log_ratio<false>(pn2, pd2), a2); a3 = fma(w, log_ratio<false>(pn3, pd3), a3); }
-                    else { a1 = fma(w, log_ratio<true>(pn1, pd1), a1); a2 = fma(w, log_ratio<true>(pn2, pd2), a2); a3 = fma(w, log_ratio<true>(pn3, pd3), a3); }
-                    double th;
-                    if (safe && (var & 8) && angle_tiny(zi, zr)) th = atan2_small<false>(zi, zr);
-                    else if (safe) th = (var & 2) ? atan2_fast<false>(zi, zr) : atan2_fast<true>(zi, zr);
-                    else { th = 0; for (int h = gStart; h <= g; ++h) { const PointTerms u = point_terms(gp(h, I.A, I.B, I.C), T); th += atan2_fast(u.num, u.den); } }
-                    a4 = fma(w, th + th, a4);
-                    pn1 = pd1 = pn2 = pd2 = pn3 = pd3 = zr = 1.0; zi = 0.0; safe = true; gStart = g + 1;
-                }
-            }
+            const int var = mode >> 3;   // bit0 EDGELEN, bit1 no residual correction, bit2 DERIVE, bit3 projection form + shortcuts
+            double a[4];
+            grouped_panel(I.A, I.B, I.C, T, var, a);
             const double S = measures[i];
-            res = vec4((S * a1) * T.tc + (S * a2) * T.ta + (S * a3) * T.tb, S * a4);
+            res = vec4((S * a[0]) * T.tc + (S * a[1]) * T.ta + (S * a[2]) * T.tb, S * a[3]);
         } else {
             double a1 = 0, a2 = 0, a3 = 0, a4 = 0;
             for (int g = 0; g < g_n; ++g) {
@@ -126,6 +158,11 @@ void emu_regular_level(const double *v, const int *cells, const double *measures
             d3 A = I.A, B = I.B, C = I.C;
             descend_h(A, B, C, level, c);
             double a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+            if ((mode & 7) == 3) {
+                double a[4];
+                grouped_panel(A, B, C, T, mode >> 3, a);
+                a1 = a[0]; a2 = a[1]; a3 = a[2]; a4 = a[3];
+            } else
             for (int g = 0; g < g_n; ++g) {
                 const LogTheta r = mode == 1 ? theta_psi_fast<true>(gp(g, A, B, C), T) : theta_psi_fast<false>(gp(g, A, B, C), T);
                 a1 = fma(g_w[g], r.t1, a1); a2 = fma(g_w[g], r.t2, a2); a3 = fma(g_w[g], r.t3, a3); a4 = fma(g_w[g], r.theta, a4);
