@@ -375,7 +375,9 @@ static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, c
         const double w = c_gauss[4 * gStart + 3], w2 = w + w;
         double th;
         if (__all_sync(0xffffffffu, !flagged)) {
-            if (__all_sync(0xffffffffu, angle_tiny(zi, zr))) th = atan2_small<RESID>(zi, zr);
+            const int am = __reduce_min_sync(0xffffffffu, angle_margin(zi, zr));   // far-field tiers, taken by the whole warp
+            if (am >= kAngleFar) th = atan_series<4, RESID>(zi, zr);
+            else if (am >= kAngleTiny) th = atan_series<9, RESID>(zi, zr);
             else th = atan2_fast<RESID>(zi, zr);
         } else {
             // careful form for the whole warp: epsilon fallback applied, angles added one by one
@@ -389,12 +391,21 @@ static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, c
                 th += atan2_fast<RESID>(u.num, u.den);
             }
         }
-        // far-field shortcut, taken by the whole warp: all three ratios within [1/sqrt2, sqrt2] -> no mantissa surgery
+        // far-field tiers, taken by the whole warp: all three ratios close enough to 1 -> no mantissa surgery, shorter series
         const double sa = pn1 + pd1, da_ = pn1 - pd1, sb = pn2 + pd2, db_ = pn2 - pd2, sc_ = pn3 + pd3, dc_ = pn3 - pd3;
-        if (__all_sync(0xffffffffu, ratio_near1(sa, da_) && ratio_near1(sb, db_) && ratio_near1(sc_, dc_))) {
-            a1 = fma(w2, atanh_near1<RESID>(sa, da_), a1);
-            a2 = fma(w2, atanh_near1<RESID>(sb, db_), a2);
-            a3 = fma(w2, atanh_near1<RESID>(sc_, dc_), a3);
+        const int rm = __reduce_min_sync(0xffffffffu, min(ratio_margin(sa, da_), min(ratio_margin(sb, db_), ratio_margin(sc_, dc_))));
+        if (rm >= kMarginVeryFar) {
+            a1 = fma(w2, atanh_series<3, RESID>(sa, da_), a1);
+            a2 = fma(w2, atanh_series<3, RESID>(sb, db_), a2);
+            a3 = fma(w2, atanh_series<3, RESID>(sc_, dc_), a3);
+        } else if (rm >= kMarginFar) {
+            a1 = fma(w2, atanh_series<6, RESID>(sa, da_), a1);
+            a2 = fma(w2, atanh_series<6, RESID>(sb, db_), a2);
+            a3 = fma(w2, atanh_series<6, RESID>(sc_, dc_), a3);
+        } else if (rm >= kMarginNear1) {
+            a1 = fma(w2, atanh_series<10, RESID>(sa, da_), a1);
+            a2 = fma(w2, atanh_series<10, RESID>(sb, db_), a2);
+            a3 = fma(w2, atanh_series<10, RESID>(sc_, dc_), a3);
         } else {
             a1 = fma(w, log_ratio<RESID>(pn1, pd1), a1);
             a2 = fma(w, log_ratio<RESID>(pn2, pd2), a2);

@@ -135,52 +135,47 @@ I2_HD double log_ratio(double N, double D) {
     return fma(ed, I2_K(19), fma(ed, I2_K(20), lg));   // ln2 split hi/lo
 }
 
-// Far-field shortcuts, used when a whole warp qualifies (the caller votes):
-//   log_ratio_near1: N/D within [1/sqrt2, sqrt2] — f = (N-D)/(N+D) is scale invariant, so no exponent / mantissa surgery;
-//   atan2_small    : x > 0 and |y| < x/8 — no octant logic, no argument reduction.
-// Same series, same accuracy as the general versions; they only drop the integer-pipe bookkeeping (~20 issue slots each).
-I2_HD bool ratio_near1(double s, double d) { return fabs(d) <= 0.1715 * s; }   // s = N + D > 0, d = N - D
+// Far-field shortcuts, used when a whole warp qualifies (the caller reduces the "margin" over the warp):
+//   atanh_series<NC>: atanh(d/s) for |d/s| small — f = (N-D)/(N+D) is scale invariant, so no exponent / mantissa surgery;
+//   atan_series<NC> : atan(y/x) for x > 0 and |y/x| small — no octant logic, no argument reduction.
+// Same series as the general versions, truncated to the NC terms the margin allows; they drop the integer-pipe
+// bookkeeping (~20 issue slots each) and 4-7 Horner steps for far pairs.
+// The margin is measured on the integer pipe: positive doubles order like their bit patterns and
+// g(x) = (high word of x) / 2^20 satisfies g(x) <= log2(x) + const <= g(x) + 0.0861, so
+//   high(s) - high(|d|) >= k * 2^20   implies   |d/s| <= 2^-(k - 0.0862).
+constexpr int kMarginNear1 = 2768241;   // 2.64 * 2^20: |f| <= 0.1716 -> 10 terms (the general version's reduced range)
+constexpr int kMarginFar = 4 << 20;     // |f| <= 0.0664 ->  6 terms (next term f^14/15 < 5e-18)
+constexpr int kMarginVeryFar = 7 << 20; // |f| <= 0.0084 ->  3 terms (next term f^8/9   < 3e-18)
+constexpr int kAngleTiny = 3 << 20;     // |y/x| <= 0.133 -> 9 terms (the general version's reduced range)
+constexpr int kAngleFar = 6 << 20;      // |y/x| <= 0.0166 -> 4 terms (next term t^10/11 < 2e-19)
+// s = N + D > 0, d = N - D: margin of |d/s| (large = far); d = 0 gives the largest margin
+I2_HD int ratio_margin(double s, double d) { return hi_word(s) - (hi_word(d) & 0x7fffffff); }
+// margin of |y/x|, or a negative number when x <= 0
+I2_HD int angle_margin(double y, double x) {
+    const int hx = hi_word(x);
+    return hx > 0 ? hx - (hi_word(y) & 0x7fffffff) : -1;
+}
 // atanh(d/s) = ln(N/D) / 2: the caller folds the factor 2 into the quadrature weight
-template <bool RESID = true>
-I2_HD double atanh_near1(double s, double d) {
+template <int NC, bool RESID = true>
+I2_HD double atanh_series(double s, double d) {
     const double r = fast_rcp(s);
     double f = d * r;
     if (RESID) f = fma(fma(-f, s, d), r, f);
     const double z = f * f;
-    double p = I2_K(32);
-    p = fma(p, z, I2_K(31));
-    p = fma(p, z, I2_K(30));
-    p = fma(p, z, I2_K(29));
-    p = fma(p, z, I2_K(28));
-    p = fma(p, z, I2_K(27));
-    p = fma(p, z, I2_K(26));
-    p = fma(p, z, I2_K(25));
-    p = fma(p, z, I2_K(24));
-    p = fma(p, z, I2_K(23));
+    double p = I2_K(23 + NC - 1);
+#pragma unroll
+    for (int k = NC - 2; k >= 0; --k) p = fma(p, z, I2_K(23 + k));
     return fma(f * z, p, f);
 }
-template <bool RESID = true>
-I2_HD double log_ratio_near1(double s, double d) { const double h = atanh_near1<RESID>(s, d); return h + h; }
-// positive doubles order like their bit patterns: "high word of |y| below the high word of x/8" (conservative in the low word)
-I2_HD bool angle_tiny(double y, double x) {
-    const int hx = hi_word(x);
-    return (hx > 0) & ((hi_word(y) & 0x7fffffff) < hx - (3 << 20));
-}
-template <bool RESID = true>
-I2_HD double atan2_small(double y, double x) {
+template <int NC, bool RESID = true>
+I2_HD double atan_series(double y, double x) {
     const double r = fast_rcp(x);
     double t = y * r;
     if (RESID) t = fma(fma(-t, x, y), r, t);
     const double z = t * t;
-    double p = I2_K(18);
-    p = fma(p, z, I2_K(17));
-    p = fma(p, z, I2_K(16));
-    p = fma(p, z, I2_K(15));
-    p = fma(p, z, I2_K(14));
-    p = fma(p, z, I2_K(13));
-    p = fma(p, z, I2_K(12));
-    p = fma(p, z, I2_K(11));
-    p = fma(p, z, I2_K(10));
+    double p = I2_K(10 + NC - 1);
+#pragma unroll
+    for (int k = NC - 2; k >= 0; --k) p = fma(p, z, I2_K(10 + k));
     return fma(t * z, p, t);
 }
 

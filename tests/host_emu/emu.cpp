@@ -4,6 +4,7 @@
 #include "../../integrator2_b200/csrc/i2_pair.cuh"
 #include "../../integrator2_b200/csrc/i2_math.cuh"
 #include <cstring>
+#include <algorithm>
 
 using namespace i2;
 
@@ -62,7 +63,9 @@ static void grouped_panel(d3 A, d3 B, d3 C, const TriJ &T, int var, double *a) {
         const double w = g_w[g], w2 = w + w;
         double th;
         if (!flagged) {
-            if (angle_tiny(zi, zr)) th = resid ? atan2_small<true>(zi, zr) : atan2_small<false>(zi, zr);
+            const int am = angle_margin(zi, zr);
+            if (am >= kAngleFar) th = resid ? atan_series<4, true>(zi, zr) : atan_series<4, false>(zi, zr);
+            else if (am >= kAngleTiny) th = resid ? atan_series<9, true>(zi, zr) : atan_series<9, false>(zi, zr);
             else th = resid ? atan2_fast<true>(zi, zr) : atan2_fast<false>(zi, zr);
         } else {
             pn1 = pd1 = pn2 = pd2 = pn3 = pd3 = 1.0;
@@ -75,14 +78,13 @@ static void grouped_panel(d3 A, d3 B, d3 C, const TriJ &T, int var, double *a) {
             }
         }
         const double sa = pn1 + pd1, da_ = pn1 - pd1, sb = pn2 + pd2, db_ = pn2 - pd2, sc_ = pn3 + pd3, dc_ = pn3 - pd3;
-        if (ratio_near1(sa, da_) && ratio_near1(sb, db_) && ratio_near1(sc_, dc_)) {
-            a[0] = fma(w2, resid ? atanh_near1<true>(sa, da_) : atanh_near1<false>(sa, da_), a[0]);
-            a[1] = fma(w2, resid ? atanh_near1<true>(sb, db_) : atanh_near1<false>(sb, db_), a[1]);
-            a[2] = fma(w2, resid ? atanh_near1<true>(sc_, dc_) : atanh_near1<false>(sc_, dc_), a[2]);
-        } else {
-            a[0] = fma(w, resid ? log_ratio<true>(pn1, pd1) : log_ratio<false>(pn1, pd1), a[0]);
-            a[1] = fma(w, resid ? log_ratio<true>(pn2, pd2) : log_ratio<false>(pn2, pd2), a[1]);
-            a[2] = fma(w, resid ? log_ratio<true>(pn3, pd3) : log_ratio<false>(pn3, pd3), a[2]);
+        const int rm = std::min(ratio_margin(sa, da_), std::min(ratio_margin(sb, db_), ratio_margin(sc_, dc_)));
+        const double S3[3] = {sa, sb, sc_}, D3[3] = {da_, db_, dc_}, PN[3] = {pn1, pn2, pn3}, PD[3] = {pd1, pd2, pd3};
+        for (int e = 0; e < 3; ++e) {
+            if (rm >= kMarginVeryFar) a[e] = fma(w2, resid ? atanh_series<3, true>(S3[e], D3[e]) : atanh_series<3, false>(S3[e], D3[e]), a[e]);
+            else if (rm >= kMarginFar) a[e] = fma(w2, resid ? atanh_series<6, true>(S3[e], D3[e]) : atanh_series<6, false>(S3[e], D3[e]), a[e]);
+            else if (rm >= kMarginNear1) a[e] = fma(w2, resid ? atanh_series<10, true>(S3[e], D3[e]) : atanh_series<10, false>(S3[e], D3[e]), a[e]);
+            else a[e] = fma(w, resid ? log_ratio<true>(PN[e], PD[e]) : log_ratio<false>(PN[e], PD[e]), a[e]);
         }
         a[3] = fma(w2, th, a[3]);
         g = gEnd;
