@@ -104,6 +104,16 @@ int i2_integrate_class(i2_context *ctx, int cls, const int *d_tasks, long long n
                        double *d_integrals, double *d_results, unsigned char *d_refinements,
                        unsigned char *d_converged, i2_stats *h_stats);
 
+/* The three classes of Evaluator3D::runAllPairs (src/evaluators/evaluator3d.cu:120-204 calls the three virtuals one
+ * after the other) in ONE call: arrays indexed by I2_CLASS_*; same arguments and results as three i2_integrate_class
+ * calls, but the two adjacent classes (short, latency-bound chains of kernels) are enqueued on internal side streams and
+ * overlap the regular class; the context's stream waits for them before the call returns (fork/join with events, no
+ * host synchronisation unless h_stats is given).  n[k] = 0 skips class k; d_refinements / d_converged / h_stats may be
+ * NULL, and so may their elements.                                                                               */
+int i2_integrate_all(i2_context *ctx, const int *const d_tasks[3], const long long n[3], int level,
+                     double *const d_integrals[3], double *const d_results[3], unsigned char *const d_refinements[3],
+                     unsigned char *const d_converged[3], i2_stats h_stats[3]);
+
 /* ---- list-free regular class ("next" row f1 of SURVEY.md §8: implicit tiled enumeration, no N^2 list) ---------------
  * d_out[i - row_lo] = sum over all triangles j that share no vertex with i (j != i) of w_j * J(K_i, K_j), level 0,
  * for rows row_lo <= i < row_hi; d_weights = double[nc] or NULL (all ones); d_out = Point3[row_hi - row_lo].

@@ -47,7 +47,7 @@ class Stats(C.Structure):
 EXPORTS = [
     "i2_create", "i2_destroy", "i2_set_stream", "i2_synchronize", "i2_set_math_mode", "i2_error_string",
     "i2_set_quadrature", "i2_mesh_geometry", "i2_set_mesh", "i2_classify_count", "i2_classify_fill",
-    "i2_add_reversed_pairs", "i2_integrate_class", "i2_symmetry_error", "i2_host_prepare", "i2_host_run",
+    "i2_add_reversed_pairs", "i2_integrate_class", "i2_integrate_all", "i2_symmetry_error", "i2_host_prepare", "i2_host_run",
     "i2_host_device_views", "i2_host_checksums", "i2_peak_rates", "i2_peak_dfma_three_operand", "i2_refine_mesh_once", "i2_launch_count", "i2_set_profiling", "i2_profile_last", "i2_selftest_math", "i2_apply_regular",
 ]
 
@@ -82,6 +82,7 @@ def load_library():
     L.i2_classify_fill.argtypes = [vp, vp, i32, vp, vp, vp]
     L.i2_add_reversed_pairs.argtypes = [vp, vp, ll]
     L.i2_integrate_class.argtypes = [vp, i32, vp, ll, i32, vp, vp, vp, vp, C.POINTER(Stats)]
+    L.i2_integrate_all.argtypes = [vp, C.POINTER(vp), C.POINTER(ll), i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(Stats)]
     L.i2_symmetry_error.argtypes = [vp, vp, ll, vp]
     L.i2_host_prepare.argtypes = [vp, vp, i32, vp, i32, C.POINTER(ll)]
     L.i2_host_run.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(Stats)]
@@ -219,6 +220,32 @@ class Context:
                                          C.byref(st) if want_stats else None))
         return dict(integrals=integrals, results=results, refinements=refinements, converged=conv,
                     stats=st.as_dict() if want_stats else None)
+
+    def integrate_all(self, tasks, level=0, want_stats=True, refinements=None, out=None):
+        """The three classes in one call (adjacent classes overlap the regular one on side streams).
+        tasks: list of 3 int32[n_k,3] device tensors; out: optional list of 3 (integrals, results) pairs.
+        -> list of 3 dicts like integrate_class."""
+        torch = self.torch
+        dev = tasks[0].device
+        n = [int(t.shape[0]) for t in tasks]
+        if out is None:
+            out = [(torch.empty((n[k], 4), dtype=torch.float64, device=dev), torch.empty((n[k], 3), dtype=torch.float64, device=dev))
+                   for k in range(3)]
+        conv = [None] * 3
+        if level < 0:
+            if refinements is None:
+                refinements = [torch.zeros((self.nc,), dtype=torch.uint8, device=dev) for _ in range(3)]
+            conv = [torch.zeros((n[k],), dtype=torch.uint8, device=dev) for k in range(3)]
+        else:
+            refinements = [None] * 3
+
+        def arr(ts):
+            return (C.c_void_p * 3)(*[_ptr(t) for t in ts])
+        st = (Stats * 3)()
+        _check(self.L.i2_integrate_all(self.h, arr(tasks), (C.c_longlong * 3)(*n), level, arr([o[0] for o in out]), arr([o[1] for o in out]),
+                                       arr(refinements), arr(conv), st if want_stats else None))
+        return [dict(integrals=out[k][0], results=out[k][1], refinements=refinements[k], converged=conv[k],
+                     stats=st[k].as_dict() if want_stats else None) for k in range(3)]
 
     def apply_regular(self, row_lo, row_hi, weights=None, out=None):
         """out[i-row_lo] = sum_{j not sharing a vertex with i} w_j J(K_i,K_j) without any task list (device tensors)."""

@@ -33,14 +33,19 @@ struct i2_context {
     int stride = 0;
     size_t triCap = 0;
 
-    // adaptive work queue scratch (owned, grown on demand)
-    double *bufB = nullptr;
-    size_t bufBCap = 0;
-    int *rest[2] = {nullptr, nullptr};
-    size_t restCap = 0;
-    unsigned char *cellFlag = nullptr;
-    size_t cellFlagCap = 0;
-    QueueState *qs = nullptr;
+    // work queue scratch, one set per neighbour class so that the three classes can run concurrently (owned, grown on demand)
+    struct ClassScratch {
+        double *bufB = nullptr;
+        size_t bufBCap = 0;
+        int *rest[2] = {nullptr, nullptr};
+        size_t restCap = 0;
+        unsigned char *cellFlag = nullptr;
+        size_t cellFlagCap = 0;
+        QueueState *qs = nullptr;
+    } scr[3];
+    // i2_integrate_all / i2_host_run: the two adjacent classes run on side streams next to the regular class
+    cudaStream_t side[2] = {nullptr, nullptr};
+    cudaEvent_t forkEv = nullptr, sideDone[2] = {nullptr, nullptr};
 
     // matrix-free path scratch (per-chunk partial row sums)
     double *partial = nullptr;
@@ -130,7 +135,10 @@ int i2_create(i2_context **out, int device) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking);
     for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&c->chunkDone[k], cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&c->qs, sizeof(QueueState));
+    for (int k = 0; k < 3 && e == cudaSuccess; ++k) e = cudaMalloc((void **)&c->scr[k].qs, sizeof(QueueState));
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaStreamCreateWithFlags(&c->side[k], cudaStreamNonBlocking);
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&c->sideDone[k], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->forkEv, cudaEventDisableTiming);
     if (e == cudaSuccess) e = upload_math_tables(c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e == cudaSuccess) e = preload_kernels();
@@ -148,10 +156,18 @@ int i2_destroy(i2_context *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     freeHostState(c);
     if (c->tri) cudaFree(c->tri);
-    if (c->bufB) cudaFree(c->bufB);
-    for (int k = 0; k < 2; ++k) { if (c->rest[k]) cudaFree(c->rest[k]); if (c->chunkDone[k]) cudaEventDestroy(c->chunkDone[k]); }
-    if (c->cellFlag) cudaFree(c->cellFlag);
-    if (c->qs) cudaFree(c->qs);
+    for (int k = 0; k < 2; ++k) {
+        if (c->side[k]) { cudaStreamSynchronize(c->side[k]); cudaStreamDestroy(c->side[k]); }
+        if (c->sideDone[k]) cudaEventDestroy(c->sideDone[k]);
+        if (c->chunkDone[k]) cudaEventDestroy(c->chunkDone[k]);
+    }
+    if (c->forkEv) cudaEventDestroy(c->forkEv);
+    for (auto &sc : c->scr) {
+        if (sc.bufB) cudaFree(sc.bufB);
+        for (int k = 0; k < 2; ++k) if (sc.rest[k]) cudaFree(sc.rest[k]);
+        if (sc.cellFlag) cudaFree(sc.cellFlag);
+        if (sc.qs) cudaFree(sc.qs);
+    }
     for (int k = 0; k < 3; ++k) if (c->prof[k]) cudaEventDestroy(c->prof[k]);
     if (c->rowCounts) cudaFree(c->rowCounts);
     if (c->partial) cudaFree(c->partial);
@@ -270,76 +286,139 @@ int i2_add_reversed_pairs(i2_context *c, int *tasks, long long n) {
     return 0;
 }
 
-int i2_integrate_class(i2_context *c, int cls, const int *tasks, long long n, int level, double *integrals, double *results,
-                       unsigned char *refinements, unsigned char *converged, i2_stats *stats) {
-    if (!c || cls < 0 || cls > 2 || n < 0) return I2_E_BADARG;
-    if (stats) std::memset(stats, 0, sizeof(*stats));
+namespace {
+
+// argument checks shared by i2_integrate_class / i2_integrate_all (n == 0 is valid and does nothing)
+int check_class_args(const i2_context *c, int cls, const int *tasks, long long n, int level, const double *integrals, const double *results) {
+    if (cls < 0 || cls > 2 || n < 0) return I2_E_BADARG;
     if (n == 0) return 0;
     if (!tasks || !integrals || !results) return I2_E_BADARG;
     if (!c->tri) return I2_E_NOMESH;
     if (!c->haveQuad) return I2_E_NOQUAD;
     if (level > 12) return I2_E_LEVEL;
     if (n > INT_MAX) return I2_E_TOOBIG;
-    I2_CUDA(cudaSetDevice(c->device));
-    cudaStream_t s = c->stream;
+    return 0;
+}
+
+// enqueues the whole of one class on stream s (no synchronisation); uses the class's own scratch
+int enqueue_class(i2_context *c, int cls, const int *tasks, long long n, int level, double *integrals, double *results,
+                  unsigned char *refinements, unsigned char *converged, cudaStream_t s, bool profile) {
+    i2_context::ClassScratch &sc = c->scr[cls];
     const PackedMesh pm = packed(c);
-    I2_CUDA(cudaMemsetAsync(c->qs, 0, sizeof(QueueState), s));
+    I2_CUDA(cudaMemsetAsync(sc.qs, 0, sizeof(QueueState), s));
     bool fused = false;
 
     if (level >= 0) {
-        if (c->profiling) I2_CUDA(cudaEventRecord(c->prof[0], s));
+        if (profile) I2_CUDA(cudaEventRecord(c->prof[0], s));
         // regular pairs with the grouped kernel: the final assembly is fused into the integrate kernel
         fused = (cls == 2 && c->mathMode == I2_MATH_FAST);
         launch_integrate(cls, c->mathMode, pm, tasks, nullptr, nullptr, n, level, integrals, fused ? results : nullptr, c->numSMs, s);
-        if (c->profiling) I2_CUDA(cudaEventRecord(c->prof[1], s));
+        if (profile) I2_CUDA(cudaEventRecord(c->prof[1], s));
     } else {
-        int rc = ensure(&c->bufB, &c->bufBCap, (size_t)4 * n);
+        int rc = ensure(&sc.bufB, &sc.bufBCap, (size_t)4 * n);
         if (rc) return rc;
-        if ((size_t)n > c->restCap) {
-            size_t cap0 = c->restCap, cap1 = c->restCap;
-            rc = ensure(&c->rest[0], &cap0, (size_t)n);
+        if ((size_t)n > sc.restCap) {
+            size_t cap0 = sc.restCap, cap1 = sc.restCap;
+            rc = ensure(&sc.rest[0], &cap0, (size_t)n);
             if (rc) return rc;
-            rc = ensure(&c->rest[1], &cap1, (size_t)n);
+            rc = ensure(&sc.rest[1], &cap1, (size_t)n);
             if (rc) return rc;
-            c->restCap = (size_t)n;
+            sc.restCap = (size_t)n;
         }
-        rc = ensure(&c->cellFlag, &c->cellFlagCap, (size_t)c->nc);
+        rc = ensure(&sc.cellFlag, &sc.cellFlagCap, (size_t)c->nc);
         if (rc) return rc;
-        I2_CUDA(cudaMemsetAsync(c->cellFlag, 0, c->nc, s));
+        I2_CUDA(cudaMemsetAsync(sc.cellFlag, 0, c->nc, s));
 
         // round 0: every task on the original control panel; every control panel present in the list is marked
         launch_integrate(cls, c->mathMode, pm, tasks, nullptr, nullptr, n, 0, integrals, nullptr, c->numSMs, s);
-        launch_flag_cells(tasks, n, c->cellFlag, s);
-        launch_bump(c->cellFlag, refinements, c->nc, s);
+        launch_flag_cells(tasks, n, sc.cellFlag, s);
+        launch_bump(sc.cellFlag, refinements, c->nc, s);
         // rounds 1..5 are enqueued unconditionally; a round whose device-side task count is 0 does nothing.
         for (int m = 1; m <= MAX_REFINE_LEVEL; ++m) {
-            double *cur = (m & 1) ? c->bufB : integrals;
-            const double *prev = (m & 1) ? integrals : c->bufB;
-            const int *listIn = m == 1 ? nullptr : c->rest[(m - 1) & 1];
-            const int *countIn = m == 1 ? nullptr : &c->qs->count[m - 1];
+            double *cur = (m & 1) ? sc.bufB : integrals;
+            const double *prev = (m & 1) ? integrals : sc.bufB;
+            const int *listIn = m == 1 ? nullptr : sc.rest[(m - 1) & 1];
+            const int *countIn = m == 1 ? nullptr : &sc.qs->count[m - 1];
             launch_integrate(cls, c->mathMode, pm, tasks, listIn, countIn, n, m, cur, nullptr, c->numSMs, s);
-            launch_compare(cur, prev, tasks, listIn, countIn, n, c->rest[m & 1], &c->qs->count[m], c->cellFlag, converged, c->qs, m,
+            launch_compare(cur, prev, tasks, listIn, countIn, n, sc.rest[m & 1], &sc.qs->count[m], sc.cellFlag, converged, sc.qs, m,
                            c->numSMs, s);
-            launch_bump(c->cellFlag, refinements, c->nc, s);
+            launch_bump(sc.cellFlag, refinements, c->nc, s);
         }
     }
-    if (!fused) launch_finalize(cls, pm, c->verts, tasks, n, integrals, c->bufB, c->qs, results, c->qs, s);
+    if (!fused) launch_finalize(cls, pm, c->verts, tasks, n, integrals, sc.bufB, sc.qs, results, sc.qs, s);
     I2_CUDA(cudaGetLastError());
-    if (c->profiling && level >= 0) I2_CUDA(cudaEventRecord(c->prof[2], s));
+    if (profile && level >= 0) I2_CUDA(cudaEventRecord(c->prof[2], s));
+    return 0;
+}
 
+void fill_stats(const QueueState &h, long long n, int level, i2_stats *stats) {
+    stats->last_round = h.lastRound;
+    stats->orientation_warnings = h.orientationWarnings;
+    stats->integrated[0] = n << (level > 0 ? 2 * level : 0);
+    long long before = n;
+    for (int m = 1; m <= h.lastRound && m <= MAX_REFINE_LEVEL; ++m) {
+        stats->integrated[m] = before << (2 * m);
+        stats->unconverged[m] = h.count[m];
+        before = h.count[m];
+    }
+}
+
+}  // namespace
+
+int i2_integrate_class(i2_context *c, int cls, const int *tasks, long long n, int level, double *integrals, double *results,
+                       unsigned char *refinements, unsigned char *converged, i2_stats *stats) {
+    if (!c) return I2_E_BADARG;
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    int rc = check_class_args(c, cls, tasks, n, level, integrals, results);
+    if (rc || n == 0) return rc;
+    I2_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    rc = enqueue_class(c, cls, tasks, n, level, integrals, results, refinements, converged, s, c->profiling);
+    if (rc) return rc;
     if (stats) {
         QueueState h;
-        I2_CUDA(cudaMemcpyAsync(&h, c->qs, sizeof(h), cudaMemcpyDeviceToHost, s));
+        I2_CUDA(cudaMemcpyAsync(&h, c->scr[cls].qs, sizeof(h), cudaMemcpyDeviceToHost, s));
         I2_CUDA(cudaStreamSynchronize(s));
-        stats->last_round = h.lastRound;
-        stats->orientation_warnings = h.orientationWarnings;
-        stats->integrated[0] = n << (level > 0 ? 2 * level : 0);
-        long long before = n;
-        for (int m = 1; m <= h.lastRound && m <= MAX_REFINE_LEVEL; ++m) {
-            stats->integrated[m] = before << (2 * m);
-            stats->unconverged[m] = h.count[m];
-            before = h.count[m];
-        }
+        fill_stats(h, n, level, stats);
+    }
+    return 0;
+}
+
+int i2_integrate_all(i2_context *c, const int *const tasks[3], const long long n[3], int level, double *const integrals[3],
+                     double *const results[3], unsigned char *const refinements[3], unsigned char *const converged[3], i2_stats stats[3]) {
+    if (!c || !tasks || !n || !integrals || !results) return I2_E_BADARG;
+    if (stats) std::memset(stats, 0, 3 * sizeof(i2_stats));
+    for (int k = 0; k < 3; ++k) {
+        const int rc = check_class_args(c, k, tasks[k], n[k], level, integrals[k], results[k]);
+        if (rc) return rc;
+    }
+    I2_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    // fork: the two adjacent classes (small, latency-bound chains of kernels) go to the side streams and overlap the
+    // regular class on the context's stream; join: the context's stream waits for both
+    I2_CUDA(cudaEventRecord(c->forkEv, s));
+    for (int k = 0; k < 2; ++k) {
+        if (n[k] == 0) continue;
+        I2_CUDA(cudaStreamWaitEvent(c->side[k], c->forkEv, 0));
+        const int rc = enqueue_class(c, k, tasks[k], n[k], level, integrals[k], results[k], refinements ? refinements[k] : nullptr,
+                                     converged ? converged[k] : nullptr, c->side[k], false);
+        if (rc) return rc;
+        I2_CUDA(cudaEventRecord(c->sideDone[k], c->side[k]));
+    }
+    if (n[2] > 0) {
+        const int rc = enqueue_class(c, 2, tasks[2], n[2], level, integrals[2], results[2], refinements ? refinements[2] : nullptr,
+                                     converged ? converged[2] : nullptr, s, c->profiling);
+        if (rc) return rc;
+    }
+    for (int k = 0; k < 2; ++k)
+        if (n[k] > 0) I2_CUDA(cudaStreamWaitEvent(s, c->sideDone[k], 0));
+    if (stats) {
+        QueueState h[3];
+        for (int k = 0; k < 3; ++k)
+            if (n[k] > 0) I2_CUDA(cudaMemcpyAsync(&h[k], c->scr[k].qs, sizeof(QueueState), cudaMemcpyDeviceToHost, s));
+        I2_CUDA(cudaStreamSynchronize(s));
+        for (int k = 0; k < 3; ++k)
+            if (n[k] > 0) fill_stats(h[k], n[k], level, &stats[k]);
     }
     return 0;
 }
@@ -443,22 +522,62 @@ int i2_host_run(i2_context *c, int level, int *const hTasks[3], double *const hR
                 unsigned char *const hRefinements[3], i2_stats hStats[3]) {
     if (!c) return I2_E_BADARG;
     if (!c->hVerts) return I2_E_NOMESH;
+    if (!c->haveQuad) return I2_E_NOQUAD;
+    if (level > 12) return I2_E_LEVEL;
     I2_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = c->stream, cs = c->copyStream;
-    const long long chunkTasks = 1LL << 24;  // 16 Mi tasks: 384 MiB of Point3 per chunk
-    int turn = 0;
-    for (int k = 0; k < 3; ++k) {
+    if (hStats) std::memset(hStats, 0, 3 * sizeof(i2_stats));
+
+    // one whole class on stream st: integration, optional (i,j)/(j,i) defect, device-to-host copies; no synchronisation
+    auto whole = [&](int k, cudaStream_t st) -> int {
+        const long long n = c->hCount[k];
+        int rc = enqueue_class(c, k, c->hTasks[k], n, level, c->hIntegrals[k], c->hResults[k], level < 0 ? c->hRefinements[k] : nullptr,
+                               nullptr, st, false);
+        if (rc) return rc;
+        if (hErrors && hErrors[k]) {
+            rc = ensure(&c->hErrors[k], &c->capErrors[k], (size_t)n);
+            if (rc) return rc;
+            launch_symmetry_error(c->hResults[k], n / 2, c->hErrors[k], st);
+            I2_CUDA(cudaGetLastError());
+            I2_CUDA(cudaMemcpyAsync(hErrors[k], c->hErrors[k], sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+        }
+        if (hResults && hResults[k])
+            I2_CUDA(cudaMemcpyAsync(hResults[k], c->hResults[k], sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, st));
+        if (hTasks && hTasks[k])
+            I2_CUDA(cudaMemcpyAsync(hTasks[k], c->hTasks[k], sizeof(int) * 3 * n, cudaMemcpyDeviceToHost, st));
+        if (level < 0 && hRefinements && hRefinements[k])
+            I2_CUDA(cudaMemcpyAsync(hRefinements[k], c->hRefinements[k], c->nc, cudaMemcpyDeviceToHost, st));
+        return 0;
+    };
+
+    // fork: the adjacent classes run on the side streams, concurrently with the regular class on the context's stream
+    I2_CUDA(cudaEventRecord(c->forkEv, s));
+    for (int k = 0; k < 2; ++k) {
+        cudaStream_t st = c->side[k];
+        I2_CUDA(cudaStreamWaitEvent(st, c->forkEv, 0));
+        if (level < 0) I2_CUDA(cudaMemsetAsync(c->hRefinements[k], 0, c->nc, st));
+        if (c->hCount[k] > 0) {
+            const int rc = whole(k, st);
+            if (rc) return rc;
+        }
+        I2_CUDA(cudaEventRecord(c->sideDone[k], st));
+    }
+    {
+        const int k = 2;
         const long long n = c->hCount[k];
         if (level < 0) I2_CUDA(cudaMemsetAsync(c->hRefinements[k], 0, c->nc, s));
-        if (n == 0) { if (hStats) std::memset(&hStats[k], 0, sizeof(i2_stats)); continue; }
         const bool wantErr = hErrors && hErrors[k];
-        if (level >= 0 && !wantErr) {
+        if (n > 0 && level >= 0 && !wantErr) {
             // fixed level: tasks are independent -> integrate chunk by chunk, copy each finished chunk on the copy stream
-            for (long long off = 0; off < n; off += chunkTasks) {
-                const long long m = (n - off < chunkTasks) ? (n - off) : chunkTasks;
-                int rc = i2_integrate_class(c, k, c->hTasks[k] + 3 * off, m, level, c->hIntegrals[k] + 4 * off, c->hResults[k] + 3 * off,
-                                            nullptr, nullptr, nullptr);
+            const long long chunkTasks = 1LL << 24;  // 16 Mi tasks: 384 MiB of Point3 per chunk
+            const bool copyOut = (hResults && hResults[k]) || (hTasks && hTasks[k]);
+            int turn = 0;
+            for (long long off = 0; off < n; off += copyOut ? chunkTasks : n) {
+                const long long m = !copyOut ? n : ((n - off < chunkTasks) ? (n - off) : chunkTasks);
+                int rc = enqueue_class(c, k, c->hTasks[k] + 3 * off, m, level, c->hIntegrals[k] + 4 * off, c->hResults[k] + 3 * off,
+                                       nullptr, nullptr, s, false);
                 if (rc) return rc;
+                if (!copyOut) break;
                 I2_CUDA(cudaEventRecord(c->chunkDone[turn], s));
                 I2_CUDA(cudaStreamWaitEvent(cs, c->chunkDone[turn], 0));
                 turn ^= 1;
@@ -467,28 +586,21 @@ int i2_host_run(i2_context *c, int level, int *const hTasks[3], double *const hR
                 if (hTasks && hTasks[k])
                     I2_CUDA(cudaMemcpyAsync(hTasks[k] + 3 * off, c->hTasks[k] + 3 * off, sizeof(int) * 3 * m, cudaMemcpyDeviceToHost, cs));
             }
-            if (hStats) { std::memset(&hStats[k], 0, sizeof(i2_stats)); hStats[k].integrated[0] = n << (2 * level); }
-        } else {
-            int rc = i2_integrate_class(c, k, c->hTasks[k], n, level, c->hIntegrals[k], c->hResults[k],
-                                        level < 0 ? c->hRefinements[k] : nullptr, nullptr, hStats ? &hStats[k] : nullptr);
+        } else if (n > 0) {
+            const int rc = whole(k, s);
             if (rc) return rc;
-            if (wantErr) {
-                rc = ensure(&c->hErrors[k], &c->capErrors[k], (size_t)n);
-                if (rc) return rc;
-                rc = i2_symmetry_error(c, c->hResults[k], n / 2, c->hErrors[k]);
-                if (rc) return rc;
-                I2_CUDA(cudaMemcpyAsync(hErrors[k], c->hErrors[k], sizeof(double) * n, cudaMemcpyDeviceToHost, s));
-            }
-            if (hResults && hResults[k])
-                I2_CUDA(cudaMemcpyAsync(hResults[k], c->hResults[k], sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, s));
-            if (hTasks && hTasks[k])
-                I2_CUDA(cudaMemcpyAsync(hTasks[k], c->hTasks[k], sizeof(int) * 3 * n, cudaMemcpyDeviceToHost, s));
-            if (level < 0 && hRefinements && hRefinements[k])
-                I2_CUDA(cudaMemcpyAsync(hRefinements[k], c->hRefinements[k], c->nc, cudaMemcpyDeviceToHost, s));
         }
     }
+    for (int k = 0; k < 2; ++k) I2_CUDA(cudaStreamWaitEvent(s, c->sideDone[k], 0));   // join
+    QueueState h[3];
+    if (hStats)
+        for (int k = 0; k < 3; ++k)
+            if (c->hCount[k] > 0) I2_CUDA(cudaMemcpyAsync(&h[k], c->scr[k].qs, sizeof(QueueState), cudaMemcpyDeviceToHost, s));
     I2_CUDA(cudaStreamSynchronize(s));
     I2_CUDA(cudaStreamSynchronize(cs));
+    if (hStats)
+        for (int k = 0; k < 3; ++k)
+            if (c->hCount[k] > 0) fill_stats(h[k], c->hCount[k], level, &hStats[k]);
     return 0;
 }
 

@@ -261,3 +261,32 @@ def test_deep_fixed_levels_all_classes_G1(ctx, oracle, level):
         ref = om.run_class(cls, tasks, level)
         rel = np.abs(r["results"].cpu().numpy() - ref["results"]).sum(1) / np.abs(ref["results"]).sum(1)
         assert rel.max() < 2e-12, (cls, level, rel.max())
+
+
+@pytest.mark.parametrize("level", [0, 1, -1])
+def test_integrate_all_equals_three_class_calls(ctx, oracle, level):
+    """i2_integrate_all (adjacent classes on side streams, overlapping the regular class) == three i2_integrate_class calls,
+    bit for bit, including the adaptive counters."""
+    import torch
+    m, om = _setup(ctx, oracle, "s5m", 0.0005)
+    tasks = [torch.as_tensor(om.tasks(c)).cuda() for c in range(3)]
+    one = [ctx.integrate_class(c, tasks[c], level) for c in range(3)]
+    for rep in range(2):      # twice: the per-class scratch is reused
+        allr = ctx.integrate_all(tasks, level)
+        for c in range(3):
+            assert torch.equal(allr[c]["results"], one[c]["results"]), (level, c)
+            assert torch.equal(allr[c]["integrals"], one[c]["integrals"]), (level, c)
+            assert allr[c]["stats"] == one[c]["stats"], (level, c)
+            if level < 0:
+                assert torch.equal(allr[c]["refinements"], one[c]["refinements"])
+                assert torch.equal(allr[c]["converged"], one[c]["converged"])
+
+
+def test_integrate_all_skips_empty_classes(ctx, oracle):
+    import torch
+    m, om = _setup(ctx, oracle, "G1")
+    t2 = torch.as_tensor(om.tasks(2)).cuda()
+    empty = torch.empty((0, 3), dtype=torch.int32, device="cuda")
+    r = ctx.integrate_all([empty, empty, t2], 0)
+    ref = ctx.integrate_class(2, t2, 0)
+    assert torch.equal(r[2]["results"], ref["results"]) and r[0]["results"].shape[0] == 0
