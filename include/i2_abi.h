@@ -142,6 +142,21 @@ int i2_host_checksums(i2_context *ctx, double h_sums[12]);
 /* device views of what i2_host_prepare built (valid until the next prepare/destroy)                        */
 int i2_host_device_views(i2_context *ctx, const int *d_tasks[3], const double *d_results[3]);
 
+/* ---- multi-GPU export: per-pair results written straight into the exporting GPU's memory over NVLink ---------------
+ * (no reference counterpart: /root/reference is single-GPU).  One process per GPU.  The exporting rank
+ * allocates the full result array with i2_peer_alloc (cudaMalloc + CUDA IPC handle, 64 opaque bytes the host side ships
+ * to the other processes by any means, e.g. torch.distributed.broadcast_object_list); every other rank maps it with
+ * i2_peer_open and passes `mapped + 24 * first_slot_of_its_shard` as d_results of i2_integrate_class / i2_integrate_all:
+ * the final-assembly stores of the kernels then ARE the gather (coalesced 768-byte warp stores through NVSwitch, no
+ * staging copy, no second pass), overlapped with the arithmetic of the other warps.  The data are visible to the owner
+ * once the writer's stream has been synchronised (i2_synchronize) and the processes have met at a host barrier.
+ * i2_peer_close unmaps (writer side), i2_peer_free releases (owner side).                                           */
+#define I2_PEER_HANDLE_BYTES 64
+int i2_peer_alloc(i2_context *ctx, unsigned long long bytes, void **d_ptr, unsigned char h_handle[I2_PEER_HANDLE_BYTES]);
+int i2_peer_open(i2_context *ctx, const unsigned char h_handle[I2_PEER_HANDLE_BYTES], void **d_ptr);
+int i2_peer_close(i2_context *ctx, void *d_ptr);
+int i2_peer_free(i2_context *ctx, void *d_ptr);
+
 /* ---- instrumentation for bench.py -------------------------------------------------------------------------
  * launch counter: kernels launched by this library since process start (all contexts).
  * profiling: when enabled, i2_integrate_class brackets its integrate kernel(s) and its finalize kernel with CUDA

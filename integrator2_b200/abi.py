@@ -48,7 +48,7 @@ EXPORTS = [
     "i2_create", "i2_destroy", "i2_set_stream", "i2_synchronize", "i2_set_math_mode", "i2_error_string",
     "i2_set_quadrature", "i2_mesh_geometry", "i2_set_mesh", "i2_classify_count", "i2_classify_fill",
     "i2_add_reversed_pairs", "i2_integrate_class", "i2_integrate_all", "i2_symmetry_error", "i2_host_prepare", "i2_host_run",
-    "i2_host_device_views", "i2_host_checksums", "i2_peak_rates", "i2_peak_dfma_three_operand", "i2_refine_mesh_once", "i2_launch_count", "i2_set_profiling", "i2_profile_last", "i2_selftest_math", "i2_apply_regular",
+    "i2_host_device_views", "i2_host_checksums", "i2_peer_alloc", "i2_peer_open", "i2_peer_close", "i2_peer_free", "i2_peak_rates", "i2_peak_dfma_three_operand", "i2_refine_mesh_once", "i2_launch_count", "i2_set_profiling", "i2_profile_last", "i2_selftest_math", "i2_apply_regular",
 ]
 
 _lib = None
@@ -96,6 +96,10 @@ def load_library():
     L.i2_profile_last.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.i2_peak_dfma_three_operand.argtypes = [vp, C.POINTER(C.c_double)]
     L.i2_peak_rates.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.i2_peer_alloc.argtypes = [vp, C.c_ulonglong, C.POINTER(vp), C.c_char_p]
+    L.i2_peer_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
+    L.i2_peer_close.argtypes = [vp, vp]
+    L.i2_peer_free.argtypes = [vp, vp]
     for name in EXPORTS:
         if name != "i2_error_string":
             getattr(L, name).restype = i32
@@ -109,7 +113,19 @@ def _check(rc):
 
 
 def _ptr(t):
-    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+    """device tensor, raw device address (int, e.g. a peer-mapped pointer from Context.peer_open) or None"""
+    if t is None:
+        return C.c_void_p(0)
+    if isinstance(t, int):
+        return C.c_void_p(t)
+    return C.c_void_p(t.data_ptr())
+
+
+class _RawCudaBuffer:
+    """__cuda_array_interface__ view of a device allocation owned by the library (Context.peer_alloc)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
 def launch_count() -> int:
@@ -287,6 +303,29 @@ class Context:
         a = C.c_double()
         _check(self.L.i2_peak_dfma_three_operand(self.h, C.byref(a)))
         return float(a.value)
+
+    # ---- multi-GPU export over NVLink peer stores ------------------------------------------------------------
+    def peer_alloc(self, rows, cols=3):
+        """Owner side: float64[rows, cols] allocation of its own + the 64-byte CUDA IPC handle to ship to the other
+        processes.  -> (tensor view on this device, handle bytes, raw address)"""
+        p = C.c_void_p()
+        h = C.create_string_buffer(64)
+        _check(self.L.i2_peer_alloc(self.h, int(max(1, rows)) * cols * 8, C.byref(p), h))
+        view = self.torch.as_tensor(_RawCudaBuffer(p.value, (int(rows), cols), "<f8"), device=f"cuda:{self.device}")
+        return view, h.raw, int(p.value)
+
+    def peer_open(self, handle: bytes) -> int:
+        """Writer side: map the owner's allocation into this process; returns the raw device address (valid on this
+        context's device; pass `addr + 24 * first_slot` as the `results` of integrate_class / integrate_all)."""
+        p = C.c_void_p()
+        _check(self.L.i2_peer_open(self.h, C.create_string_buffer(handle, 64), C.byref(p)))
+        return int(p.value)
+
+    def peer_close(self, addr: int):
+        _check(self.L.i2_peer_close(self.h, C.c_void_p(addr)))
+
+    def peer_free(self, addr: int):
+        _check(self.L.i2_peer_free(self.h, C.c_void_p(addr)))
 
     # ---- host-buffer API (end-to-end) ------------------------------------------------------------------
     def host_prepare(self, vertices, cells):

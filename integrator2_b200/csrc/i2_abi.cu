@@ -612,6 +612,51 @@ int i2_selftest_math(i2_context *c, int op, const double *a, const double *b, lo
     return 0;
 }
 
+// ---- multi-GPU export over NVLink peer stores: the owner's result array is mapped into the other processes, and the
+//      kernels' final-assembly stores write into it directly (see include/i2_abi.h) ------------------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == I2_PEER_HANDLE_BYTES, "CUDA IPC handle size");
+
+int i2_peer_alloc(i2_context *c, unsigned long long bytes, void **ptr, unsigned char handle[I2_PEER_HANDLE_BYTES]) {
+    if (!c || !ptr || !handle || bytes == 0) return I2_E_BADARG;
+    I2_CUDA(cudaSetDevice(c->device));
+    void *p = nullptr;
+    I2_CUDA(cudaMalloc(&p, (size_t)bytes));     // a whole allocation of its own: an IPC handle always maps from the base
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return (int)e;
+    }
+    std::memcpy(handle, &h, sizeof(h));
+    *ptr = p;
+    return 0;
+}
+
+int i2_peer_open(i2_context *c, const unsigned char handle[I2_PEER_HANDLE_BYTES], void **ptr) {
+    if (!c || !ptr || !handle) return I2_E_BADARG;
+    I2_CUDA(cudaSetDevice(c->device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    // cudaIpcMemLazyEnablePeerAccess: the mapping enables peer access between the two devices (NVLink / NVSwitch) on demand
+    I2_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int i2_peer_close(i2_context *c, void *ptr) {
+    if (!c || !ptr) return I2_E_BADARG;
+    I2_CUDA(cudaSetDevice(c->device));
+    I2_CUDA(cudaStreamSynchronize(c->stream));
+    I2_CUDA(cudaIpcCloseMemHandle(ptr));
+    return 0;
+}
+
+int i2_peer_free(i2_context *c, void *ptr) {
+    if (!c || !ptr) return I2_E_BADARG;
+    I2_CUDA(cudaSetDevice(c->device));
+    I2_CUDA(cudaFree(ptr));
+    return 0;
+}
+
 int i2_launch_count(long long *count) {
     if (!count) return I2_E_BADARG;
     *count = g_launchCount;

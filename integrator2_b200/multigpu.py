@@ -4,7 +4,9 @@ The path shards naturally: every ordered pair (and every refined child of it) is
 (/root/reference has no multi-GPU code at all).  Each class's task list is cut into `world` contiguous shards of
 equal predicted cost; all refined descendants of a task stay on the task's rank, so the per-task sums and the Runge
 decisions are local.  The only exchange step is the gather of the per-pair results (Point3, 24 B/pair) to the
-exporting rank, done with NCCL point-to-point transfers over NVLink (variable-length shards, no padding).
+exporting rank.  Two implementations: `PeerExport` (default for the export use case) maps the exporting rank's array into
+every process and lets the integrate kernels store their results into it directly over NVLink (compute + gather fused in
+one kernel); `integrate_and_gather` is the NCCL point-to-point baseline (variable-length shards, chunks overlapped).
 """
 from __future__ import annotations
 
@@ -110,6 +112,44 @@ def integrate_and_gather(ctx, cls, tasks_local, level, out_local, full, bounds, 
             if ops:
                 works += dist.batch_isend_irecv(ops)
     return works
+
+
+class PeerExport:
+    """Export array of one class (Point3[n_total]) living on rank `dst`, mapped into every other rank's address space
+    with CUDA IPC (C ABI: i2_peer_alloc / i2_peer_open).  A rank passes `results_arg()` as the results pointer of
+    integrate_class / integrate_all: the kernels' final-assembly stores then land in rank dst's HBM directly over
+    NVLink — compute and gather are ONE kernel, there is no staging buffer, no NCCL call and no second pass over the data.
+    After the step: torch.cuda.synchronize() on every rank, then a host barrier; `full` (rank dst) is complete."""
+
+    def __init__(self, ctx, n_total, bounds, rank, world, dst=0, handle_exchange=None):
+        self.ctx, self.bounds, self.rank, self.dst = ctx, bounds, rank, dst
+        self.full, self.addr, self.mapped = None, 0, False
+        handle = None
+        if rank == dst:
+            self.full, handle, self.addr = ctx.peer_alloc(n_total)
+        if world > 1:
+            if handle_exchange is None:
+                import torch.distributed as dist
+                box = [handle]
+                dist.broadcast_object_list(box, src=dst)
+                handle = box[0]
+            else:
+                handle = handle_exchange(handle)
+            if rank != dst:
+                self.addr = ctx.peer_open(handle)
+                self.mapped = True
+
+    def results_arg(self):
+        """raw device address of this rank's row block inside the export array (24 B per Point3 row)"""
+        return self.addr + 24 * self.bounds[self.rank][0]
+
+    def close(self):
+        if self.mapped:
+            self.ctx.peer_close(self.addr)
+        elif self.addr:
+            self.full = None
+            self.ctx.peer_free(self.addr)
+        self.addr, self.mapped = 0, False
 
 
 def wait_all(works, side_stream=None):
