@@ -320,6 +320,46 @@ def main():
                        "what": "same step, but every per-pair Point3 result is also gathered to rank 0 (NCCL point-to-point, 8 chunks "
                                "overlapped with compute); bound by rank 0's NVLink ingest, reported for the export use case"}
 
+    # ---- N > 1: export variant with the gather FUSED into the integrate kernels: rank 0's export arrays are mapped into every
+    # process (CUDA IPC) and each rank's kernels store their per-pair results straight into them over NVLink/NVSwitch
+    peer_info = None
+    if world > 1:
+        from integrator2_b200.multigpu import PeerExport
+        gathered = None
+        torch.cuda.empty_cache()
+        exports = [PeerExport(ctx, counts[k], all_bounds[k], rank, world) for k in range(3)]
+        peer_out = [(outs[k][0], exports[k].results_arg()) for k in range(3)]
+
+        def step_peer():
+            if refins is not None:
+                for r in refins:
+                    r.zero_()
+            ctx.integrate_all(tasks, args.level, want_stats=False, refinements=refins, out=peer_out)
+
+        for _ in range(2):
+            step_peer()
+        barrier()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(stream)
+        for _ in range(args.steps):
+            step_peer()
+        p1.record(stream)
+        barrier()
+        tp = torch.tensor([p0.elapsed_time(p1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        ms_p = float(tp.item()) / args.steps
+        chk_peer = [float(e.full.abs().sum()) for e in exports] if rank == 0 else None
+        peer_info = {"value": total_pairs / (ms_p * 1e-3), "unit": UNIT, "ms_per_step": ms_p,
+                     "bytes_into_rank0_per_step": int(sum(counts) * 24 * (world - 1) / world),
+                     "checksum_sum_abs_J_on_rank0": chk_peer,
+                     "what": "same step with compute and gather fused: every rank's kernels store their per-pair Point3 results directly into "
+                             "rank 0's export arrays over NVLink peer mappings (i2_peer_alloc / i2_peer_open, multigpu.PeerExport); no NCCL "
+                             "call, no staging copy"}
+        barrier()
+        for e in exports:
+            e.close()
+        barrier()
+
     # ---- roofline of the dominant kernel (regular pairs), measured live with CUDA events on the launch stream ----
     roof = None
     if rank == 0:
@@ -359,22 +399,32 @@ def main():
     #   e2e.full_d2h         additionally every per-pair result and its (i,j) key is copied to pinned host memory
     #                        (what outputResultsToFile does before formatting): 36 B/pair, PCIe-bound.
     e2e = None
-    if not args.no_e2e and world == 1:
-        del outs, tasks, tasks_full
+    if not args.no_e2e:
+        del outs, tasks
+        if world == 1:
+            del tasks_full
         torch.cuda.empty_cache()
         c2 = abi.Context(local)
-        cnt = c2.host_prepare(mesh.vertices, mesh.cells)
+        c2.host_set_shard(rank, world)     # N > 1: every rank prepares the (replicated, 0.4 MB) mesh and integrates its shard
+        cnt_full = c2.host_prepare(mesh.vertices, mesh.cells)
+        cnt = c2.host_shard()[1]
         reps = max(2, min(args.steps, 5))
 
         def timed(fn):
+            # host clock around the blocking calls; N > 1: ranks start together and the slowest rank's time counts
             for _ in range(2):
                 fn()
-            torch.cuda.synchronize()
+            barrier()
             t0 = time.perf_counter()
             for _ in range(reps):
                 fn()
             torch.cuda.synchronize()
-            return (time.perf_counter() - t0) / reps
+            dt = (time.perf_counter() - t0) / reps
+            if world > 1:
+                tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dt = float(tt.item())
+            return dt
 
         sums = []
 
@@ -384,6 +434,10 @@ def main():
             sums.append(c2.host_checksums())
 
         dt_res = timed(resident)
+        if world > 1:      # per-class checksums of the shards -> whole-job checksums (validation, outside the timed region)
+            st = torch.as_tensor(sums[-1], device=dev)
+            dist.all_reduce(st)
+            sums.append(st.cpu().numpy())
         ht = [torch.empty((n, 3), dtype=torch.int32, pin_memory=True) for n in cnt]
         hr = [torch.empty((n, 3), dtype=torch.float64, pin_memory=True) for n in cnt]
 
@@ -392,13 +446,13 @@ def main():
             c2.host_run(args.level, ht, hr)
 
         dt_full = timed(full)
-        d2h = int(sum(cnt) * (24 + 12))
-        e2e = {"value": sum(cnt) / dt_res, "unit": UNIT, "h2d_bytes_per_step": int(mesh.vertices.nbytes + mesh.cells.nbytes),
-               "d2h_bytes_per_step": 96, "ms_per_step": dt_res * 1e3,
+        d2h = int(sum(cnt_full) * (24 + 12))
+        e2e = {"value": sum(cnt_full) / dt_res, "unit": UNIT, "h2d_bytes_per_step": int(mesh.vertices.nbytes + mesh.cells.nbytes) * world,
+               "d2h_bytes_per_step": 96 * world, "ms_per_step": dt_res * 1e3,
                "what": "i2_host_prepare (H2D mesh, geometry, classification, ordered task lists) + i2_host_run (3 classes) with the per-pair "
                        "results left in HBM like Evaluator3D::runAllPairs does, + D2H of the per-class checksums",
                "checksum_sum_abs_J": [float(x) for x in sums[-1][:, 3]],
-               "full_d2h": {"value": sum(cnt) / dt_full, "unit": UNIT, "ms_per_step": dt_full * 1e3, "d2h_bytes_per_step": d2h,
+               "full_d2h": {"value": sum(cnt_full) / dt_full, "unit": UNIT, "ms_per_step": dt_full * 1e3, "d2h_bytes_per_step": d2h,
                             "d2h_gb_per_s": d2h / dt_full / 1e9,
                             "what": "same, plus every per-pair result (24 B) and (i,j,k) key (12 B) copied to pinned host memory, chunks overlapped with compute"}}
         c2.close()
@@ -421,7 +475,7 @@ def main():
                            "triangles": mesh.n_cells, "quadrature": "Cowper 13-point (order 7)", "sharding": f"{world} contiguous equal-cost shards per class, results resident per rank (no data-path collective)",
                            "l2": "inputs+outputs per step (task lists 12 B/pair, results 56 B/pair) are far larger than L2; no flush needed"},
                 "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
-                "with_gather_to_rank0": gather_info, "checksum_sum_abs_J": checksum}
+                "with_gather_to_rank0": gather_info, "with_peer_store_to_rank0": peer_info, "checksum_sum_abs_J": checksum}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -139,6 +139,13 @@ int i2_host_run(i2_context *ctx, int level, int *const h_tasks[3], double *const
 /* per class (sum J_x, sum J_y, sum J_z, sum |J|_1) of the results left in device memory by i2_host_run: the small
  * 'metric' a caller reads back when the per-pair results stay resident (what Evaluator3D::runAllPairs leaves behind) */
 int i2_host_checksums(i2_context *ctx, double h_sums[12]);
+/* multi-GPU use of the host-buffer path (one process and one context per GPU): rank r of w integrates, per class, the
+ * contiguous equal-count shard r of the ordered task list.  Call i2_host_set_shard before i2_host_prepare (default: 0 of
+ * 1 = everything); i2_host_prepare still returns the FULL counts, i2_host_shard the shard's first slot and length per
+ * class; the host buffers given to i2_host_run are then shard-sized and i2_host_checksums covers the shard only.
+ * h_errors needs the whole lists (slot t pairs with slot n/2 + t) and is refused (I2_E_BADARG) when w > 1.             */
+int i2_host_set_shard(i2_context *ctx, int rank, int world);
+int i2_host_shard(i2_context *ctx, long long h_first[3], long long h_count[3]);
 /* device views of what i2_host_prepare built (valid until the next prepare/destroy)                        */
 int i2_host_device_views(i2_context *ctx, const int *d_tasks[3], const double *d_results[3]);
 

@@ -48,7 +48,7 @@ EXPORTS = [
     "i2_create", "i2_destroy", "i2_set_stream", "i2_synchronize", "i2_set_math_mode", "i2_error_string",
     "i2_set_quadrature", "i2_mesh_geometry", "i2_set_mesh", "i2_classify_count", "i2_classify_fill",
     "i2_add_reversed_pairs", "i2_integrate_class", "i2_integrate_all", "i2_symmetry_error", "i2_host_prepare", "i2_host_run",
-    "i2_host_device_views", "i2_host_checksums", "i2_peer_alloc", "i2_peer_open", "i2_peer_close", "i2_peer_free", "i2_peak_rates", "i2_peak_dfma_three_operand", "i2_refine_mesh_once", "i2_launch_count", "i2_set_profiling", "i2_profile_last", "i2_selftest_math", "i2_apply_regular",
+    "i2_host_device_views", "i2_host_checksums", "i2_peer_alloc", "i2_peer_open", "i2_peer_close", "i2_peer_free", "i2_host_set_shard", "i2_host_shard", "i2_peak_rates", "i2_peak_dfma_three_operand", "i2_refine_mesh_once", "i2_launch_count", "i2_set_profiling", "i2_profile_last", "i2_selftest_math", "i2_apply_regular",
 ]
 
 _lib = None
@@ -96,6 +96,8 @@ def load_library():
     L.i2_profile_last.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.i2_peak_dfma_three_operand.argtypes = [vp, C.POINTER(C.c_double)]
     L.i2_peak_rates.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.i2_host_set_shard.argtypes = [vp, i32, i32]
+    L.i2_host_shard.argtypes = [vp, C.POINTER(ll), C.POINTER(ll)]
     L.i2_peer_alloc.argtypes = [vp, C.c_ulonglong, C.POINTER(vp), C.c_char_p]
     L.i2_peer_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     L.i2_peer_close.argtypes = [vp, vp]
@@ -335,6 +337,15 @@ class Context:
         _check(self.L.i2_host_prepare(self.h, v.ctypes.data, v.shape[0], c.ctypes.data, c.shape[0], cnt))
         self.nc = c.shape[0]
         return [int(x) for x in cnt]
+
+    def host_set_shard(self, rank, world):
+        """multi-GPU: this context integrates shard `rank` of `world` of every class (call before host_prepare)"""
+        _check(self.L.i2_host_set_shard(self.h, int(rank), int(world)))
+
+    def host_shard(self):
+        a, b = (C.c_longlong * 3)(), (C.c_longlong * 3)()
+        _check(self.L.i2_host_shard(self.h, a, b))
+        return [int(x) for x in a], [int(x) for x in b]
 
     def host_run(self, level, h_tasks, h_results, h_errors=None, h_refinements=None):
         """h_* : lists of 3 pinned CPU torch tensors (or None entries). Returns list of 3 stats dicts."""

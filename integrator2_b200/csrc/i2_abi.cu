@@ -64,6 +64,9 @@ struct i2_context {
     double *hErrors[3] = {nullptr, nullptr, nullptr};
     unsigned char *hRefinements[3] = {nullptr, nullptr, nullptr};
     long long hCount[3] = {0, 0, 0};
+    // multi-GPU use of the host-entry path: this context integrates slots [hLo, hLo + hN) of every class
+    int shardRank = 0, shardWorld = 1;
+    long long hLo[3] = {0, 0, 0}, hN[3] = {0, 0, 0};
     size_t capVerts = 0, capCells = 0, capNormals = 0, capMeasures = 0, capTasks[3] = {0, 0, 0}, capIntegrals[3] = {0, 0, 0},
            capResults[3] = {0, 0, 0}, capRefinements[3] = {0, 0, 0}, capErrors[3] = {0, 0, 0};
     cudaEvent_t chunkDone[2] = {nullptr, nullptr};
@@ -491,7 +494,29 @@ int i2_host_prepare(i2_context *c, const double *hv, int nv, const int *hc, int 
         rc = i2_add_reversed_pairs(c, c->hTasks[k], pairs[k]);
         if (rc) return rc;
     }
+    for (int k = 0; k < 3; ++k) {   // contiguous equal-count shard of this context (the whole list unless i2_host_set_shard was called)
+        const long long base = c->hCount[k] / c->shardWorld, rem = c->hCount[k] % c->shardWorld;
+        c->hLo[k] = base * c->shardRank + (c->shardRank < rem ? c->shardRank : rem);
+        c->hN[k] = base + (c->shardRank < rem ? 1 : 0);
+    }
     I2_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int i2_host_set_shard(i2_context *c, int rank, int world) {
+    if (!c || world < 1 || rank < 0 || rank >= world) return I2_E_BADARG;
+    c->shardRank = rank;
+    c->shardWorld = world;
+    return 0;
+}
+
+int i2_host_shard(i2_context *c, long long first[3], long long count[3]) {
+    if (!c || !first || !count) return I2_E_BADARG;
+    if (!c->hVerts) return I2_E_NOMESH;
+    for (int k = 0; k < 3; ++k) {
+        first[k] = c->hLo[k];
+        count[k] = c->hN[k];
+    }
     return 0;
 }
 
@@ -502,7 +527,7 @@ int i2_host_checksums(i2_context *c, double sums[12]) {
     double *d = nullptr;
     I2_CUDA(cudaMalloc((void **)&d, sizeof(double) * 12));
     I2_CUDA(cudaMemsetAsync(d, 0, sizeof(double) * 12, c->stream));
-    for (int k = 0; k < 3; ++k) launch_checksum(c->hResults[k], c->hCount[k], d + 4 * k, c->numSMs, c->stream);
+    for (int k = 0; k < 3; ++k) launch_checksum(c->hResults[k] + 3 * c->hLo[k], c->hN[k], d + 4 * k, c->numSMs, c->stream);
     I2_CUDA(cudaMemcpyAsync(sums, d, sizeof(double) * 12, cudaMemcpyDeviceToHost, c->stream));
     I2_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(d);
@@ -529,12 +554,17 @@ int i2_host_run(i2_context *c, int level, int *const hTasks[3], double *const hR
     if (hStats) std::memset(hStats, 0, 3 * sizeof(i2_stats));
 
     // one whole class on stream st: integration, optional (i,j)/(j,i) defect, device-to-host copies; no synchronisation
+    // device views of this context's shard of class k
+    auto dTasks = [&](int k) { return c->hTasks[k] + 3 * c->hLo[k]; };
+    auto dIntegrals = [&](int k) { return c->hIntegrals[k] + 4 * c->hLo[k]; };
+    auto dResults = [&](int k) { return c->hResults[k] + 3 * c->hLo[k]; };
     auto whole = [&](int k, cudaStream_t st) -> int {
-        const long long n = c->hCount[k];
-        int rc = enqueue_class(c, k, c->hTasks[k], n, level, c->hIntegrals[k], c->hResults[k], level < 0 ? c->hRefinements[k] : nullptr,
+        const long long n = c->hN[k];
+        int rc = enqueue_class(c, k, dTasks(k), n, level, dIntegrals(k), dResults(k), level < 0 ? c->hRefinements[k] : nullptr,
                                nullptr, st, false);
         if (rc) return rc;
         if (hErrors && hErrors[k]) {
+            if (c->shardWorld > 1) return I2_E_BADARG;   // the (i,j)/(j,i) defect pairs slot t with slot n/2 + t: whole lists only
             rc = ensure(&c->hErrors[k], &c->capErrors[k], (size_t)n);
             if (rc) return rc;
             launch_symmetry_error(c->hResults[k], n / 2, c->hErrors[k], st);
@@ -542,9 +572,9 @@ int i2_host_run(i2_context *c, int level, int *const hTasks[3], double *const hR
             I2_CUDA(cudaMemcpyAsync(hErrors[k], c->hErrors[k], sizeof(double) * n, cudaMemcpyDeviceToHost, st));
         }
         if (hResults && hResults[k])
-            I2_CUDA(cudaMemcpyAsync(hResults[k], c->hResults[k], sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, st));
+            I2_CUDA(cudaMemcpyAsync(hResults[k], dResults(k), sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, st));
         if (hTasks && hTasks[k])
-            I2_CUDA(cudaMemcpyAsync(hTasks[k], c->hTasks[k], sizeof(int) * 3 * n, cudaMemcpyDeviceToHost, st));
+            I2_CUDA(cudaMemcpyAsync(hTasks[k], dTasks(k), sizeof(int) * 3 * n, cudaMemcpyDeviceToHost, st));
         if (level < 0 && hRefinements && hRefinements[k])
             I2_CUDA(cudaMemcpyAsync(hRefinements[k], c->hRefinements[k], c->nc, cudaMemcpyDeviceToHost, st));
         return 0;
@@ -556,7 +586,7 @@ int i2_host_run(i2_context *c, int level, int *const hTasks[3], double *const hR
         cudaStream_t st = c->side[k];
         I2_CUDA(cudaStreamWaitEvent(st, c->forkEv, 0));
         if (level < 0) I2_CUDA(cudaMemsetAsync(c->hRefinements[k], 0, c->nc, st));
-        if (c->hCount[k] > 0) {
+        if (c->hN[k] > 0) {
             const int rc = whole(k, st);
             if (rc) return rc;
         }
@@ -564,7 +594,7 @@ int i2_host_run(i2_context *c, int level, int *const hTasks[3], double *const hR
     }
     {
         const int k = 2;
-        const long long n = c->hCount[k];
+        const long long n = c->hN[k];
         if (level < 0) I2_CUDA(cudaMemsetAsync(c->hRefinements[k], 0, c->nc, s));
         const bool wantErr = hErrors && hErrors[k];
         if (n > 0 && level >= 0 && !wantErr) {
@@ -574,7 +604,7 @@ int i2_host_run(i2_context *c, int level, int *const hTasks[3], double *const hR
             int turn = 0;
             for (long long off = 0; off < n; off += copyOut ? chunkTasks : n) {
                 const long long m = !copyOut ? n : ((n - off < chunkTasks) ? (n - off) : chunkTasks);
-                int rc = enqueue_class(c, k, c->hTasks[k] + 3 * off, m, level, c->hIntegrals[k] + 4 * off, c->hResults[k] + 3 * off,
+                int rc = enqueue_class(c, k, dTasks(k) + 3 * off, m, level, dIntegrals(k) + 4 * off, dResults(k) + 3 * off,
                                        nullptr, nullptr, s, false);
                 if (rc) return rc;
                 if (!copyOut) break;
@@ -582,9 +612,9 @@ int i2_host_run(i2_context *c, int level, int *const hTasks[3], double *const hR
                 I2_CUDA(cudaStreamWaitEvent(cs, c->chunkDone[turn], 0));
                 turn ^= 1;
                 if (hResults && hResults[k])
-                    I2_CUDA(cudaMemcpyAsync(hResults[k] + 3 * off, c->hResults[k] + 3 * off, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost, cs));
+                    I2_CUDA(cudaMemcpyAsync(hResults[k] + 3 * off, dResults(k) + 3 * off, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost, cs));
                 if (hTasks && hTasks[k])
-                    I2_CUDA(cudaMemcpyAsync(hTasks[k] + 3 * off, c->hTasks[k] + 3 * off, sizeof(int) * 3 * m, cudaMemcpyDeviceToHost, cs));
+                    I2_CUDA(cudaMemcpyAsync(hTasks[k] + 3 * off, dTasks(k) + 3 * off, sizeof(int) * 3 * m, cudaMemcpyDeviceToHost, cs));
             }
         } else if (n > 0) {
             const int rc = whole(k, s);
@@ -595,12 +625,12 @@ int i2_host_run(i2_context *c, int level, int *const hTasks[3], double *const hR
     QueueState h[3];
     if (hStats)
         for (int k = 0; k < 3; ++k)
-            if (c->hCount[k] > 0) I2_CUDA(cudaMemcpyAsync(&h[k], c->scr[k].qs, sizeof(QueueState), cudaMemcpyDeviceToHost, s));
+            if (c->hN[k] > 0) I2_CUDA(cudaMemcpyAsync(&h[k], c->scr[k].qs, sizeof(QueueState), cudaMemcpyDeviceToHost, s));
     I2_CUDA(cudaStreamSynchronize(s));
     I2_CUDA(cudaStreamSynchronize(cs));
     if (hStats)
         for (int k = 0; k < 3; ++k)
-            if (c->hCount[k] > 0) fill_stats(h[k], c->hCount[k], level, &hStats[k]);
+            if (c->hN[k] > 0) fill_stats(h[k], c->hN[k], level, &hStats[k]);
     return 0;
 }
 

@@ -40,8 +40,10 @@ def test_peer_alloc_is_a_valid_results_target(ctx):
 
 WORKER = """
     import os, sys
-    sys.path.insert(0, {root!r})
+    sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+    import numpy as np
     import torch, torch.distributed as dist
+    from helpers import reference_noise_bound, REL_TOL, K_NOISE
     from integrator2_b200 import abi
     from integrator2_b200.meshio import load_fixture
     from integrator2_b200.multigpu import PeerExport, shard_bounds, integrate_and_gather, wait_all
@@ -74,14 +76,19 @@ WORKER = """
                 assert not torch.isnan(a).any(), (level, k, "rows missing")
                 lo, hi = bounds[k][0]
                 assert torch.equal(a[lo:hi], b[lo:hi]) or level < 0, (level, k, "own shard differs")
-                relv = (a - b).abs().sum(1) / b.abs().sum(1).clamp_min(1e-300)
-                rel = float(relv.max())
-                # same kernels on both GPUs; warp-mates differ at the shard seam (tier selection is warp-wide): a few ulp.
-                # Under error control an ulp can flip a Runge decision that sits exactly on the threshold (a tie).
-                if level >= 0:
-                    assert rel < 1e-12, (level, k, rel)
+                # same kernels on both GPUs, but the warp-mates of a pair differ once a shard does not start at slot 0 and the
+                # far-field tier of the group logs is chosen per warp: the two runs carry different samples of the rounding
+                # noise, which ill-conditioned pairs amplify -> the tolerance statement of tests/helpers.py (DESIGN.md section 4).
+                # Under error control an ulp can also flip a Runge decision that sits exactly on the threshold (a tie).
+                err = (a - b).abs().sum(1).cpu().numpy()
+                ref = b.abs().sum(1).cpu().numpy()
+                rel = float((err / np.maximum(ref, 1e-300)).max())
+                if k == 2:
+                    allowed = REL_TOL * ref + K_NOISE * reference_noise_bound(m.vertices, m.cells, tasks_full[k].cpu().numpy())
                 else:
-                    assert float((relv > 1e-12).double().mean()) < 1e-4, (level, k, rel)
+                    allowed = 1e-11 * ref        # adjacent classes: reference operation order, no warp-wide decisions
+                outside = float((err > allowed).mean())
+                assert outside <= (0.0 if level == 0 else 1e-4), (level, k, rel, outside)   # the noise model is the level-0 one
                 print(f"PEER level {{level}} class {{k}}: n={{counts[k]}} max rel diff vs single-GPU {{rel:.2e}}", flush=True)
         torch.cuda.synchronize(); dist.barrier()
         for e in exports:
