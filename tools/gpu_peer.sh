@@ -8,5 +8,5 @@ nvidia-smi -L > gpurun_out/gpus.txt
 echo "== pytest peer export"
 timeout 900 python -m pytest tests/test_gpu_peer_export.py tests/test_gpu_parity.py -m gpu -q -x -s -k "peer or host_buffer" --timeout 800 > gpurun_out/pytest_peer.log 2>&1; tail -25 gpurun_out/pytest_peer.log
 echo "== bench N=$N"
-true
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_n$N.log 2>&1
 tail -3 gpurun_out/bench_n$N.log | cut -c1-6000
