@@ -377,20 +377,21 @@ def main():
             ms_k = sum(t_int) / len(t_int)
             flops = FLOP_PER_REGULAR_PAIR * my_counts[2] * (4 ** max(args.level, 0))
             achieved = flops / (ms_k * 1e-3) / 1e12
-            # dram__bytes_read+write of this kernel from the ncu --set full capture in profiles/r01_ncu_k_regular_grouped_v5_final.txt:
-            # 19.453 GB for 286 403 650 pairs = 67.92 B/pair (algorithmic: 12 B task + 32 B integrals + 24 B result = 68 B)
-            traffic = 67.92 * my_counts[2] if args.level == 0 else None
+            # dram__bytes_read+write of this kernel from the ncu --set full capture in profiles/r01_ncu_k_regular_grouped_v7_final.txt:
+            # 19.447 GB for 286 403 650 pairs = 67.90 B/pair (algorithmic: 12 B task + 32 B integrals + 24 B result = 68 B)
+            traffic = 67.90 * my_counts[2] if args.level == 0 else None
             roof = {"bound": "fp64", "achieved": achieved, "peak": dfma_tf, "unit": "TFLOP/s", "frac": achieved / dfma_tf,
                     "traffic": traffic, "kernel": "k_regular_grouped (not-neighbours, level 0, fused assembly)", "kernel_ms": ms_k,
                     "algorithmic_flop_per_pair": FLOP_PER_REGULAR_PAIR, "pairs_per_launch": my_counts[2],
                     "peak_source": "measured on this device by i2_peak_rates (DFMA chains); MEASURED_PEAKS.json has no FP64 figure",
                     "mufu_peak_gops": mufu_g,
                     "peak_three_register_operands": dfma3_tf,
-                    "note": "achieved uses the per-point work model of SURVEY.md 8(d) (6.1 kflop/pair); the grouped kernel executes ~1530 FP64 "
-                            "instructions (~2.45 kflop) per pair, i.e. frac > 1 means work removed, not a faster pipe; peak_three_register_operands is the DFMA rate when every "
-                            "instruction reads three distinct registers (the practical ceiling of real code, ~75 % of peak); FP64-pipe active 62 % (83 % of the three-operand ceiling) in "
-                            "profiles/r01_ncu_k_regular_grouped_v5_final.txt",
-                    "executed_fp64_inst_per_pair": 1530}
+                    "note": "achieved uses the per-point work model of SURVEY.md 8(d) (6.1 kflop/pair); the grouped kernel executes ~1130 FP64 "
+                            "instructions (~1.8 kflop) per pair, i.e. frac > 1 means work removed, not a faster pipe; peak_three_register_operands is the DFMA rate when every "
+                            "instruction reads three distinct registers (the practical ceiling of real code, ~75 % of peak); FP64-pipe active 63 % (84 % of the three-operand ceiling) in "
+                            "profiles/r01_ncu_k_regular_grouped_v7_final.txt",
+                    "executed_fp64_inst_per_pair": 1130,
+                    "fp64_pipe_active_frac": 0.629}
 
     # ---- end to end through the host-buffer C ABI (N=1): host mesh in -> prepare (H2D, geometry, classification, task
     # lists) -> three classes -> results.  Two variants, both timed with the host clock around the blocking calls:
