@@ -9,6 +9,9 @@ import torch
 from integrator2_b200 import abi
 from integrator2_b200.meshio import load_fixture
 
+if os.environ.get("I2_LIB_PATH"):       # an experimental build of the library (tools/gpu_unroll.sh)
+    abi.LIB_PATH = os.path.abspath(os.environ["I2_LIB_PATH"])
+
 ctx = abi.Context(0)
 m = load_fixture("Vint16k")
 ctx.set_mesh(m.vertices, m.cells)
@@ -17,7 +20,7 @@ tasks = ctx.tasks_from_pairs(lists[2])
 n = int(tasks.shape[0])
 buf = (torch.empty((n, 4), dtype=torch.float64, device="cuda"), torch.empty((n, 3), dtype=torch.float64, device="cuda"))
 ctx.set_profiling(True)
-out = {"minblocks": os.environ.get("I2_MINBLOCKS", "4"), "variant": os.environ.get("I2_VARIANT", "0")}
+out = {"lib": os.path.basename(abi.LIB_PATH), "minblocks": os.environ.get("I2_MINBLOCKS", "4"), "variant": os.environ.get("I2_VARIANT", "0")}
 ts = []
 for rep in range(5):
     ctx.integrate_class(2, tasks, 0, want_stats=False, out=buf)
