@@ -348,7 +348,8 @@ static __device__ __forceinline__ int raise_flag(int flagged, const PointTerms &
 // argument below the reference's epsilon, a large solid angle, a Gauss point next to a vertex of T in the projection form)
 // only raises a sticky flag, and ONE __all_sync per group of equal weights decides whether the warp redoes the group point
 // by point in the careful form.
-template <bool EDGELEN, bool RESID, bool DERIVE = false, bool PROJ = false>
+// MS = distance (in doubles) between consecutive components of the staged points (kThreads when every thread has its own set)
+template <bool EDGELEN, bool RESID, bool DERIVE = false, bool PROJ = false, int MS = kThreads>
 static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, const TriJ &T, double &a1, double &a2, double &a3, double &a4) {
     a1 = 0.0; a2 = 0.0; a3 = 0.0; a4 = 0.0;
     const int ngroups = c_ngroups;
@@ -356,11 +357,11 @@ static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, c
 #pragma unroll 1
     for (int grp = 0; grp < ngroups; ++grp) {
         const int gStart = g, gEnd = c_groupStart[grp + 1];
-        const double *pM = myM + 3 * kThreads * gStart, *const pEnd = myM + 3 * kThreads * gEnd;
+        const double *pM = myM + 3 * MS * gStart, *const pEnd = myM + 3 * MS * gEnd;
         double sq[3];
         auto point = [&]() -> PointTerms {
-            const d3 M = {pM[0], pM[kThreads], pM[2 * kThreads]};
-            pM += 3 * kThreads;
+            const d3 M = {pM[0], pM[MS], pM[2 * MS]};
+            pM += 3 * MS;
             return PROJ ? point_terms_proj(M, T, sq) : point_terms_raw<EDGELEN, DERIVE>(M, T);
         };
         // first point of the group: the running products start from its terms (no multiplication by one)
@@ -390,7 +391,7 @@ static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, c
             pn1 = pd1 = pn2 = pd2 = pn3 = pd3 = 1.0;
             th = 0.0;
             for (int h = gStart; h < gEnd; ++h) {
-                const d3 Mh = {myM[(3 * h + 0) * kThreads], myM[(3 * h + 1) * kThreads], myM[(3 * h + 2) * kThreads]};
+                const d3 Mh = {myM[(3 * h + 0) * MS], myM[(3 * h + 1) * MS], myM[(3 * h + 2) * MS]};
                 PointTerms u = point_terms_raw<EDGELEN, DERIVE>(Mh, T);
                 eps_fixup(u);
                 pn1 *= u.N1; pd1 *= u.D1; pn2 *= u.N2; pd2 *= u.D2; pn3 *= u.N3; pd3 *= u.D3;
