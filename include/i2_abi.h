@@ -122,6 +122,19 @@ int i2_integrate_all(i2_context *ctx, const int *const d_tasks[3], const long lo
  * limits (N > 46 340 triangles) and the unit that shards by rows across GPUs.                                    */
 int i2_apply_regular(i2_context *ctx, int row_lo, int row_hi, const double *d_weights, double *d_out);
 
+/* The same row sums under AUTOMATIC ERROR CONTROL: every pair (i, j) runs the Runge loop of
+ * EvaluatorJ3DK::numericalIntegration (src/evaluators/evaluatorJ3DK.cu:895-1012) — round 0 on the control panel, round 1 on
+ * its 4 children, criterion of src/evaluators/evaluator3d.cu:76-99, further rounds (16 ... 1024 children, at most 5) only
+ * for the pairs that fail it — inside one kernel, without task lists, refined meshes or a work queue in memory.  The value
+ * of a pair follows the reference's ping-pong buffers: the newest value of the buffer selected by the parity
+ * of the class's last round L.  d_out = sums for this call's own L (h_stats->last_round); d_out_other (may be NULL) = sums
+ * for the other parity, which a multi-GPU caller takes when the maximum of L over all ranks has the other parity.
+ * d_refinements (may be NULL) = unsigned char[row_hi - row_lo], the per-cell value NumericalIntegrator3D::
+ * getRefinementsRequired(not_neighbors) would hold: 1 + the number of compare rounds some pair of the row failed.
+ * h_stats (may be NULL; synchronises): integrated[0] = pairs examined, unconverged[m] = pairs failing round m.        */
+int i2_apply_regular_adaptive(i2_context *ctx, int row_lo, int row_hi, const double *d_weights, double *d_out,
+                              double *d_out_other, unsigned char *d_refinements, i2_stats *h_stats);
+
 /* delta = |J_ij + J_ji|_1 / max(|J_ij|_1, |J_ji|_1) for slots t and n_half+t: replaces
  * kCalculateIntegrationError (src/evaluators/evaluator3d.cu:45-57)                                         */
 int i2_symmetry_error(i2_context *ctx, const double *d_results, long long n_half, double *d_errors);

@@ -48,7 +48,7 @@ EXPORTS = [
     "i2_create", "i2_destroy", "i2_set_stream", "i2_synchronize", "i2_set_math_mode", "i2_error_string",
     "i2_set_quadrature", "i2_mesh_geometry", "i2_set_mesh", "i2_classify_count", "i2_classify_fill",
     "i2_add_reversed_pairs", "i2_integrate_class", "i2_integrate_all", "i2_symmetry_error", "i2_host_prepare", "i2_host_run",
-    "i2_host_device_views", "i2_host_checksums", "i2_peer_alloc", "i2_peer_open", "i2_peer_close", "i2_peer_free", "i2_host_set_shard", "i2_host_shard", "i2_peak_rates", "i2_peak_dfma_three_operand", "i2_refine_mesh_once", "i2_launch_count", "i2_set_profiling", "i2_profile_last", "i2_selftest_math", "i2_apply_regular",
+    "i2_host_device_views", "i2_host_checksums", "i2_peer_alloc", "i2_peer_open", "i2_peer_close", "i2_peer_free", "i2_host_set_shard", "i2_host_shard", "i2_peak_rates", "i2_peak_dfma_three_operand", "i2_refine_mesh_once", "i2_launch_count", "i2_set_profiling", "i2_profile_last", "i2_selftest_math", "i2_apply_regular", "i2_apply_regular_adaptive",
 ]
 
 _lib = None
@@ -90,6 +90,7 @@ def load_library():
     L.i2_host_device_views.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
     L.i2_refine_mesh_once.argtypes = [vp, vp, i32, vp, i32, vp, vp, vp, vp]
     L.i2_apply_regular.argtypes = [vp, i32, i32, vp, vp]
+    L.i2_apply_regular_adaptive.argtypes = [vp, i32, i32, vp, vp, vp, vp, C.POINTER(Stats)]
     L.i2_selftest_math.argtypes = [vp, i32, vp, vp, ll, vp]
     L.i2_launch_count.argtypes = [C.POINTER(ll)]
     L.i2_set_profiling.argtypes = [vp, i32]
@@ -272,6 +273,20 @@ class Context:
             out = torch.empty((row_hi - row_lo, 3), dtype=torch.float64, device=f"cuda:{self.device}")
         _check(self.L.i2_apply_regular(self.h, int(row_lo), int(row_hi), _ptr(weights), _ptr(out)))
         return out
+
+    def apply_regular_adaptive(self, row_lo, row_hi, weights=None, want_stats=True):
+        """Row sums of the regular class under automatic error control, list-free (see i2_apply_regular_adaptive).
+        -> dict(out, other, refinements, stats)"""
+        torch = self.torch
+        dev = f"cuda:{self.device}"
+        n = row_hi - row_lo
+        out = torch.empty((n, 3), dtype=torch.float64, device=dev)
+        other = torch.empty((n, 3), dtype=torch.float64, device=dev)
+        ref = torch.zeros((n,), dtype=torch.uint8, device=dev)
+        st = Stats()
+        _check(self.L.i2_apply_regular_adaptive(self.h, int(row_lo), int(row_hi), _ptr(weights), _ptr(out), _ptr(other), _ptr(ref),
+                                                C.byref(st) if want_stats else None))
+        return dict(out=out, other=other, refinements=ref, stats=st.as_dict() if want_stats else None)
 
     def symmetry_error(self, results):
         torch = self.torch

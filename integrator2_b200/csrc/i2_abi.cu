@@ -50,6 +50,8 @@ struct i2_context {
     // matrix-free path scratch (per-chunk partial row sums)
     double *partial = nullptr;
     size_t partialCap = 0;
+    unsigned char *depthBuf = nullptr;   // list-free adaptive path: per (column chunk, row) refinement depth
+    size_t depthCap = 0;
 
     // classification scratch
     unsigned long long *rowCounts = nullptr;
@@ -174,6 +176,7 @@ int i2_destroy(i2_context *c) {
     for (int k = 0; k < 3; ++k) if (c->prof[k]) cudaEventDestroy(c->prof[k]);
     if (c->rowCounts) cudaFree(c->rowCounts);
     if (c->partial) cudaFree(c->partial);
+    if (c->depthBuf) cudaFree(c->depthBuf);
     if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
     if (c->copyStream) cudaStreamDestroy(c->copyStream);
     delete c;
@@ -445,6 +448,51 @@ int i2_apply_regular(i2_context *c, int rowLo, int rowHi, const double *weights,
     if (rc) return rc;
     launch_apply_regular(packed(c), rowLo, rowHi, 0, c->nc, chunks, weights, c->partial, out, c->stream);
     I2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int i2_apply_regular_adaptive(i2_context *c, int rowLo, int rowHi, const double *weights, double *out, double *outOther,
+                              unsigned char *refinements, i2_stats *stats) {
+    if (!c || rowLo < 0 || rowHi < rowLo) return I2_E_BADARG;
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    if (!c->tri) return I2_E_NOMESH;
+    if (!c->haveQuad) return I2_E_NOQUAD;
+    if (rowHi > c->nc) return I2_E_BADARG;
+    if (rowHi == rowLo) return 0;
+    if (!out) return I2_E_BADARG;
+    I2_CUDA(cudaSetDevice(c->device));
+    const int rows = rowHi - rowLo;
+    // 4 lanes per row -> 32 rows per CTA; enough CTAs for a few waves of 3 CTAs/SM: split the columns when there are few row blocks
+    const int rowBlocks = (rows + kThreads / 4 - 1) / (kThreads / 4);
+    int chunks = (c->numSMs * 3 * 2 + rowBlocks - 1) / rowBlocks;
+    if (chunks < 1) chunks = 1;
+    const int maxChunks = (c->nc + 255) / 256;
+    if (chunks > maxChunks) chunks = maxChunks;
+    // scratch: 8 doubles of header (6 x 64-bit round counters, the class's last round) + per-chunk partial sums
+    int rc = ensure(&c->partial, &c->partialCap, (size_t)8 + (size_t)chunks * rows * 6);
+    if (!rc) rc = ensure(&c->depthBuf, &c->depthCap, (size_t)chunks * rows);
+    if (rc) return rc;
+    unsigned long long *counts = reinterpret_cast<unsigned long long *>(c->partial);
+    int *lastRound = reinterpret_cast<int *>(c->partial + 6);
+    I2_CUDA(cudaMemsetAsync(c->partial, 0, 8 * sizeof(double), c->stream));
+    launch_apply_regular_adaptive(packed(c), rowLo, rowHi, 0, c->nc, chunks, weights, c->partial + 8, c->depthBuf, lastRound, counts, out,
+                                  outOther, refinements, c->stream);
+    I2_CUDA(cudaGetLastError());
+    if (stats) {
+        unsigned long long h[8];
+        I2_CUDA(cudaMemcpyAsync(h, c->partial, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        I2_CUDA(cudaStreamSynchronize(c->stream));
+        int L;
+        std::memcpy(&L, &h[6], sizeof(int));
+        stats->last_round = L;
+        stats->integrated[0] = (long long)h[0];
+        long long before = (long long)h[0];
+        for (int m = 1; m <= L && m <= MAX_REFINE_LEVEL; ++m) {
+            stats->integrated[m] = before << (2 * m);
+            stats->unconverged[m] = (long long)h[m];
+            before = (long long)h[m];
+        }
+    }
     return 0;
 }
 

@@ -652,6 +652,273 @@ void launch_apply_regular(const PackedMesh &pm, int rowLo, int rowHi, int colLo,
     k_reduce_partials<<<(rows * 3 + 255) / 256, 256, 0, s>>>(partial, rows, chunks, out3);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// list-free regular class WITH automatic error control: the Runge loop of NumericalIntegrator3D / EvaluatorJ3DK
+// (src/evaluators/evaluatorJ3DK.cu:895-1012, src/evaluators/evaluator3d.cu:76-99) per pair, without a task list, a
+// refined mesh or a work queue in memory — for meshes beyond the reference's N^2-list limits.
+//   4 lanes = one control panel i; lane l holds the Gauss points of child l of i (level 1) in shared memory, the
+//   parent's points sit once per row.  Columns stream through shared memory in tiles; per step of 4 columns every lane
+//   evaluates its child against the 4 triangles (-> I_1 by a 4-lane shuffle sum, round 1) and the parent against ONE of
+//   them (-> I_0, round 0): 5 evaluations per lane per 4 pairs, perfectly balanced.  Lane q then owns pair (i, j_q):
+//   Runge criterion; a pair that fails it (rare: < 1 % of the regular pairs of the example meshes) is refined further by
+//   the WHOLE warp, 32 lanes over the 16 / 64 / 256 / 1024 children of rounds 2..5, until it converges.
+//   Everything is summed in a fixed order: results are bitwise reproducible.
+// The reference keeps converged values in two ping-pong buffers without copying: the final value of a
+// pair is the newest value of the buffer selected by the parity of the class's LAST round L.  Both candidates are
+// accumulated (accE: newest even-round value, accO: newest odd-round value); k_reduce_partials_adaptive picks by L.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kAdRows = kThreads / 4;
+constexpr int kAdTileJ = 16;
+
+struct ApplyAdaptiveOut {
+    double *partial;             // [chunks][rows][6]: accE.xyz, accO.xyz
+    unsigned char *depth;        // [chunks][rows]: max over the chunk's pairs of the number of compare rounds failed (0..5)
+    int *lastRound;              // L of the class (atomicMax)
+    unsigned long long *counts;  // [6]: counts[0] = pairs examined, counts[m] = pairs unconverged after round m
+};
+
+static __device__ __forceinline__ d4 shfl4(d4 v, int src) {
+    return {__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src), __shfl_sync(0xffffffffu, v.z, src),
+            __shfl_sync(0xffffffffu, v.w, src)};
+}
+
+// influence triangle from one row of a shared-memory column tile (B and C are derived from A, the tangents and the edge lengths)
+static __device__ __forceinline__ void load_tile_T(const double *t, TriJ &T) {
+    T.A = {t[0], t[1], t[2]};
+    T.ta = {t[9], t[10], t[11]}; T.tb = {t[12], t[13], t[14]}; T.tc = {t[15], t[16], t[17]};
+    T.Nu = {t[18], t[19], t[20]};
+    T.La = t[21]; T.Lb = t[22]; T.Lc = t[23];
+    T.c2 = T.Lc * T.Lb * dot(T.tc, T.tb);
+    T.s1 = hi_word(T.Lc) - kNearEdgeShift; T.s2 = hi_word(T.La) - kNearEdgeShift; T.s3 = hi_word(T.Lb) - kNearEdgeShift;
+}
+// Gauss points of child `c` (level `lev`) of control panel `ii` into the calling thread's slot myC ([point][component], stride kThreads)
+static __device__ __forceinline__ void stage_child_points(const double *__restrict__ tri, int stride, int ng, int ii, int lev, int c, double *myC) {
+    d3 A = ld3(tri + PK_A * stride, stride, ii), B = ld3(tri + PK_B * stride, stride, ii), C = ld3(tri + PK_C * stride, stride, ii);
+    descend(A, B, C, lev, c);
+#pragma unroll 1
+    for (int g = 0; g < ng; ++g) {
+        const d3 M = gauss_point(g, A, B, C);
+        myC[(3 * g + 0) * kThreads] = M.x; myC[(3 * g + 1) * kThreads] = M.y; myC[(3 * g + 2) * kThreads] = M.z;
+    }
+}
+// Rounds 2..5 of ONE pair (control panel srcI of area srcS against the tile row tT), all 32 lanes of the warp over the
+// 16 / 64 / 256 / 1024 children.  I1 / I0 = the pair's round-1 / round-0 values.  Rare path, kept out of line so that its
+// registers do not weigh on the main loop.  res: newest even-round value, newest odd-round value; last = last round
+// executed, failed = number of compare rounds the pair failed.
+struct DeepResult { d4 evenV, oddV; int last, failed; };
+static __device__ __noinline__ void deep_rounds(const double *__restrict__ tri, int stride, int ng, double *myC, const double *tT, int srcI,
+                                                double srcS, d4 I1, d4 I0, double pow2p, unsigned int *smCount, DeepResult *res) {
+    const int lane = threadIdx.x & 31;
+    TriJ Ts;
+    load_tile_T(tT, Ts);
+    d4 prev = I1, evenV = I0, oddV = I1;
+    int m = 2;
+    bool un = true;
+    double Sm = 0.0625 * srcS;
+#pragma unroll 1
+    for (; m <= MAX_REFINE_LEVEL && un; ++m, Sm *= 0.25) {
+        const int children = 1 << (2 * m);
+        const int perLane = children > 32 ? children / 32 : 1;
+        d4 part = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+        for (int k = 0; k < perLane; ++k) {
+            const int c = lane + 32 * k;
+            stage_child_points(tri, stride, ng, srcI, m, c & (children - 1), myC);   // lanes beyond the 16 children of round 2 duplicate one
+            const double S = c < children ? Sm : 0.0;                                 // ... with weight 0 (the votes stay full-mask)
+            double a1, a2, a3, a4;
+            grouped_eval<true, false, true, true>(myC, ng, Ts, a1, a2, a3, a4);
+            const d4 e = vec4((S * a1) * Ts.tc + (S * a2) * Ts.ta + (S * a3) * Ts.tb, S * a4);
+            part.x += e.x; part.y += e.y; part.z += e.z; part.w += e.w;
+        }
+        const d4 cur = warp_sum(part, 32);
+        un = runge_unconverged(cur, prev, pow2p);
+        if (m & 1) oddV = cur; else evenV = cur;
+        prev = cur;
+        if (un && lane == 0) atomicAdd(&smCount[m], 1u);
+    }
+    res->evenV = evenV; res->oddV = oddV; res->last = m - 1; res->failed = un ? MAX_REFINE_LEVEL : m - 2;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
+k_apply_regular_adaptive(PackedMesh pm, int rowLo, int rowHi, int colLo, int colHi, int colChunk, const double *__restrict__ weights,
+                         ApplyAdaptiveOut o) {
+    extern __shared__ double smDyn[];                                   // 53.6 KB: above the 48 KB static limit
+    double *smC = smDyn;                                                  // per thread: Gauss points of its child (or of a deep child)
+    double *smP = smC + MAX_GAUSS_POINTS * 3 * kThreads;                  // per row: Gauss points of the control panel itself
+    double *smT = smP + MAX_GAUSS_POINTS * 3 * kAdRows;                   // column tile
+    __shared__ int smId[kAdTileJ * 3];
+    __shared__ unsigned int smCount[6];
+    const int rows = rowHi - rowLo;
+    const int lane = threadIdx.x & 31, sub = threadIdx.x & 3, rowInCta = threadIdx.x >> 2;
+    const int r = blockIdx.x * kAdRows + rowInCta;
+    const bool active = r < rows;
+    const int i = rowLo + (active ? r : rows - 1);
+    const int ng = c_ngauss;
+    const int stride = pm.stride;
+    const double pow2p = c_pow2p;
+    const double *__restrict__ tri = pm.tri;
+    double *myC = smC + threadIdx.x;
+    const double *myP = smP + rowInCta;
+    const tri3 ci = ldtri(pm.cells, i);
+    const double Si = __ldg(tri + PK_S * stride + i);
+    if (threadIdx.x < 6) smCount[threadIdx.x] = 0;
+
+    auto stage_child = [&](int ii, int lev, int c) { stage_child_points(tri, stride, ng, ii, lev, c, myC); };
+    auto load_T = [&](int jj, TriJ &T) { load_tile_T(smT + jj * kTileStride, T); };
+    // (Psi, Theta) of one staged panel of area S against T
+    auto eval_child = [&](const TriJ &T, double S) -> d4 {
+        double a1, a2, a3, a4;
+        grouped_eval<true, false, true, true>(myC, ng, T, a1, a2, a3, a4);
+        return vec4((S * a1) * T.tc + (S * a2) * T.ta + (S * a3) * T.tb, S * a4);
+    };
+
+    {   // the four lanes of a row share the work of staging the parent's points; each stages its own child
+        const d3 A = ld3(tri + PK_A * stride, stride, i), B = ld3(tri + PK_B * stride, stride, i), C = ld3(tri + PK_C * stride, stride, i);
+        for (int g = sub; g < ng; g += 4) {
+            const d3 M = gauss_point(g, A, B, C);
+            smP[(3 * g + 0) * kAdRows + rowInCta] = M.x; smP[(3 * g + 1) * kAdRows + rowInCta] = M.y; smP[(3 * g + 2) * kAdRows + rowInCta] = M.z;
+        }
+        stage_child(i, 1, sub);
+    }
+
+    d3 accE = {0.0, 0.0, 0.0}, accO = {0.0, 0.0, 0.0};
+    int depth = 0, lastRound = 0;
+    unsigned int examined = 0;
+    const int j0 = colLo + blockIdx.y * colChunk;
+    const int j1 = min(j0 + colChunk, colHi);
+    for (int tile = j0; tile < j1; tile += kAdTileJ) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < kAdTileJ * 28; e += kThreads) {
+            const int comp = e / kAdTileJ, jj = e % kAdTileJ, j = tile + jj;
+            double v = 0.0;
+            if (j < j1) {
+                if (comp < 21) v = __ldg(tri + comp * stride + j);
+                else if (comp < 24) v = __ldg(tri + (PK_L + comp - 21) * stride + j);
+                else if (comp < 27) v = __ldg(tri + (PK_N + comp - 24) * stride + j);
+                else v = weights ? __ldg(weights + j) : 1.0;
+            }
+            smT[jj * kTileStride + comp] = v;
+        }
+        for (int e = threadIdx.x; e < kAdTileJ * 3; e += kThreads) {
+            const int jj = e / 3, j = tile + jj;
+            smId[e] = j < j1 ? __ldg(pm.cells + 3 * (long long)j + e % 3) : -1;
+        }
+        __syncthreads();
+        const int nj = min(kAdTileJ, j1 - tile);
+#pragma unroll 1
+        for (int jj0 = 0; jj0 < nj; jj0 += 4) {
+            // round 1: every lane's child against the 4 triangles of the step; lane q keeps the 4-lane sum for column q
+            d4 I1 = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {
+                TriJ T;
+                load_T(min(jj0 + q, nj - 1), T);   // a clamped duplicate is discarded with its owner lane below
+                const d4 c = warp_sum(eval_child(T, 0.25 * Si), 4);
+                if (q == sub) I1 = c;
+            }
+            // round 0: the control panel itself against this lane's column
+            const int jm = min(jj0 + sub, nj - 1);
+            TriJ T;
+            load_T(jm, T);
+            d4 I0;
+            {
+                double a1, a2, a3, a4;
+                grouped_eval<true, false, true, true, kAdRows>(myP, ng, T, a1, a2, a3, a4);
+                I0 = vec4((Si * a1) * T.tc + (Si * a2) * T.ta + (Si * a3) * T.tb, Si * a4);
+            }
+            const int ja = smId[3 * jm], jb = smId[3 * jm + 1], jc = smId[3 * jm + 2];
+            const bool skip = !active || (jj0 + sub >= nj) || (tile + jm == i) || ci.a == ja || ci.a == jb || ci.a == jc ||
+                              ci.b == ja || ci.b == jb || ci.b == jc || ci.c == ja || ci.c == jb || ci.c == jc;
+            bool unconv = !skip && runge_unconverged(I1, I0, pow2p);
+            d4 valE = I0, valO = I1;      // newest even-round / odd-round value of this lane's pair
+            int myLast = 1, myFailed = unconv ? 1 : 0;
+            unsigned um = __ballot_sync(0xffffffffu, unconv);
+            if (um) {
+                if (lane == 0) atomicAdd(&smCount[1], __popc(um));
+                // rounds 2..5 of every failing pair, one pair at a time, 32 lanes over its children (warp-uniform loop)
+                while (um) {
+                    const int src = __ffs(um) - 1;
+                    um &= um - 1;
+                    const int srcI = __shfl_sync(0xffffffffu, i, src), srcJm = __shfl_sync(0xffffffffu, jm, src);
+                    const double srcS = __shfl_sync(0xffffffffu, Si, src);
+                    DeepResult res;
+                    deep_rounds(tri, stride, ng, myC, smT + srcJm * kTileStride, srcI, srcS, shfl4(I1, src), shfl4(I0, src), pow2p, smCount, &res);
+                    if (lane == src) { valE = res.evenV; valO = res.oddV; myLast = res.last; myFailed = res.failed; }
+                }
+                stage_child(i, 1, sub);   // the deep rounds overwrote this thread's slot
+            }
+            if (!skip) {
+                const d3 nj3 = {smT[jm * kTileStride + 24], smT[jm * kTileStride + 25], smT[jm * kTileStride + 26]};
+                const double w = smT[jm * kTileStride + 27];
+                const d3 JE = assemble_J(valE, nj3, 0.0, false), JO = assemble_J(valO, nj3, 0.0, false);
+                accE.x = fma(w, JE.x, accE.x); accE.y = fma(w, JE.y, accE.y); accE.z = fma(w, JE.z, accE.z);
+                accO.x = fma(w, JO.x, accO.x); accO.y = fma(w, JO.y, accO.y); accO.z = fma(w, JO.z, accO.z);
+                depth = max(depth, myFailed);
+                lastRound = max(lastRound, myLast);
+                ++examined;
+            }
+        }
+    }
+    // the 4 lanes of a row hold the sums of their columns: fixed-order 4-lane sum, lane 0 of the row writes
+    d4 e4 = warp_sum(vec4(accE, 0.0), 4), o4 = warp_sum(vec4(accO, 0.0), 4);
+    for (int off = 2; off > 0; off >>= 1) depth = max(depth, __shfl_xor_sync(0xffffffffu, depth, off));
+    if (active && sub == 0) {
+        double *p = o.partial + ((long long)blockIdx.y * rows + r) * 6;
+        p[0] = e4.x; p[1] = e4.y; p[2] = e4.z; p[3] = o4.x; p[4] = o4.y; p[5] = o4.z;
+        o.depth[(long long)blockIdx.y * rows + r] = (unsigned char)depth;
+    }
+    lastRound = __reduce_max_sync(0xffffffffu, lastRound);
+    examined = __reduce_add_sync(0xffffffffu, examined);
+    if (lane == 0) {
+        if (lastRound > 0) atomicMax(o.lastRound, lastRound);
+        atomicAdd(o.counts, (unsigned long long)examined);
+    }
+    __syncthreads();
+    if (threadIdx.x >= 1 && threadIdx.x < 6 && smCount[threadIdx.x]) atomicAdd(o.counts + threadIdx.x, (unsigned long long)smCount[threadIdx.x]);
+}
+
+// out[r] = sum over chunks of the candidate selected by the parity of the class's last round L (odd L: newest odd-round
+// values), other[r] = the other candidate (a multi-GPU caller whose global L has the other parity takes that one);
+// refinements[r] = 1 + max over the row's pairs of the compare rounds failed (NumericalIntegrator3D::getRefinementsRequired)
+__global__ void k_reduce_partials_adaptive(const double *__restrict__ partial, const unsigned char *__restrict__ depth, int rows, int chunks,
+                                           const int *__restrict__ lastRound, double *__restrict__ out, double *__restrict__ other,
+                                           unsigned char *__restrict__ refinements) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows * 3) return;
+    const int r = e / 3, k = e % 3;
+    const bool odd = (*lastRound & 1) != 0;
+    double sE = 0.0, sO = 0.0;
+    for (int c = 0; c < chunks; ++c) {
+        const double *p = partial + ((long long)c * rows + r) * 6;
+        sE += p[k]; sO += p[3 + k];
+    }
+    out[e] = odd ? sO : sE;
+    if (other) other[e] = odd ? sE : sO;
+    if (refinements && k == 0) {
+        int d = 0;
+        for (int c = 0; c < chunks; ++c) d = max(d, (int)depth[(long long)c * rows + r]);
+        refinements[r] = (unsigned char)(1 + d);
+    }
+}
+
+void launch_apply_regular_adaptive(const PackedMesh &pm, int rowLo, int rowHi, int colLo, int colHi, int chunks, const double *weights,
+                                   double *partial6, unsigned char *depth, int *lastRound, unsigned long long *counts6, double *out3,
+                                   double *other3, unsigned char *refinements, cudaStream_t s) {
+    const int rows = rowHi - rowLo, cols = colHi - colLo;
+    if (rows <= 0 || cols <= 0) return;
+    const int colChunk = (cols + chunks - 1) / chunks;
+    dim3 grid((rows + kAdRows - 1) / kAdRows, chunks);
+    ApplyAdaptiveOut o{partial6, depth, lastRound, counts6};
+    constexpr size_t smem = sizeof(double) * (MAX_GAUSS_POINTS * 3 * (kThreads + kAdRows) + kAdTileJ * kTileStride);
+    static const cudaError_t attr = cudaFuncSetAttribute(k_apply_regular_adaptive<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    (void)attr;
+    ++g_launchCount;
+    k_apply_regular_adaptive<3><<<grid, kThreads, smem, s>>>(pm, rowLo, rowHi, colLo, colHi, colChunk, weights, o);
+    ++g_launchCount;
+    k_reduce_partials_adaptive<<<(rows * 3 + 255) / 256, 256, 0, s>>>(partial6, depth, rows, chunks, lastRound, out3, other3, refinements);
+}
+
 // tuning knob (env I2_MINBLOCKS = 3|4|5): resident CTAs per SM the regular kernel is compiled for
 static int g_minBlocks = [] { const char *e = getenv("I2_MINBLOCKS"); return e ? atoi(e) : 4; }();
 static int g_variant = [] { const char *e = getenv("I2_VARIANT"); return e ? atoi(e) : 27; }();
@@ -712,6 +979,7 @@ cudaError_t preload_kernels() {
     I2_TOUCH(k_regular_grouped<4, 31>);
     I2_TOUCH(k_regular_grouped<4, 27>);
     I2_TOUCH(k_apply_regular<4>);
+    I2_TOUCH(k_apply_regular_adaptive<3>);
 #undef I2_TOUCH
     return cudaSuccess;
 }

@@ -52,6 +52,10 @@ void launch_integrate(int cls, int mathMode, const PackedMesh &pm, const int *ta
                       long long countHost, int level, double *out4, double *fusedResults3, int numSMs, cudaStream_t s);
 void launch_apply_regular(const PackedMesh &pm, int rowLo, int rowHi, int colLo, int colHi, int chunks, const double *weights,
                           double *partial, double *out3, cudaStream_t s);
+// list-free regular class with the Runge loop per pair (see k_apply_regular_adaptive)
+void launch_apply_regular_adaptive(const PackedMesh &pm, int rowLo, int rowHi, int colLo, int colHi, int chunks, const double *weights,
+                                   double *partial6, unsigned char *depth, int *lastRound, unsigned long long *counts6, double *out3,
+                                   double *other3, unsigned char *refinements, cudaStream_t s);
 void launch_checksum(const double *results3, long long n, double *sums4, int numSMs, cudaStream_t s);
 void launch_compare(const double *cur4, const double *prev4, const int *tasks, const int *listIn, const int *countIn,
                     long long countHost, int *listOut, int *countOut, unsigned char *cellFlag, unsigned char *converged,

@@ -87,3 +87,53 @@ def test_apply_regular_beyond_the_reference_limit(ctx):
     n /= np.linalg.norm(n, axis=1, keepdims=True)
     along = (out * n).sum(1)
     assert (np.sign(along) == np.sign(along[0])).all()
+
+
+@pytest.mark.parametrize("name,scale", [("G1", 1.0), ("s5m", 0.0005)])
+def test_apply_regular_adaptive_equals_device_work_queue(ctx, name, scale):
+    """List-free Runge loop (i2_apply_regular_adaptive) against the list-based device work queue (i2_integrate_class,
+    level = adaptive) on the same mesh: same rounds, same per-round counts up to ties, same per-cell refinement counters,
+    and row sums that agree to rounding — including the reference's ping-pong rule for which round's value a converged
+    pair ends with."""
+    import torch
+    m = load_fixture(name, scale)
+    ctx.set_mesh(m.vertices, m.cells)
+    tasks = ctx.tasks_from_pairs(ctx.classify()[2])
+    q = ctx.integrate_class(2, tasks, -1)
+    rowsum = torch.zeros((m.n_cells, 3), dtype=torch.float64, device="cuda")
+    rowsum.index_add_(0, tasks[:, 0].long(), q["results"])
+    absJ = torch.zeros(m.n_cells, dtype=torch.float64, device="cuda")
+    absJ.index_add_(0, tasks[:, 0].long(), q["results"].abs().sum(1))
+    a = ctx.apply_regular_adaptive(0, m.n_cells)
+    st, sq = a["stats"], q["stats"]
+    assert st["last_round"] == sq["last_round"], (st, sq)
+    assert st["integrated"][0] == int(tasks.shape[0])
+    ties = 0
+    for k in range(1, sq["last_round"] + 1):
+        d = abs(st["unconverged"][k] - sq["unconverged"][k])
+        ties = max(ties, d)
+        assert d <= max(8, 0.15 * sq["unconverged"][k]), (name, k, st, sq)
+    if name == "G1":
+        assert ties == 0
+    assert int((a["refinements"] != q["refinements"]).sum()) <= 4 * ties + 4
+    err = (a["out"] - rowsum).abs().sum(1)
+    rel = err / absJ                      # against the sum of |J| of the row: the row sums themselves cancel
+    assert float(rel.median()) < 1e-12, float(rel.median())
+    # a flipped tie changes one pair by up to ~1e-3 of its value; everything else is rounding
+    assert int((rel > 1e-9).sum()) <= 2 * ties + (0 if name == "G1" else 2), (name, int((rel > 1e-9).sum()), ties)
+    assert float(rel.max()) < 1e-4
+    # the other parity: same pairs, the other ping-pong buffer — close, finite, and different somewhere
+    assert torch.isfinite(a["other"]).all()
+    assert float(((a["other"] - a["out"]).abs().sum(1) / absJ).max()) < 2e-2
+    assert float((a["other"] - a["out"]).abs().sum()) > 0.0
+    # rows [lo, hi) only, with weights: equals the same rows of the weighted list-based sums
+    w = torch.rand(m.n_cells, dtype=torch.float64, device="cuda", generator=torch.Generator(device="cuda").manual_seed(1)) + 0.5
+    lo, hi = m.n_cells // 3, m.n_cells // 3 + 40
+    b = ctx.apply_regular_adaptive(lo, hi, w)
+    rs = torch.zeros((m.n_cells, 3), dtype=torch.float64, device="cuda")
+    rs.index_add_(0, tasks[:, 0].long(), q["results"] * w[tasks[:, 1].long()][:, None])
+    relb = (b["out"] - rs[lo:hi]).abs().sum(1) / absJ[lo:hi]
+    assert float(relb.median()) < 1e-12 and float(relb.max()) < 1e-4
+    # bitwise reproducible
+    a2 = ctx.apply_regular_adaptive(0, m.n_cells)
+    assert torch.equal(a2["out"], a["out"]) and torch.equal(a2["refinements"], a["refinements"])
