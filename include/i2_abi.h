@@ -85,6 +85,8 @@ int i2_refine_mesh_once(i2_context *ctx, const double *d_vertices_in, int nv_in,
  *      Two passes so that the lists come out deterministic (lexicographic in (i,j), i<j, k = slot).       */
 int i2_classify_count(i2_context *ctx, const int *d_cells, int nc, long long h_counts[3]);
 int i2_classify_fill(i2_context *ctx, const int *d_cells, int nc, int *d_simple, int *d_attached, int *d_not);
+/* any of the three lists may be NULL and is then skipped: a mesh whose regular list would not fit (N^2/2 x 12 B) takes
+ * only the two adjacent lists from here and integrates the regular class list-free (i2_apply_regular[_adaptive])       */
 /* tasks[n..2n) = (j, i, n+idx): replaces kAddReversedPairs (src/evaluators/evaluator3d.cu:22-31)            */
 int i2_add_reversed_pairs(i2_context *ctx, int *d_tasks, long long n);
 

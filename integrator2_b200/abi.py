@@ -199,13 +199,15 @@ class Context:
         self.nc = nc
         return normals, measures
 
-    def classify(self):
-        """-> list of 3 int32[n,3] device tensors (i<j pairs, lexicographic, k = slot)."""
+    def classify(self, regular=True):
+        """-> list of 3 int32[n,3] device tensors (i<j pairs, lexicographic, k = slot).  regular=False skips the regular
+        list (None in its place; meshes whose N^2/2 list would not fit integrate that class list-free)."""
         torch = self.torch
         cnt = (C.c_longlong * 3)()
         _check(self.L.i2_classify_count(self.h, _ptr(self.d_cells), self.nc, cnt))
+        self.pair_counts = [int(x) for x in cnt]
         dev = f"cuda:{self.device}"
-        lists = [torch.empty((int(cnt[k]), 3), dtype=torch.int32, device=dev) for k in range(3)]
+        lists = [torch.empty((int(cnt[k]), 3), dtype=torch.int32, device=dev) if (k < 2 or regular) else None for k in range(3)]
         _check(self.L.i2_classify_fill(self.h, _ptr(self.d_cells), self.nc, _ptr(lists[0]), _ptr(lists[1]), _ptr(lists[2])))
         return lists
 

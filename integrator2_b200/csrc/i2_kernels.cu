@@ -1207,7 +1207,7 @@ __global__ void __launch_bounds__(256) k_classify_fill(const int *__restrict__ c
             for (int w = 0; w < warp; ++w) pos += warpCnt[w][cls];
             pos += __popc(masks[cls] & ((1u << lane) - 1u));
             int *dst = cls == 0 ? simple : (cls == 1 ? attached : notn);
-            dst[3 * pos] = i; dst[3 * pos + 1] = j; dst[3 * pos + 2] = (int)pos;
+            if (dst) { dst[3 * pos] = i; dst[3 * pos + 1] = j; dst[3 * pos + 2] = (int)pos; }   // a NULL list is skipped
         }
         __syncthreads();
         if (threadIdx.x < 3) {

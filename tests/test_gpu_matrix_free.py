@@ -137,3 +137,15 @@ def test_apply_regular_adaptive_equals_device_work_queue(ctx, name, scale):
     # bitwise reproducible
     a2 = ctx.apply_regular_adaptive(0, m.n_cells)
     assert torch.equal(a2["out"], a["out"]) and torch.equal(a2["refinements"], a["refinements"])
+
+
+def test_classification_without_the_regular_list(ctx):
+    """i2_classify_fill with a NULL regular list: the two adjacent lists are unchanged, the count of the regular class is
+    still reported (what a mesh beyond the N^2-list limit uses together with the list-free regular kernels)."""
+    import torch
+    m = load_fixture("s5m", 0.0005)
+    ctx.set_mesh(m.vertices, m.cells)
+    full = ctx.classify()
+    part = ctx.classify(regular=False)
+    assert part[2] is None and ctx.pair_counts[2] == int(full[2].shape[0])
+    assert torch.equal(part[0], full[0]) and torch.equal(part[1], full[1])
