@@ -37,8 +37,10 @@ struct i2_context {
     struct ClassScratch {
         double *bufB = nullptr;
         size_t bufBCap = 0;
-        int *rest[2] = {nullptr, nullptr};
+        int *rest[2] = {nullptr, nullptr};   // [0] = dense list of unconverged slots (input order), [1] = per-CTA staging segments
         size_t restCap = 0;
+        int *blockCnt = nullptr;             // per-CTA counts of the deterministic compaction
+        size_t blockCntCap = 0;
         unsigned char *cellFlag = nullptr;
         size_t cellFlagCap = 0;
         QueueState *qs = nullptr;
@@ -171,6 +173,7 @@ int i2_destroy(i2_context *c) {
         if (sc.bufB) cudaFree(sc.bufB);
         for (int k = 0; k < 2; ++k) if (sc.rest[k]) cudaFree(sc.rest[k]);
         if (sc.cellFlag) cudaFree(sc.cellFlag);
+        if (sc.blockCnt) cudaFree(sc.blockCnt);
         if (sc.qs) cudaFree(sc.qs);
     }
     for (int k = 0; k < 3; ++k) if (c->prof[k]) cudaEventDestroy(c->prof[k]);
@@ -332,6 +335,7 @@ int enqueue_class(i2_context *c, int cls, const int *tasks, long long n, int lev
             sc.restCap = (size_t)n;
         }
         rc = ensure(&sc.cellFlag, &sc.cellFlagCap, (size_t)c->nc);
+        if (!rc) rc = ensure(&sc.blockCnt, &sc.blockCntCap, (size_t)kCompareMaxBlocks);
         if (rc) return rc;
         I2_CUDA(cudaMemsetAsync(sc.cellFlag, 0, c->nc, s));
 
@@ -343,10 +347,10 @@ int enqueue_class(i2_context *c, int cls, const int *tasks, long long n, int lev
         for (int m = 1; m <= MAX_REFINE_LEVEL; ++m) {
             double *cur = (m & 1) ? sc.bufB : integrals;
             const double *prev = (m & 1) ? integrals : sc.bufB;
-            const int *listIn = m == 1 ? nullptr : sc.rest[(m - 1) & 1];
+            const int *listIn = m == 1 ? nullptr : sc.rest[0];
             const int *countIn = m == 1 ? nullptr : &sc.qs->count[m - 1];
             launch_integrate(cls, c->mathMode, pm, tasks, listIn, countIn, n, m, cur, nullptr, c->numSMs, s);
-            launch_compare(cur, prev, tasks, listIn, countIn, n, sc.rest[m & 1], &sc.qs->count[m], sc.cellFlag, converged, sc.qs, m,
+            launch_compare(cur, prev, tasks, listIn, countIn, n, sc.rest[1], sc.blockCnt, sc.rest[0], &sc.qs->count[m], sc.cellFlag, converged, sc.qs, m,
                            c->numSMs, s);
             launch_bump(sc.cellFlag, refinements, c->nc, s);
         }

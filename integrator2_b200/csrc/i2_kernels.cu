@@ -987,20 +987,29 @@ cudaError_t preload_kernels() {
 // ---------------------------------------------------------------------------------------------------------
 // adaptive error control: Runge compare + warp-ballot compaction of the unconverged task slots
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+// Runge comparison + DETERMINISTIC compaction of the unconverged slots.  Every CTA owns a contiguous segment of the input
+// list and appends its unconverged slots, in input order, to the same segment of `staging` (ballot + prefix over the
+// CTA's warps, no atomics); k_compact_gather then packs the segments densely in CTA order.  The output list therefore
+// keeps the input order (ascending slots), whatever the scheduling: which tasks share a warp in the next round — and with
+// it the warp-wide far-field tier decisions of the regular kernel — is the same in every run, so adaptive results are
+// bitwise reproducible (an atomic ticket per warp made the order depend on which kernels ran concurrently).
+constexpr int kCompareThreads = 256;
+__global__ void __launch_bounds__(kCompareThreads)
 k_compare(const double *__restrict__ cur, const double *__restrict__ prev, const int *__restrict__ tasks, const int *__restrict__ listIn,
-          const int *__restrict__ countIn, long long countHost, int *__restrict__ listOut, int *countOut, unsigned char *cellFlag,
+          const int *__restrict__ countIn, long long countHost, int *__restrict__ staging, int *__restrict__ blockCnt, unsigned char *cellFlag,
           unsigned char *converged, QueueState *qs, int round) {
+    __shared__ int warpCnt[kCompareThreads / 32];
     const long long n = countIn ? (long long)*countIn : countHost;
-    const int lane = threadIdx.x & 31;
-    const long long warpId = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long warpStride = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long seg = (n + gridDim.x - 1) / gridDim.x;
+    const long long segLo = (long long)blockIdx.x * seg, segHi = segLo + seg < n ? segLo + seg : n;
     const double pow2p = c_pow2p;
-    for (long long base = warpId * 32; base < n; base += warpStride * 32) {
-        const long long r = base + lane;
+    int running = 0;
+    for (long long base = segLo; base < segHi; base += kCompareThreads) {
+        const long long r = base + threadIdx.x;
         bool unconv = false;
         int slot = 0;
-        if (r < n) {
+        if (r < segHi) {
             slot = listIn ? __ldg(listIn + r) : (int)r;
             const double2 *c = reinterpret_cast<const double2 *>(cur + 4 * (long long)slot);
             const double2 *p = reinterpret_cast<const double2 *>(prev + 4 * (long long)slot);
@@ -1010,23 +1019,54 @@ k_compare(const double *__restrict__ cur, const double *__restrict__ prev, const
             if (unconv) cellFlag[__ldg(tasks + 3 * (long long)slot)] = 1;  // benign race: everyone writes 1
         }
         const unsigned m = __ballot_sync(0xffffffffu, unconv);
-        if (m) {
-            int pos = 0;
-            if (lane == 0) pos = atomicAdd(countOut, __popc(m));
-            pos = __shfl_sync(0xffffffffu, pos, 0);
-            if (unconv) listOut[pos + __popc(m & ((1u << lane) - 1u))] = slot;
-        }
+        if (lane == 0) warpCnt[warp] = __popc(m);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < kCompareThreads / 32; ++w) { const int cw = warpCnt[w]; before += w < warp ? cw : 0; total += cw; }
+        if (unconv) staging[segLo + running + before + __popc(m & ((1u << lane) - 1u))] = slot;
+        running += total;
+        __syncthreads();
     }
+    if (threadIdx.x == 0) blockCnt[blockIdx.x] = running;
     if (blockIdx.x == 0 && threadIdx.x == 0 && n > 0) qs->lastRound = round;
 }
 
+// packs the per-CTA segments of `staging` densely into listOut in CTA order; *countOut = total
+__global__ void __launch_bounds__(kCompareThreads)
+k_compact_gather(const int *__restrict__ staging, const int *__restrict__ blockCnt, const int *__restrict__ countIn, long long countHost,
+                 int *__restrict__ listOut, int *countOut) {
+    __shared__ int red[kCompareThreads / 32];
+    __shared__ int offsetSh;
+    const long long n = countIn ? (long long)*countIn : countHost;
+    const long long seg = (n + gridDim.x - 1) / gridDim.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int part = 0;
+    for (int b = threadIdx.x; b < (int)blockIdx.x; b += kCompareThreads) part += __ldg(blockCnt + b);
+    part = __reduce_add_sync(0xffffffffu, part);
+    if (lane == 0) red[warp] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int off = 0;
+        for (int w = 0; w < kCompareThreads / 32; ++w) off += red[w];
+        offsetSh = off;
+    }
+    __syncthreads();
+    const int offset = offsetSh, mine = __ldg(blockCnt + blockIdx.x);
+    const long long segLo = (long long)blockIdx.x * seg;
+    for (int t = threadIdx.x; t < mine; t += kCompareThreads) listOut[offset + t] = staging[segLo + t];
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *countOut = offset + mine;
+}
+
 void launch_compare(const double *cur4, const double *prev4, const int *tasks, const int *listIn, const int *countIn, long long countHost,
-                    int *listOut, int *countOut, unsigned char *cellFlag, unsigned char *converged, QueueState *qs, int round, int numSMs,
-                    cudaStream_t s) {
-    long long blocks = countIn ? (long long)numSMs * 8 : (countHost + 255) / 256;
-    if (blocks > (long long)numSMs * 32) blocks = (long long)numSMs * 32;
+                    int *staging, int *blockCnt, int *listOut, int *countOut, unsigned char *cellFlag, unsigned char *converged, QueueState *qs,
+                    int round, int numSMs, cudaStream_t s) {
+    long long blocks = countIn ? (long long)numSMs * 8 : (countHost + kCompareThreads - 1) / kCompareThreads;
+    if (blocks > kCompareMaxBlocks) blocks = kCompareMaxBlocks;
     if (blocks < 1) blocks = 1;
-    ++g_launchCount; k_compare<<<(unsigned)blocks, 256, 0, s>>>(cur4, prev4, tasks, listIn, countIn, countHost, listOut, countOut, cellFlag, converged, qs, round);
+    ++g_launchCount;
+    k_compare<<<(unsigned)blocks, kCompareThreads, 0, s>>>(cur4, prev4, tasks, listIn, countIn, countHost, staging, blockCnt, cellFlag, converged, qs, round);
+    ++g_launchCount;
+    k_compact_gather<<<(unsigned)blocks, kCompareThreads, 0, s>>>(staging, blockCnt, countIn, countHost, listOut, countOut);
 }
 
 __global__ void k_flag_cells(const int *__restrict__ tasks, long long n, unsigned char *cellFlag) {

@@ -57,9 +57,12 @@ void launch_apply_regular_adaptive(const PackedMesh &pm, int rowLo, int rowHi, i
                                    double *partial6, unsigned char *depth, int *lastRound, unsigned long long *counts6, double *out3,
                                    double *other3, unsigned char *refinements, cudaStream_t s);
 void launch_checksum(const double *results3, long long n, double *sums4, int numSMs, cudaStream_t s);
+// Runge comparison of round `round` + deterministic compaction of the unconverged slots: staging = int[capacity of the list]
+// (per-CTA segments), blockCnt = int[kCompareMaxBlocks], listOut = dense list in input order, *countOut = its length
+constexpr int kCompareMaxBlocks = 148 * 32;
 void launch_compare(const double *cur4, const double *prev4, const int *tasks, const int *listIn, const int *countIn,
-                    long long countHost, int *listOut, int *countOut, unsigned char *cellFlag, unsigned char *converged,
-                    QueueState *qs, int round, int numSMs, cudaStream_t s);
+                    long long countHost, int *staging, int *blockCnt, int *listOut, int *countOut, unsigned char *cellFlag,
+                    unsigned char *converged, QueueState *qs, int round, int numSMs, cudaStream_t s);
 void launch_flag_cells(const int *tasks, long long n, unsigned char *cellFlag, cudaStream_t s);
 void launch_bump(unsigned char *cellFlag, unsigned char *refinements, int nc, cudaStream_t s);
 // adds the closed-form singular integral (adjacent classes), assembles J; bufA/bufB selected by QueueState::lastRound
