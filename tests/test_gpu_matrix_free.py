@@ -90,7 +90,7 @@ def test_apply_regular_beyond_the_reference_limit(ctx):
 
 
 @pytest.mark.parametrize("name,scale", [("G1", 1.0), ("s5m", 0.0005)])
-def test_apply_regular_adaptive_equals_device_work_queue(ctx, name, scale):
+def test_apply_regular_adaptive_equals_device_work_queue(ctx, oracle, name, scale):
     """List-free Runge loop (i2_apply_regular_adaptive) against the list-based device work queue (i2_integrate_class,
     level = adaptive) on the same mesh: same rounds, same per-round counts up to ties, same per-cell refinement counters,
     and row sums that agree to rounding — including the reference's ping-pong rule for which round's value a converged
@@ -122,6 +122,17 @@ def test_apply_regular_adaptive_equals_device_work_queue(ctx, name, scale):
     # a flipped tie changes one pair by up to ~1e-3 of its value; everything else is rounding
     assert int((rel > 1e-9).sum()) <= 2 * ties + (0 if name == "G1" else 2), (name, int((rel > 1e-9).sum()), ties)
     assert float(rel.max()) < 1e-4
+    if name == "G1":
+        # and against the CPU oracle's adaptive run (the restatement of the reference's host loop, pinned to the reference's
+        # own dumps): same rounds, same counters, row sums to 1e-12 of the row's sum of |J|
+        om = oracle.OracleMesh(m.vertices, m.cells)
+        t = om.tasks(2)
+        ref = om.run_class(2, t, -1)
+        assert st["last_round"] == int(ref["stats"][0])
+        assert np.array_equal(a["refinements"].cpu().numpy(), ref["refinements"])
+        rs = np.zeros((m.n_cells, 3)); ab = np.zeros(m.n_cells)
+        np.add.at(rs, t[:, 0], ref["results"]); np.add.at(ab, t[:, 0], np.abs(ref["results"]).sum(1))
+        assert (np.abs(a["out"].cpu().numpy() - rs).sum(1) / ab).max() < 1e-12
     # the other parity: same pairs, the other ping-pong buffer — close, finite, and different somewhere
     assert torch.isfinite(a["other"]).all()
     assert float(((a["other"] - a["out"]).abs().sum(1) / absJ).max()) < 2e-2

@@ -76,3 +76,48 @@ def test_adaptive_cost_model_orders_near_before_far():
     per = np.array([c_np[lo:hi].sum() for lo, hi in b])
     assert per.max() / per.mean() < 1.02
     assert b == shard_bounds(t.shape[0], 4, c_np) or abs(b[1][0] - shard_bounds(t.shape[0], 4, c_np)[1][0]) <= 1
+
+
+def test_peer_export_bookkeeping_without_a_gpu():
+    """multigpu.PeerExport: who allocates, who maps, which address a rank hands to the kernels, who frees / unmaps
+    (the CUDA side — i2_peer_alloc / i2_peer_open and the stores over NVLink — is covered by tests/test_gpu_peer_export.py)."""
+    from integrator2_b200.multigpu import PeerExport
+
+    class FakeCtx:
+        def __init__(self):
+            self.calls = []
+
+        def peer_alloc(self, rows, cols=3):
+            self.calls.append(("alloc", rows))
+            return "FULL", b"h" * 64, 1 << 20
+
+        def peer_open(self, handle):
+            assert handle == b"h" * 64
+            self.calls.append(("open",))
+            return 1 << 30
+
+        def peer_close(self, addr):
+            self.calls.append(("close", addr))
+
+        def peer_free(self, addr):
+            self.calls.append(("free", addr))
+
+    bounds = shard_bounds(1001, 3)
+    box = {}
+
+    def exchange(handle):          # stands in for dist.broadcast_object_list
+        if handle is not None:
+            box["h"] = handle
+        return box["h"]
+
+    owner, writer = FakeCtx(), FakeCtx()
+    e0 = PeerExport(owner, 1001, bounds, 0, 3, handle_exchange=exchange)
+    e2 = PeerExport(writer, 1001, bounds, 2, 3, handle_exchange=exchange)
+    assert e0.full == "FULL" and e0.results_arg() == (1 << 20) + 24 * bounds[0][0]
+    assert e2.full is None and e2.results_arg() == (1 << 30) + 24 * bounds[2][0]
+    e0.close(); e2.close(); e2.close()
+    assert owner.calls == [("alloc", 1001), ("free", 1 << 20)]
+    assert writer.calls == [("open",), ("close", 1 << 30)]
+    single = FakeCtx()
+    e = PeerExport(single, 7, [(0, 7)], 0, 1)
+    assert e.results_arg() == 1 << 20 and single.calls == [("alloc", 7)]
