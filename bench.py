@@ -113,7 +113,9 @@ def run_reference(args, mesh, n_pairs_total):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cfg = {"workload": f"{args.mesh}.dat -r {args.level} all classes ({n_pairs_total} ordered pairs)", "inputs": "larger than L2 (no flush needed)"}
+    cfg = {"workload": workload_name(args.mesh, args.scale, args.level, class_pair_counts(mesh)), "triangles": mesh.n_cells,
+           "quadrature": "Cowper 13-point (order 7)", "command": f"integrator2test3D -f {args.mesh}.dat -s {args.scale} -r {args.level}" if args.level >= 0
+           else f"integrator2test3D -f {args.mesh}.dat -s {args.scale}", "l2": "inputs+outputs per step are far larger than L2; no flush needed"}
     if os.path.exists(binary):
         path = mesh_dat_path(args.mesh, mesh)
         times = []
@@ -138,7 +140,7 @@ def run_reference(args, mesh, n_pairs_total):
             value = n_pairs_total / (ms_step * 1e-3)
             line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
                     "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-                    "data": f"reference example mesh ({args.mesh}.dat), no random data", "config": cfg,
+                    "data": f"reference example mesh (tests/golden/meshes.npz, parsed from {args.mesh}.dat); no random data", "config": cfg,
                     "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
                                      "sample": "whole workload; the reference is CUDA-only (no CPU path): its unmodified sources compiled for sm_100, "
                                                "1 host thread + this B200, time window = its own three 'Time for ... integration' lines"},
@@ -151,7 +153,7 @@ def run_reference(args, mesh, n_pairs_total):
     v, c, sample = cpu_oracle_rate_from_mesh(O, om, mesh, args.level, budget_s=15.0)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": n_pairs_total / v * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-            "data": "reference example mesh", "config": cfg,
+            "data": f"reference example mesh (tests/golden/meshes.npz, parsed from {args.mesh}.dat); no random data", "config": cfg,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": c, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -187,12 +189,7 @@ def main():
 
     if args.impl == "reference":
         # pair counts without a GPU: from the mesh size and the two small classes
-        from oracle import oracle_py as O
-        om = O.OracleMesh(mesh.vertices, mesh.cells)
-        total = 2 * sum(int(x.shape[0]) for x in om.classify()) if mesh.n_cells <= 4000 else None
-        if total is None:
-            total = reference_total_pairs(mesh)
-        run_reference(args, mesh, total)
+        run_reference(args, mesh, sum(class_pair_counts(mesh)))   # pair counts without a GPU: vertex / edge incidence
         return
 
     import torch
@@ -472,8 +469,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": f"reference example mesh (tests/golden/meshes.npz, parsed from {args.mesh}.dat); no random data",
-                "config": {"workload": f"{args.mesh}.dat scale {args.scale} level {'adaptive' if args.level < 0 else args.level}: "
-                                       f"{counts[0]} vertex-adjacent + {counts[1]} edge-adjacent + {counts[2]} regular = {total_pairs} ordered pairs",
+                "config": {"workload": workload_name(args.mesh, args.scale, args.level, counts),
                            "triangles": mesh.n_cells, "quadrature": "Cowper 13-point (order 7)", "sharding": f"{world} contiguous equal-cost shards per class, results resident per rank (no data-path collective)",
                            "l2": "inputs+outputs per step (task lists 12 B/pair, results 56 B/pair) are far larger than L2; no flush needed"},
                 "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
@@ -481,6 +477,27 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def class_pair_counts(mesh):
+    """(vertex-adjacent, edge-adjacent, regular) ORDERED pair counts from vertex / edge incidence, without an O(N^2) pass and
+    without a GPU: a pair sharing an edge is counted twice in sum_v k_v (k_v - 1), a pair sharing one vertex once."""
+    import numpy as np
+    n = mesh.n_cells
+    c = mesh.cells.astype(np.int64)
+    kv = np.bincount(c.ravel())
+    share_vertex = int((kv * (kv - 1)).sum())
+    e = np.sort(np.concatenate([c[:, [0, 1]], c[:, [1, 2]], c[:, [2, 0]]]), axis=1)
+    _, cnt = np.unique(e[:, 0] * (c.max() + 1) + e[:, 1], return_counts=True)
+    share_edge = int((cnt * (cnt - 1)).sum())
+    va = share_vertex - 2 * share_edge
+    return va, share_edge, n * (n - 1) - va - share_edge
+
+
+def workload_name(mesh_name, scale, level, counts):
+    """config.workload: the same string for our arm and for the reference arm"""
+    return (f"{mesh_name}.dat scale {scale} level {'adaptive' if level < 0 else level}: "
+            f"{counts[0]} vertex-adjacent + {counts[1]} edge-adjacent + {counts[2]} regular = {sum(counts)} ordered pairs")
 
 
 def regular_pair_count(mesh):
