@@ -50,3 +50,20 @@ def test_product_never_links_or_imports_the_oracle():
                     if re.search(r"liboracle|oracle_py|from oracle|import oracle|orc_", txt):
                         bad.append(os.path.join(dirpath, fn))
     assert not bad, bad
+
+
+def test_ctypes_binding_matches_the_header_prototypes():
+    """Every prototype of include/i2_abi.h has the same number of parameters as the argtypes the ctypes binding declares
+    (a mismatch would corrupt the call on the GPU box, where it is expensive to find)."""
+    from integrator2_b200 import abi
+    L = abi.load_library()
+    text = open(os.path.join(ROOT, "include", "i2_abi.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = re.findall(r"(?:int|const char \*)\s*\*?\s*(i2_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S)
+    assert len(protos) == len(_declared())
+    for name, params in protos:
+        params = " ".join(params.split())
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        fn = getattr(L, name)
+        assert fn.argtypes is not None, f"{name}: no argtypes in abi.py"
+        assert len(fn.argtypes) == n, f"{name}: header has {n} parameters, abi.py declares {len(fn.argtypes)}"
