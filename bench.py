@@ -389,7 +389,12 @@ def main():
                             "instruction reads three distinct registers (the practical ceiling of real code, ~75 % of peak); FP64-pipe active 63 % (84 % of the three-operand ceiling) in "
                             "profiles/r01_ncu_k_regular_grouped_v7_final.txt",
                     "executed_fp64_inst_per_pair": 1130,
-                    "fp64_pipe_active_frac": 0.629}
+                    "fp64_pipe_active_frac": 0.629,
+                    # 55 MUFU (RSQ64H / RCP64H) warp instructions per pair in the same capture; the XU pipe is not a limiter
+                    "executed_mufu_per_pair": 55,
+                    "mufu_frac": (55.0 * my_counts[2] / (ms_k * 1e-3) / 1e9) / mufu_g if (args.level == 0 and mufu_g > 0) else None,
+                    "issue_slots_active_frac": 0.572,
+                    "dispatch_bound_frac": 0.89}
 
     # ---- end to end through the host-buffer C ABI (N=1): host mesh in -> prepare (H2D, geometry, classification, task
     # lists) -> three classes -> results.  Two variants, both timed with the host clock around the blocking calls:
