@@ -107,6 +107,17 @@ def mesh_dat_path(name, mesh):
     return p
 
 
+def reference_command(binary, mesh_path, scale, level):
+    """Command line of the reference CLI for a workload.  `-r N` selects a FIXED refinement level; automatic error control
+    is the absence of `-r` (/root/reference/tests/integrator3D/main.cu:114-123) — `-r -1` must never be passed."""
+    cmd = [binary, "-f", mesh_path]
+    if scale != 1.0:
+        cmd += ["-s", repr(scale)]
+    if level >= 0:
+        cmd += ["-r", str(level)]
+    return cmd
+
+
 def run_reference(args, mesh, n_pairs_total):
     """Reference arm: the UNMODIFIED reference CUDA build on this GPU, timed by its own GpuTimer lines."""
     binary = os.path.join(ROOT, "oracle", "_ref", "integrator2test3D")
@@ -114,14 +125,12 @@ def run_reference(args, mesh, n_pairs_total):
     if rank != 0:
         return
     cfg = {"workload": workload_name(args.mesh, args.scale, args.level, class_pair_counts(mesh)), "triangles": mesh.n_cells,
-           "quadrature": "Cowper 13-point (order 7)", "command": f"integrator2test3D -f {args.mesh}.dat -s {args.scale} -r {args.level}" if args.level >= 0
-           else f"integrator2test3D -f {args.mesh}.dat -s {args.scale}", "l2": "inputs+outputs per step are far larger than L2; no flush needed"}
+           "quadrature": "Cowper 13-point (order 7)", "command": " ".join(reference_command("integrator2test3D", args.mesh + ".dat", args.scale, args.level)),
+           "l2": "inputs+outputs per step are far larger than L2; no flush needed"}
     if os.path.exists(binary):
         path = mesh_dat_path(args.mesh, mesh)
         times = []
-        cmd = [binary, "-f", path, "-r", str(args.level)]
-        if args.scale != 1.0:
-            cmd += ["-s", repr(args.scale)]
+        cmd = reference_command(binary, path, args.scale, args.level)
         ok = True
         for it in range(args.warmup + args.steps):
             t0 = time.time()
@@ -174,6 +183,7 @@ def main():
     ap.add_argument("--mf-mesh", default="G1", help="matrixfree: base mesh (G1 -> configs[4]; s5m2 with --scale 0.0005 --sphere-level 2 --level -1 -> configs[3], 125 280 triangles)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-largest", action="store_true", help="skip the largest-mesh (configs[3], 125 280 triangles) object")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -197,75 +207,57 @@ def main():
     from integrator2_b200 import abi
 
     torch.cuda.set_device(local)
+    uid = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        box = [abi.MultiGpu.unique_id() if rank == 0 else None]     # the library's own NCCL communicator: id from rank 0
+        dist.broadcast_object_list(box, src=0)
+        uid = box[0]
     dev = torch.device(f"cuda:{local}")
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)          # every torch op and every library kernel of this process runs on this stream
-    ctx = abi.Context(local)
+    # The multi-GPU layer of the C ABI (i2_mgpu_*): one process per GPU here, the same entry points the CLI / host classes use
+    # with one process driving all GPUs.  Sharded prepare, integration of the shard, NCCL inside the library.
+    mg = abi.MultiGpu(device=local, rank=rank, world=world, uid=uid)
+    ctx = mg.contexts[0]
 
-    # ---- resident inputs: mesh SoA + the three ordered task lists (built on the device) ----------------------
-    ctx.set_mesh(mesh.vertices, mesh.cells)
-    lists = ctx.classify()
-    tasks_full = [ctx.tasks_from_pairs(p) for p in lists]
-    del lists
-    counts = [int(t.shape[0]) for t in tasks_full]
+    # ---- resident inputs: mesh SoA + this rank's shard of the three ordered task lists (built on the device) ----
+    counts = mg.prepare(mesh.vertices, mesh.cells, args.level)
     total_pairs = sum(counts)
-    # equal-cost contiguous shard of every class for this rank
-    from integrator2_b200.multigpu import adaptive_task_cost, cost_balanced_bounds, shard_bounds
-    if args.level < 0 and world > 1:
-        # adaptive error control: shards of equal PREDICTED cost (class weight x expected refinement depth from the
-        # centroid-distance / panel-size ratio), still contiguous so that all descendants of a task stay on its rank
-        all_bounds = [cost_balanced_bounds(adaptive_task_cost(mesh.vertices, mesh.cells, t, cls), world) for cls, t in enumerate(tasks_full)]
-    else:
-        all_bounds = [shard_bounds(n, world) for n in counts]
-    bounds = [b[rank] for b in all_bounds]
-    tasks = [t[lo:hi].contiguous() for t, (lo, hi) in zip(tasks_full, bounds)]
-    if world > 1:
-        del tasks_full
-    my_counts = [int(t.shape[0]) for t in tasks]
-    outs = [(torch.empty((n, 4), dtype=torch.float64, device=dev), torch.empty((n, 3), dtype=torch.float64, device=dev)) for n in my_counts]
-    gathered = None
-    if world > 1 and rank == 0:
-        gathered = [torch.empty((n, 3), dtype=torch.float64, device=dev) for n in counts]
-    refin = torch.zeros((mesh.n_cells,), dtype=torch.uint8, device=dev) if args.level < 0 else None
-    refins = [torch.zeros((mesh.n_cells,), dtype=torch.uint8, device=dev) for _ in range(3)] if args.level < 0 else None
-
-    side = torch.cuda.Stream(device=dev) if world > 1 else None
-    chk = torch.zeros((3, 4), dtype=torch.float64, device=dev)
+    my_first, my_counts = mg.shard(rank)
 
     def step():
-        # every rank integrates its shard of every class; the per-pair results stay resident on the rank that computed them.
-        # Tasks are independent, so the step has no data-path collective; ranks meet at the barrier that brackets the timing.
-        # One i2_integrate_all call = the three integrateOver* virtuals; the two adjacent classes overlap the regular one.
-        if refins is not None:
-            for r in refins:
-                r.zero_()
-        ctx.integrate_all(tasks, args.level, want_stats=False, refinements=refins, out=outs)
-
-    def global_checksum():
-        # validation outside the timed region: per-class sum |J|_1 over all ranks (NCCL all-reduce of 3 doubles)
-        for cls in range(3):
-            chk[cls, 3] = outs[cls][1].abs().sum()
-        if world > 1:
-            dist.all_reduce(chk)
-        return [float(x) for x in chk[:, 3].tolist()]
-
-    def step_with_gather():
-        # export variant: finished chunks of per-pair results travel to rank 0 over NCCL while the next chunk computes
-        from integrator2_b200.multigpu import integrate_and_gather, wait_all
-        works = []
-        for cls in (2, 0, 1):
-            works += integrate_and_gather(ctx, cls, tasks[cls], args.level, outs[cls], gathered[cls] if rank == 0 else None,
-                                          all_bounds[cls], rank, world, side, chunks=8 if cls == 2 else 1)
-        wait_all(works, side)
+        # every rank integrates its shard of every class (the pairs with forward slots [lo, hi) in both orders); the per-pair
+        # results stay on the rank that computed them (row-striped: each rank would format / write the rows it owns).
+        # Fixed level: no data-path collective.  Error control: NCCL all-reduce(max) of the three last rounds and of the
+        # per-cell refinement counters before the final assembly, inside i2_mgpu_run.
+        mg.run(args.level)
 
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    def timed_steps(fn, steps, warm):
+        with torch.cuda.stream(stream):
+            for _ in range(warm):
+                fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                fn()
+            e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps
 
     with torch.cuda.stream(stream):
         for _ in range(args.warmup):
@@ -276,142 +268,124 @@ def main():
         sampler.start()
         time.sleep(0.25)
     launches0 = abi.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    with torch.cuda.stream(stream):
-        e0.record(stream)
-        for _ in range(args.steps):
-            step()
-        e1.record(stream)
-    barrier()
-    ms_total = e0.elapsed_time(e1)
+    ms_step = timed_steps(step, args.steps, 0)
     launches = abi.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
         lt = torch.tensor([launches], dtype=torch.int64, device=dev)
         dist.all_reduce(lt)
         launches = int(lt.item())
-    ms_step = ms_total / args.steps
     value = total_pairs / (ms_step * 1e-3)
-    checksum = global_checksum()
-
-    # ---- N > 1: the export variant (all per-pair results gathered to rank 0 over NVLink), timed separately ------------
-    gather_info = None
-    if world > 1:
-        for _ in range(2):
-            step_with_gather()
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record(stream)
-        for _ in range(args.steps):
-            step_with_gather()
-        g1.record(stream)
-        barrier()
-        tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-        ms_g = float(tg.item()) / args.steps
-        gather_info = {"value": total_pairs / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g,
-                       "bytes_into_rank0_per_step": int(sum(counts) * 24 * (world - 1) / world),
-                       "what": "same step, but every per-pair Point3 result is also gathered to rank 0 (NCCL point-to-point, 8 chunks "
-                               "overlapped with compute); bound by rank 0's NVLink ingest, reported for the export use case"}
-
-    # ---- N > 1: export variant with the gather FUSED into the integrate kernels: rank 0's export arrays are mapped into every
-    # process (CUDA IPC) and each rank's kernels store their per-pair results straight into them over NVLink/NVSwitch
-    peer_info = None
-    if world > 1:
-        from integrator2_b200.multigpu import PeerExport
-        gathered = None
-        torch.cuda.empty_cache()
-        exports = [PeerExport(ctx, counts[k], all_bounds[k], rank, world) for k in range(3)]
-        peer_out = [(outs[k][0], exports[k].results_arg()) for k in range(3)]
-
-        def step_peer():
-            if refins is not None:
-                for r in refins:
-                    r.zero_()
-            ctx.integrate_all(tasks, args.level, want_stats=False, refinements=refins, out=peer_out)
-
-        for _ in range(2):
-            step_peer()
-        barrier()
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        p0.record(stream)
-        for _ in range(args.steps):
-            step_peer()
-        p1.record(stream)
-        barrier()
-        tp = torch.tensor([p0.elapsed_time(p1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
-        ms_p = float(tp.item()) / args.steps
-        chk_peer = [float(e.full.abs().sum()) for e in exports] if rank == 0 else None
-        peer_info = {"value": total_pairs / (ms_p * 1e-3), "unit": UNIT, "ms_per_step": ms_p,
-                     "bytes_into_rank0_per_step": int(sum(counts) * 24 * (world - 1) / world),
-                     "checksum_sum_abs_J_on_rank0": chk_peer,
-                     "what": "same step with compute and gather fused: every rank's kernels store their per-pair Point3 results directly into "
-                             "rank 0's export arrays over NVLink peer mappings (i2_peer_alloc / i2_peer_open, multigpu.PeerExport); no NCCL "
-                             "call, no staging copy"}
-        barrier()
-        for e in exports:
-            e.close()
-        barrier()
+    checksum = [float(x) for x in mg.checksums()[:, 3]]     # per-class sum |J|_1 over ALL shards (NCCL all-reduce in the library)
 
     # ---- roofline of the dominant kernel (regular pairs), measured live with CUDA events on the launch stream ----
     roof = None
     if rank == 0:
         ctx.set_profiling(True)
         t_int = []
-        with torch.cuda.stream(stream):
-            for _ in range(3):
-                ctx.integrate_class(2, tasks[2], args.level, want_stats=False, refinements=refin, out=outs[2])
-                if args.level >= 0:
+        if args.level >= 0:
+            with torch.cuda.stream(stream):
+                for _ in range(3):
+                    ctx.host_run_rounds(args.level)     # fixed level: no collective inside, rank 0 can run it alone
                     t_int.append(ctx.profile_last()[0])
         ctx.set_profiling(False)
         dfma_tf, mufu_g = ctx.peak_rates()
         dfma3_tf = ctx.peak_dfma_three_operand()
         if t_int:
             ms_k = sum(t_int) / len(t_int)
+            prof = load_kernel_profile()
             flops = FLOP_PER_REGULAR_PAIR * my_counts[2] * (4 ** max(args.level, 0))
             achieved = flops / (ms_k * 1e-3) / 1e12
-            # dram__bytes_read+write of this kernel from the ncu --set full capture in profiles/r01_ncu_k_regular_grouped_v7_final.txt:
-            # 19.447 GB for 286 403 650 pairs = 67.90 B/pair (algorithmic: 12 B task + 32 B integrals + 24 B result = 68 B)
-            traffic = 67.90 * my_counts[2] if args.level == 0 else None
+            exec_inst = prof.get("fp64_inst_per_pair")
             roof = {"bound": "fp64", "achieved": achieved, "peak": dfma_tf, "unit": "TFLOP/s", "frac": achieved / dfma_tf,
-                    "traffic": traffic, "kernel": "k_regular_grouped (not-neighbours, level 0, fused assembly)", "kernel_ms": ms_k,
+                    "traffic": prof["dram_bytes_per_pair"] * my_counts[2] if (args.level == 0 and prof.get("dram_bytes_per_pair")) else None,
+                    "kernel": "k_regular_grouped (not-neighbours, level 0, fused assembly)", "kernel_ms": ms_k,
                     "algorithmic_flop_per_pair": FLOP_PER_REGULAR_PAIR, "pairs_per_launch": my_counts[2],
                     "peak_source": "measured on this device by i2_peak_rates (DFMA chains); MEASURED_PEAKS.json has no FP64 figure",
                     "mufu_peak_gops": mufu_g,
                     "peak_three_register_operands": dfma3_tf,
-                    "note": "achieved uses the per-point work model of SURVEY.md 8(d) (6.1 kflop/pair); the grouped kernel executes ~1130 FP64 "
-                            "instructions (~1.8 kflop) per pair, i.e. frac > 1 means work removed, not a faster pipe; peak_three_register_operands is the DFMA rate when every "
-                            "instruction reads three distinct registers (the practical ceiling of real code, ~75 % of peak); FP64-pipe active 63 % (84 % of the three-operand ceiling) in "
-                            "profiles/r01_ncu_k_regular_grouped_v7_final.txt",
-                    "executed_fp64_inst_per_pair": 1130,
-                    "fp64_pipe_active_frac": 0.629,
-                    # 55 MUFU (RSQ64H / RCP64H) warp instructions per pair in the same capture; the XU pipe is not a limiter
-                    "executed_mufu_per_pair": 55,
-                    "mufu_frac": (55.0 * my_counts[2] / (ms_k * 1e-3) / 1e9) / mufu_g if (args.level == 0 and mufu_g > 0) else None,
-                    "issue_slots_active_frac": 0.572,
-                    "dispatch_bound_frac": 0.89}
+                    # second statement of the roofline, against what the kernel EXECUTES: FP64 warp instructions per pair from the
+                    # ncu capture named in `counters_from` (same binary: the capture records the library's build id) x 32 lanes
+                    # x 2 flop (an upper bound: DADD/DMUL count as one) over the live kernel time
+                    "executed": None if not exec_inst else {
+                        "fp64_inst_per_pair": exec_inst,
+                        "tflops_if_all_fma": exec_inst * 2.0 * my_counts[2] / (ms_k * 1e-3) / 1e12,
+                        "frac_of_dfma_peak": exec_inst * 2.0 * my_counts[2] / (ms_k * 1e-3) / 1e12 / dfma_tf,
+                        # a warp-wide FP64 instruction occupies a sub-partition's pipe for 2 cycles: 2 warp instructions / clk / SM
+                        "fp64_pipe_issue_frac_live": (exec_inst * my_counts[2] / 32.0) / (148 * 2.0 * clocks_hz(clocks) * ms_k * 1e-3) if clocks_hz(clocks) else None},
+                    "counters": {k: prof.get(k) for k in ("fp64_pipe_active_frac", "issue_slots_active_frac", "mufu_warp_inst_per_pair", "other_warp_inst_per_pair",
+                                                          "achieved_occupancy_frac", "registers", "stall_wait_frac", "stall_math_throttle_frac")},
+                    "counters_from": prof.get("source"),
+                    "note": "achieved uses the per-point work model of SURVEY.md 8(d) (6.1 kflop/pair); the grouped kernel removes 27 logs and 9 atan2 per pair that the "
+                            "model counts, so frac > 1 means work removed, not a faster pipe — `executed` is the utilisation statement; peak_three_register_operands is the DFMA "
+                            "rate when every instruction reads three distinct registers (the practical ceiling of real code)"}
 
-    # ---- end to end through the host-buffer C ABI (N=1): host mesh in -> prepare (H2D, geometry, classification, task
-    # lists) -> three classes -> results.  Two variants, both timed with the host clock around the blocking calls:
-    #   e2e.value            results stay resident in HBM (exactly what Evaluator3D::runAllPairs leaves behind) and the
-    #                        per-class checksums (96 B) are read back as the step's metric;
-    #   e2e.full_d2h         additionally every per-pair result and its (i,j) key is copied to pinned host memory
-    #                        (what outputResultsToFile does before formatting): 36 B/pair, PCIe-bound.
+    # ---- N > 1: export to ONE GPU, two ways, timed separately (the default step is row-striped: no rank ingests more than it
+    # computed).  Both are bound by rank 0's NVLink ingest, measured by `nvlink_ingest` with plain copies.
+    gather_info = peer_info = ingest = None
+    if world > 1:
+        n_all = [c for c in counts]
+        # (a) NCCL send/recv inside the library (i2_mgpu_gather), after the step's kernels
+        gathered = [torch.empty((n, 3), dtype=torch.float64, device=dev) for n in n_all] if rank == 0 else [None] * 3
+
+        def step_gather():
+            mg.run(args.level)
+            for cls in (2, 0, 1):
+                mg.gather(cls, 0, 0, gathered[cls])
+
+        ms_g = timed_steps(step_gather, args.steps, 2)
+        chk_g = [float(g.abs().sum()) for g in gathered] if rank == 0 else None
+        into0 = int(sum(counts) * 24 - sum(my_counts) * 24) if rank == 0 else 0
+        gather_info = {"value": total_pairs / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g, "bytes_into_rank0_per_step": into0,
+                       "checksum_sum_abs_J_on_rank0": chk_g,
+                       "what": "step + i2_mgpu_gather: every result shard sent to rank 0 with ncclSend/ncclRecv by the library"}
+        del gathered
+        torch.cuda.empty_cache()
+        # (b) compute and gather in ONE kernel: rank 0's export arrays are mapped into every process (CUDA IPC) and the
+        # kernels' 16-byte coalesced result stores go straight into them over NVLink (i2_mgpu_set_results_target)
+        from integrator2_b200.multigpu import PeerExport
+        bounds = [[(2 * mg.shard(r)[0][k], 2 * mg.shard(r)[0][k] + mg.shard(r)[1][k]) for r in range(world)] for k in range(3)]
+        exports = [PeerExport(ctx, counts[k], bounds[k], rank, world) for k in range(3)]
+        mg.set_results_target(0, [e.results_arg() for e in exports])
+        ms_p = timed_steps(step, args.steps, 2)
+        chk_peer = [float(e.full.abs().sum()) for e in exports] if rank == 0 else None
+        peer_info = {"value": total_pairs / (ms_p * 1e-3), "unit": UNIT, "ms_per_step": ms_p, "bytes_into_rank0_per_step": into0,
+                     "checksum_sum_abs_J_on_rank0": chk_peer,
+                     "what": "step with compute and gather fused: every rank's kernels store their per-pair Point3 results directly into "
+                             "rank 0's export arrays over NVLink peer mappings (i2_peer_*, i2_mgpu_set_results_target); no NCCL call, no staging copy"}
+        # (c) the ceiling both are measured against: all other ranks copy a buffer of the same size into rank 0 at once
+        nbytes = exports[2].bounds[rank][1] * 24 - exports[2].bounds[rank][0] * 24
+        src = torch.empty((max(nbytes // 8, 1),), dtype=torch.float64, device=dev).normal_()
+        dst = torch.as_tensor(abi._RawCudaBuffer(exports[2].results_arg(), (max(nbytes // 8, 1),), "<f8"), device=dev)
+
+        def copy_in():
+            if rank != 0:
+                dst.copy_(src)
+
+        ms_c = timed_steps(copy_in, 5, 2)
+        moved = counts[2] * 24 - my_counts[2] * 24 if rank == 0 else 0
+        mv = torch.tensor([moved], dtype=torch.float64, device=dev)
+        dist.all_reduce(mv, op=dist.ReduceOp.MAX)
+        ingest = {"gb_per_s": float(mv.item()) / (ms_c * 1e-3) / 1e9, "bytes": int(mv.item()), "ms": ms_c,
+                  "what": f"{world - 1} ranks copy their regular-class result shard (torch copy_ = cudaMemcpy-class kernel) into rank 0's "
+                          "peer-mapped array simultaneously: the NVLink ingest ceiling of one GPU on this box"}
+        if rank == 0:
+            for info in (gather_info, peer_info):
+                info["ingest_gb_per_s"] = info["bytes_into_rank0_per_step"] / (info["ms_per_step"] * 1e-3) / 1e9
+                info["frac_of_copy_ceiling_if_nothing_else_ran"] = (info["bytes_into_rank0_per_step"] / 1e9 / ingest["gb_per_s"]) / (info["ms_per_step"] * 1e-3)
+        barrier()
+        mg.set_results_target(0, None)
+        del dst, src
+        for e in exports:
+            e.close()
+        barrier()
+
+    # ---- end to end through the host-buffer C ABI: host mesh in -> sharded prepare (H2D, geometry, classification by
+    # vertex incidence, this rank's task lists) -> three classes -> checksums over all ranks (NCCL) read back.
+    #   e2e.value     per-pair results stay resident in HBM, row-striped (what Evaluator3D::runAllPairs leaves behind)
+    #   e2e.full_d2h  additionally every rank copies ITS per-pair results and (i,j,k) keys to pinned host memory
     e2e = None
     if not args.no_e2e:
-        del outs, tasks
-        if world == 1:
-            del tasks_full
-        torch.cuda.empty_cache()
-        c2 = abi.Context(local)
-        c2.host_set_shard(rank, world)     # N > 1: every rank prepares the (replicated, 0.4 MB) mesh and integrates its shard
-        cnt_full = c2.host_prepare(mesh.vertices, mesh.cells)
-        cnt = c2.host_shard()[1]
         reps = max(2, min(args.steps, 5))
 
         def timed(fn):
@@ -433,33 +407,38 @@ def main():
         sums = []
 
         def resident():
-            c2.host_prepare(mesh.vertices, mesh.cells)
-            c2.host_run(args.level, None, None)
-            sums.append(c2.host_checksums())
+            mg.prepare(mesh.vertices, mesh.cells, args.level)
+            mg.run(args.level)
+            sums.append(mg.checksums())
 
         dt_res = timed(resident)
-        if world > 1:      # per-class checksums of the shards -> whole-job checksums (validation, outside the timed region)
-            st = torch.as_tensor(sums[-1], device=dev)
-            dist.all_reduce(st)
-            sums.append(st.cpu().numpy())
-        ht = [torch.empty((n, 3), dtype=torch.int32, pin_memory=True) for n in cnt]
-        hr = [torch.empty((n, 3), dtype=torch.float64, pin_memory=True) for n in cnt]
+        ht = [torch.empty((n, 3), dtype=torch.int32, pin_memory=True) for n in my_counts]
+        hr = [torch.empty((n, 3), dtype=torch.float64, pin_memory=True) for n in my_counts]
 
         def full():
-            c2.host_prepare(mesh.vertices, mesh.cells)
-            c2.host_run(args.level, ht, hr)
+            mg.prepare(mesh.vertices, mesh.cells, args.level)
+            ctx.host_run(args.level, ht, hr)        # fixed level: finished chunks travel while the next ones compute
 
-        dt_full = timed(full)
-        d2h = int(sum(cnt_full) * (24 + 12))
-        e2e = {"value": sum(cnt_full) / dt_res, "unit": UNIT, "h2d_bytes_per_step": int(mesh.vertices.nbytes + mesh.cells.nbytes) * world,
+        dt_full = timed(full) if args.level >= 0 else None
+        d2h = int(sum(counts) * (24 + 12))
+        e2e = {"value": sum(counts) / dt_res, "unit": UNIT, "h2d_bytes_per_step": int(mesh.vertices.nbytes + mesh.cells.nbytes) * world,
                "d2h_bytes_per_step": 96 * world, "ms_per_step": dt_res * 1e3,
-               "what": "i2_host_prepare (H2D mesh, geometry, classification, ordered task lists) + i2_host_run (3 classes) with the per-pair "
-                       "results left in HBM like Evaluator3D::runAllPairs does, + D2H of the per-class checksums",
+               "what": "i2_mgpu_prepare (H2D mesh, geometry, classification by vertex incidence, this rank's shard of the ordered task lists) + "
+                       "i2_mgpu_run (3 classes) with the per-pair results left in HBM like Evaluator3D::runAllPairs does, + i2_mgpu_checksums "
+                       "(per-class checksums over all ranks, NCCL all-reduce, D2H)",
                "checksum_sum_abs_J": [float(x) for x in sums[-1][:, 3]],
-               "full_d2h": {"value": sum(cnt_full) / dt_full, "unit": UNIT, "ms_per_step": dt_full * 1e3, "d2h_bytes_per_step": d2h,
-                            "d2h_gb_per_s": d2h / dt_full / 1e9,
-                            "what": "same, plus every per-pair result (24 B) and (i,j,k) key (12 B) copied to pinned host memory, chunks overlapped with compute"}}
-        c2.close()
+               "full_d2h": None if dt_full is None else {
+                   "value": sum(counts) / dt_full, "unit": UNIT, "ms_per_step": dt_full * 1e3, "d2h_bytes_per_step": d2h,
+                   "d2h_gb_per_s": d2h / dt_full / 1e9,
+                   "what": "same, plus every per-pair result (24 B) and (i,j,k) key (12 B) copied to pinned host memory by the rank that owns it "
+                           "(row-striped export), chunks overlapped with compute"}}
+
+    # ---- the largest mesh of BASELINE.json (configs[3]: s5m2 refined twice, 125 280 triangles, 1.57e10 ordered pairs, automatic
+    # error control), all three classes, through the same multi-GPU entry points (i2_mgpu_apply_*): row blocks cut by predicted
+    # cost, regular class list-free, one NCCL all-reduce of the result vector per application
+    largest = None
+    if not args.no_largest and args.workload == "lists":
+        largest = run_largest_mesh(mg, rank, world, dev, stream, timed_steps)
 
     cpu = None
     if rank == 0 and not args.no_cpu:
@@ -475,13 +454,68 @@ def main():
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": f"reference example mesh (tests/golden/meshes.npz, parsed from {args.mesh}.dat); no random data",
                 "config": {"workload": workload_name(args.mesh, args.scale, args.level, counts),
-                           "triangles": mesh.n_cells, "quadrature": "Cowper 13-point (order 7)", "sharding": f"{world} contiguous equal-cost shards per class, results resident per rank (no data-path collective)",
+                           "triangles": mesh.n_cells, "quadrature": "Cowper 13-point (order 7)",
+                           "sharding": f"{world} shards per class through i2_mgpu_* (pairs with forward slots [lo, hi), multiples of 32, in both orders; "
+                                       "results row-striped per rank; error control: NCCL all-reduce of last rounds and refinement counters in the step)",
                            "l2": "inputs+outputs per step (task lists 12 B/pair, results 56 B/pair) are far larger than L2; no flush needed"},
                 "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
-                "with_gather_to_rank0": gather_info, "with_peer_store_to_rank0": peer_info, "checksum_sum_abs_J": checksum}
+                "with_gather_to_rank0": gather_info, "with_peer_store_to_rank0": peer_info, "nvlink_ingest": ingest,
+                "largest_mesh": largest, "checksum_sum_abs_J": checksum}
         print(json.dumps(line), flush=True)
+    mg.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def clocks_hz(clocks):
+    try:
+        return float(clocks["sm_mhz"]) * 1e6
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def load_kernel_profile():
+    """Counters of the regular-pair kernel from the newest committed ncu summary (profiles/r02_ncu_k_regular_grouped*.json, written
+    by tools/ncu_summary.py from an `ncu --set full` capture of the binary in the tree) — read, never hard-coded."""
+    import glob
+    best = {}
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r02_ncu_k_regular_grouped*.json"))):
+        try:
+            d = json.load(open(path))
+            d["source"] = os.path.relpath(path, ROOT)
+            best = d
+        except Exception:  # noqa: BLE001
+            continue
+    return best
+
+
+def run_largest_mesh(mg, rank, world, dev, stream, timed_steps):
+    import numpy as np
+    import torch
+    from integrator2_b200.meshio import load_fixture, subdivide
+    mesh = subdivide(load_fixture("s5m2", 0.0005), 2)
+    n = mesh.n_cells
+    va, ea, reg = class_pair_counts(mesh)
+    cuts = mg.apply_prepare(mesh.vertices, mesh.cells, -1)
+    state = {}
+
+    def step():
+        state["stats"] = None
+        mg.apply(-1, want_out=False)
+
+    ms = timed_steps(step, 1, 1)
+    out, stats = mg.apply(-1, want_out=True, want_stats=True)        # untimed: the result vector and the counts, for the record
+    if rank != 0:
+        return None
+    return {"workload": f"s5m2.dat scale 0.0005 refined 2x by midpoint subdivision: {n} triangles, {va} vertex-adjacent + {ea} edge-adjacent + {reg} "
+                        f"regular = {va + ea + reg} ordered pairs, automatic error control (Runge rule, <= 5 rounds), row sums sum_j J(K_i,K_j) over "
+                        "ALL classes (BASELINE.json configs[3] at full size; the reference cannot enumerate N > 46 340)",
+            "value": (va + ea + reg) / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": 1, "warmup": 1, "n_gpus": world,
+            "row_cuts": cuts, "sharding": "row blocks cut by predicted adaptive cost (k_row_cost), multiples of 32 rows; "
+                                          "one NCCL all-reduce of Point3[n] leaves the full vector on every GPU",
+            "rounds": {c: {"last_round": stats[k]["last_round"], "integrated": stats[k]["integrated"], "unconverged": stats[k]["unconverged"]}
+                       for k, c in enumerate(("vertex_adjacent", "edge_adjacent", "regular"))},
+            "checksum_sum_abs": float(np.abs(out).sum()), "checksum_sum": [float(x) for x in out.sum(0)]}
 
 
 def class_pair_counts(mesh):

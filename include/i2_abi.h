@@ -32,6 +32,7 @@ typedef struct i2_context i2_context;
 #define I2_E_NOQUAD (-3)     /* i2_set_quadrature was not called                                      */
 #define I2_E_LEVEL (-4)      /* fixed refinement level outside 0..12                                  */
 #define I2_E_TOOBIG (-5)     /* a count does not fit the 32-bit slots of the reference's int3 tasks   */
+#define I2_E_NCCL (-6)       /* multi-GPU layer: libnccl.so.2 could not be loaded or an NCCL call failed */
 
 #define I2_CLASS_SIMPLE 0
 #define I2_CLASS_ATTACHED 1
@@ -106,6 +107,15 @@ int i2_integrate_class(i2_context *ctx, int cls, const int *d_tasks, long long n
                        double *d_integrals, double *d_results, unsigned char *d_refinements,
                        unsigned char *d_converged, i2_stats *h_stats);
 
+/* The same for the ordered list Evaluator3D::runAllPairs builds (src/evaluators/evaluator3d.cu:156-169): d_tasks = n_half pairs
+ * (i, j) followed by their n_half reversed pairs (j, i), 2 n_half tasks in all.  The regular-pair kernel takes a few far-field
+ * decisions per warp of 32 consecutive tasks; here the warps of the reversed half start at its first task, so a result depends
+ * only on the task's position inside its half: a GPU that integrates the pairs [lo, hi) and their reversed pairs, lo and hi
+ * multiples of 32 (i2_host_set_shard / i2_mgpu_*), produces the very bits of the unsharded call.                              */
+int i2_integrate_pairs(i2_context *ctx, int cls, const int *d_tasks, long long n_half, int level,
+                       double *d_integrals, double *d_results, unsigned char *d_refinements,
+                       unsigned char *d_converged, i2_stats *h_stats);
+
 /* The three classes of Evaluator3D::runAllPairs (src/evaluators/evaluator3d.cu:120-204 calls the three virtuals one
  * after the other) in ONE call: arrays indexed by I2_CLASS_*; same arguments and results as three i2_integrate_class
  * calls, but the two adjacent classes (short, latency-bound chains of kernels) are enqueued on internal side streams and
@@ -137,6 +147,24 @@ int i2_apply_regular(i2_context *ctx, int row_lo, int row_hi, const double *d_we
 int i2_apply_regular_adaptive(i2_context *ctx, int row_lo, int row_hi, const double *d_weights, double *d_out,
                               double *d_out_other, unsigned char *d_refinements, i2_stats *h_stats);
 
+/* ---- the whole operator for a block of rows, all neighbour classes: d_out[i - row_lo] = sum over j != i of w_j J(K_i, K_j) ----
+ * The regular class runs list-free (i2_apply_regular at level 0, i2_apply_regular_adaptive under error control); the vertex- and
+ * edge-adjacent partners of the rows come from the vertex incidence as row-major task lists (all partners j of row i, sorted by
+ * (i, j)), are integrated by the same kernels as i2_integrate_class — regular part by quadrature, closed-form singular part
+ * (src/evaluators/evaluatorJ3DK.cu:849-881) — and added to the row sums in list order (deterministic).  This is the entry point
+ * for meshes beyond the reference's N^2-list limit (BASELINE.json configs[3], [4]) and shards by rows: no cross-GPU sums.
+ *   i2_apply_prepare   rows [row_lo, row_hi) of the mesh given to i2_set_mesh (or uploaded by i2_host_prepare / i2_mgpu_*)
+ *   i2_apply           level = 0 or I2_LEVEL_ADAPTIVE; d_weights double[nc] or NULL; d_out Point3[rows];
+ *                      d_refinements unsigned char[3][rows] or NULL (error control: the per-cell counters of the three classes
+ *                      for the block's rows); h_stats[3] or NULL (synchronises)
+ *   i2_apply_rounds / i2_apply_last_rounds / i2_apply_finish   the same in two halves for multi-GPU callers: under error control
+ *                      the GPUs agree on each class's last round (maximum; h_last = {simple, attached, regular}) in between */
+int i2_apply_prepare(i2_context *ctx, int row_lo, int row_hi);
+int i2_apply(i2_context *ctx, int level, const double *d_weights, double *d_out, unsigned char *d_refinements, i2_stats h_stats[3]);
+int i2_apply_rounds(i2_context *ctx, int level, const double *d_weights);
+int i2_apply_last_rounds(i2_context *ctx, int h_last[3], int set);
+int i2_apply_finish(i2_context *ctx, int level, const double *d_weights, double *d_out, unsigned char *d_refinements, i2_stats h_stats[3]);
+
 /* delta = |J_ij + J_ji|_1 / max(|J_ij|_1, |J_ji|_1) for slots t and n_half+t: replaces
  * kCalculateIntegrationError (src/evaluators/evaluator3d.cu:45-57)                                         */
 int i2_symmetry_error(i2_context *ctx, const double *d_results, long long n_half, double *d_errors);
@@ -146,7 +174,9 @@ int i2_symmetry_error(i2_context *ctx, const double *d_results, long long n_half
  * ordered task lists exactly like Evaluator3D::runAllPairs (src/evaluators/evaluator3d.cu:120-169);
  * h_task_counts[c] = 2 * pairs of class c.  i2_host_run integrates all three classes and copies tasks,
  * results (and deltas when h_errors[c] != NULL) back; copies of finished chunks overlap the computation
- * of the next ones when the host buffers are pinned.  Any h_tasks[c]/h_results[c] may be NULL (skipped).   */
+ * of the next ones when the host buffers are pinned.  Any h_tasks[c]/h_results[c] may be NULL (skipped).
+ * The classification is by vertex incidence (partners of a triangle = the triangles listed under its three vertices), the
+ * regular list is implicit in per-row prefix sums and is written together with its reversed pairs by one kernel.         */
 int i2_host_prepare(i2_context *ctx, const double *h_vertices, int nv, const int *h_cells, int nc,
                     long long h_task_counts[3]);
 int i2_host_run(i2_context *ctx, int level, int *const h_tasks[3], double *const h_results[3],
@@ -154,22 +184,90 @@ int i2_host_run(i2_context *ctx, int level, int *const h_tasks[3], double *const
 /* per class (sum J_x, sum J_y, sum J_z, sum |J|_1) of the results left in device memory by i2_host_run: the small
  * 'metric' a caller reads back when the per-pair results stay resident (what Evaluator3D::runAllPairs leaves behind) */
 int i2_host_checksums(i2_context *ctx, double h_sums[12]);
-/* multi-GPU use of the host-buffer path (one process and one context per GPU): rank r of w integrates, per class, the
- * contiguous equal-count shard r of the ordered task list.  Call i2_host_set_shard before i2_host_prepare (default: 0 of
- * 1 = everything); i2_host_prepare still returns the FULL counts, i2_host_shard the shard's first slot and length per
- * class; the host buffers given to i2_host_run are then shard-sized and i2_host_checksums covers the shard only.
- * h_errors needs the whole lists (slot t pairs with slot n/2 + t) and is refused (I2_E_BADARG) when w > 1.             */
+/* multi-GPU use of the host-buffer path (one context per GPU; i2_mgpu_* below drives it): rank r of w owns, per class, the
+ * pairs whose forward slots lie in [lo_r, hi_r) — equal counts, lo and hi multiples of 32 — in BOTH orders, and its task list is
+ * [those pairs ; their reversed pairs]: the shape of a small runAllPairs list, so the (i,j)/(j,i) defect is local and, because
+ * warp groups are formed per half from multiples of 32, every result has the same bits as in the unsharded run.  Call
+ * i2_host_set_shard before i2_host_prepare (default: 0 of 1 = everything); i2_host_prepare still returns the FULL counts but
+ * materialises only the shard (classification by vertex incidence: no O(N^2) pass, the regular list is filled for the shard's
+ * slot range alone); i2_host_shard returns lo_r and the shard's task count 2 (hi_r - lo_r) per class; the host buffers given to
+ * i2_host_run are shard-sized and i2_host_checksums covers the shard.                                                    */
 int i2_host_set_shard(i2_context *ctx, int rank, int world);
 int i2_host_shard(i2_context *ctx, long long h_first[3], long long h_count[3]);
+/* predicted cost of every row's regular pairs under error control (level-0 pair integrations: 5 + 66.7 P(rho), rho = centroid
+ * distance / sqrt(larger area)), upper_only: pairs j > i counted twice; and the first regular forward slot of every row
+ * (nc + 1 values).  Either output may be NULL.  Used to place cost-balanced shard cuts (i2_mgpu_prepare, level < 0).      */
+int i2_host_row_costs(i2_context *ctx, int upper_only, double *h_cost, unsigned long long *h_row_first_regular);
+/* The two halves of i2_host_run for callers that shard over several contexts with their OWN communicator (MPI, gloo, ...):
+ * i2_host_run_rounds enqueues the integration rounds of the shard; under error control the shards must then agree on each class's
+ * last round (maximum; i2_host_last_rounds gets / sets the three device-side values) and on the per-cell refinement counters
+ * (element-wise maximum; i2_host_refinements gets / sets unsigned char[3][nc]); i2_host_run_finalize adds the closed-form
+ * singular parts, assembles J and, with check != 0, computes the (i,j)/(j,i) defects; i2_host_fetch copies a class of the shard
+ * (tasks, results, defects; any may be NULL) to the host.  i2_mgpu_run is exactly this sequence with NCCL in the middle.     */
+int i2_host_run_rounds(i2_context *ctx, int level);
+int i2_host_last_rounds(i2_context *ctx, int h_last[3], int set);
+int i2_host_refinements(i2_context *ctx, unsigned char *h_refinements, int set);
+int i2_host_run_finalize(i2_context *ctx, int level, int check);
+int i2_host_fetch(i2_context *ctx, int cls, int *h_tasks, double *h_results, double *h_errors);
 /* device views of what i2_host_prepare built (valid until the next prepare/destroy)                        */
 int i2_host_device_views(i2_context *ctx, const int *d_tasks[3], const double *d_results[3]);
 
-/* ---- multi-GPU export: per-pair results written straight into the exporting GPU's memory over NVLink ---------------
- * (no reference counterpart: /root/reference is single-GPU).  One process per GPU.  The exporting rank
+/* ---- multi-GPU: the pair lists of Evaluator3D::runAllPairs (src/evaluators/evaluator3d.cu:120-204) sharded over the GPUs of
+ * one box (no reference counterpart: /root/reference is single-GPU; SURVEY.md §8(b),(e)).  One handle drives the GPUs of this
+ * process: all of them from one process (i2_mgpu_create_local: CLI / host classes, env I2_GPUS) or one per process
+ * (i2_mgpu_create_rank; rank 0 calls i2_mgpu_unique_id and ships the 128 bytes to the others by any means).  NCCL is loaded
+ * with dlopen("libnccl.so.2") on first use; world = 1 needs no NCCL.
+ *   i2_mgpu_prepare   host mesh in; every GPU uploads it, classifies by vertex incidence and builds ITS shard of the three
+ *                     ordered lists (see i2_host_set_shard); level < 0 places the cuts of the regular class by predicted
+ *                     adaptive cost.  h_task_counts = ordered tasks of the whole mesh.
+ *   i2_mgpu_run       one pass of the hot path over every shard (level >= 0 or I2_LEVEL_ADAPTIVE; check != 0 also computes the
+ *                     (i,j)/(j,i) defects).  Error control: NCCL all-reduce(max) of each class's last round before the final
+ *                     assembly (the value of a converged pair depends on the parity of the GLOBAL last round) and
+ *                     of the per-cell refinement counters.  Asynchronous unless h_stats (per-round counts summed over all
+ *                     shards) is given.
+ *   i2_mgpu_checksums per class (sum J_x, J_y, J_z, sum |J|_1) over ALL shards (all-reduce), the step's small metric
+ *   i2_mgpu_shard     forward-slot range of any rank: first slot and task count 2 (hi - lo) per class
+ *   i2_mgpu_fetch     row-striped export: one local GPU's shard (tasks, results, defects; shard order) to host arrays
+ *   i2_mgpu_gather    export to one GPU: result (what = 0) or task (what = 1) shards of a class concatenated in rank order into
+ *                     d_dst on GPU `root` (ncclSend / ncclRecv); enqueued on the contexts' streams
+ *   i2_mgpu_set_results_target  make local GPU k write class c's results to d_results[c] instead of its own buffer, e.g. into a
+ *                     peer-mapped slice of the exporting GPU's array (i2_peer_*): compute and gather in one kernel           */
+typedef struct i2_mgpu i2_mgpu;
+#define I2_MGPU_ID_BYTES 128
+int i2_mgpu_unique_id(unsigned char h_id[I2_MGPU_ID_BYTES]);
+int i2_mgpu_create_rank(i2_mgpu **mg, int device, int rank, int world, const unsigned char h_id[I2_MGPU_ID_BYTES]);
+int i2_mgpu_create_local(i2_mgpu **mg, int ngpus, const int *devices /* NULL: 0 .. ngpus-1 */);
+int i2_mgpu_destroy(i2_mgpu *mg);
+int i2_mgpu_info(i2_mgpu *mg, int *world, int *n_local, int *first_rank);
+i2_context *i2_mgpu_context(i2_mgpu *mg, int local_index);
+int i2_mgpu_set_quadrature(i2_mgpu *mg, const double *h_xy, const double *h_w, int n, int order);
+int i2_mgpu_set_math_mode(i2_mgpu *mg, int mode);
+int i2_mgpu_synchronize(i2_mgpu *mg);
+int i2_mgpu_prepare(i2_mgpu *mg, const double *h_vertices, int nv, const int *h_cells, int nc, int level, long long h_task_counts[3]);
+int i2_mgpu_shard(i2_mgpu *mg, int rank, long long h_first[3], long long h_count[3]);
+int i2_mgpu_set_results_target(i2_mgpu *mg, int local_index, double *const d_results[3]);
+int i2_mgpu_run(i2_mgpu *mg, int level, int check, i2_stats h_stats[3]);
+int i2_mgpu_checksums(i2_mgpu *mg, double h_sums[12]);
+int i2_mgpu_gather(i2_mgpu *mg, int cls, int what, int root, void *d_dst);
+int i2_mgpu_fetch(i2_mgpu *mg, int local_index, int cls, int *h_tasks, double *h_results, double *h_errors);
+int i2_mgpu_refinements(i2_mgpu *mg, int cls, unsigned char *h_refinements);
+/* the whole operator (i2_apply_*) by row blocks over the GPUs: BASELINE.json configs[3] / [4], meshes beyond the N^2-list limit.
+ * i2_mgpu_apply_prepare uploads the mesh and cuts the rows — by predicted cost under error control (level < 0), equally
+ * otherwise; h_row_cuts (int[world + 1]) may be NULL.  i2_mgpu_apply: every GPU computes its rows (regular class list-free,
+ * adjacent classes from row-major lists; under error control one all-reduce(max) of the three last rounds in between), then ONE
+ * NCCL all-reduce of Point3[nc] leaves the full vector on every GPU.  h_weights double[nc] or NULL, h_out Point3[nc] or NULL,
+ * h_stats[3] or NULL (counts summed over the GPUs); asynchronous when both h_out and h_stats are NULL.                      */
+int i2_mgpu_apply_prepare(i2_mgpu *mg, const double *h_vertices, int nv, const int *h_cells, int nc, int level, int *h_row_cuts);
+int i2_mgpu_apply(i2_mgpu *mg, int level, const double *h_weights, double *h_out, i2_stats h_stats[3]);
+int i2_mgpu_apply_result(i2_mgpu *mg, int local_index, double **d_full, unsigned char **d_refinements);
+
+/* ---- multi-GPU export by peer stores: per-pair results written straight into the exporting GPU's memory over NVLink --
+ * One process per GPU.  The exporting rank
  * allocates the full result array with i2_peer_alloc (cudaMalloc + CUDA IPC handle, 64 opaque bytes the host side ships
  * to the other processes by any means, e.g. torch.distributed.broadcast_object_list); every other rank maps it with
- * i2_peer_open and passes `mapped + 24 * first_slot_of_its_shard` as d_results of i2_integrate_class / i2_integrate_all:
- * the final-assembly stores of the kernels then ARE the gather (coalesced 768-byte warp stores through NVSwitch, no
+ * i2_peer_open and passes `mapped + 24 * first_task_of_its_shard` as d_results of i2_integrate_class / i2_integrate_all or to
+ * i2_mgpu_set_results_target:
+ * the final-assembly stores of the kernels then ARE the gather (16-byte coalesced warp stores through NVSwitch, no
  * staging copy, no second pass), overlapped with the arithmetic of the other warps.  The data are visible to the owner
  * once the writer's stream has been synchronised (i2_synchronize) and the processes have met at a host barrier.
  * i2_peer_close unmaps (writer side), i2_peer_free releases (owner side).                                           */

@@ -47,8 +47,12 @@ class Stats(C.Structure):
 EXPORTS = [
     "i2_create", "i2_destroy", "i2_set_stream", "i2_synchronize", "i2_set_math_mode", "i2_error_string",
     "i2_set_quadrature", "i2_mesh_geometry", "i2_set_mesh", "i2_classify_count", "i2_classify_fill",
-    "i2_add_reversed_pairs", "i2_integrate_class", "i2_integrate_all", "i2_symmetry_error", "i2_host_prepare", "i2_host_run",
+    "i2_add_reversed_pairs", "i2_integrate_class", "i2_integrate_pairs", "i2_integrate_all", "i2_symmetry_error", "i2_host_prepare", "i2_host_run",
     "i2_host_device_views", "i2_host_checksums", "i2_peer_alloc", "i2_peer_open", "i2_peer_close", "i2_peer_free", "i2_host_set_shard", "i2_host_shard", "i2_peak_rates", "i2_peak_dfma_three_operand", "i2_refine_mesh_once", "i2_launch_count", "i2_set_profiling", "i2_profile_last", "i2_selftest_math", "i2_apply_regular", "i2_apply_regular_adaptive",
+    "i2_host_row_costs", "i2_host_run_rounds", "i2_host_last_rounds", "i2_host_refinements", "i2_host_run_finalize", "i2_host_fetch", "i2_mgpu_unique_id", "i2_mgpu_create_rank", "i2_mgpu_create_local", "i2_mgpu_destroy", "i2_mgpu_info", "i2_mgpu_context",
+    "i2_mgpu_set_quadrature", "i2_mgpu_set_math_mode", "i2_mgpu_synchronize", "i2_mgpu_prepare", "i2_mgpu_shard", "i2_mgpu_set_results_target",
+    "i2_mgpu_run", "i2_mgpu_checksums", "i2_mgpu_gather", "i2_mgpu_fetch", "i2_mgpu_refinements",
+    "i2_mgpu_apply_prepare", "i2_mgpu_apply", "i2_mgpu_apply_result", "i2_apply_prepare", "i2_apply", "i2_apply_rounds", "i2_apply_last_rounds", "i2_apply_finish",
 ]
 
 _lib = None
@@ -82,6 +86,7 @@ def load_library():
     L.i2_classify_fill.argtypes = [vp, vp, i32, vp, vp, vp]
     L.i2_add_reversed_pairs.argtypes = [vp, vp, ll]
     L.i2_integrate_class.argtypes = [vp, i32, vp, ll, i32, vp, vp, vp, vp, C.POINTER(Stats)]
+    L.i2_integrate_pairs.argtypes = [vp, i32, vp, ll, i32, vp, vp, vp, vp, C.POINTER(Stats)]
     L.i2_integrate_all.argtypes = [vp, C.POINTER(vp), C.POINTER(ll), i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(Stats)]
     L.i2_symmetry_error.argtypes = [vp, vp, ll, vp]
     L.i2_host_prepare.argtypes = [vp, vp, i32, vp, i32, C.POINTER(ll)]
@@ -103,8 +108,40 @@ def load_library():
     L.i2_peer_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     L.i2_peer_close.argtypes = [vp, vp]
     L.i2_peer_free.argtypes = [vp, vp]
+    L.i2_host_row_costs.argtypes = [vp, i32, vp, vp]
+    L.i2_host_run_rounds.argtypes = [vp, i32]
+    L.i2_host_last_rounds.argtypes = [vp, C.POINTER(i32), i32]
+    L.i2_host_refinements.argtypes = [vp, vp, i32]
+    L.i2_host_run_finalize.argtypes = [vp, i32, i32]
+    L.i2_host_fetch.argtypes = [vp, i32, vp, vp, vp]
+    L.i2_mgpu_unique_id.argtypes = [C.c_char_p]
+    L.i2_mgpu_create_rank.argtypes = [C.POINTER(vp), i32, i32, i32, C.c_char_p]
+    L.i2_mgpu_create_local.argtypes = [C.POINTER(vp), i32, C.POINTER(i32)]
+    L.i2_mgpu_destroy.argtypes = [vp]
+    L.i2_mgpu_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.i2_mgpu_context.argtypes = [vp, i32]
+    L.i2_mgpu_context.restype = vp
+    L.i2_mgpu_set_quadrature.argtypes = [vp, vp, vp, i32, i32]
+    L.i2_mgpu_set_math_mode.argtypes = [vp, i32]
+    L.i2_mgpu_synchronize.argtypes = [vp]
+    L.i2_mgpu_prepare.argtypes = [vp, vp, i32, vp, i32, i32, C.POINTER(ll)]
+    L.i2_mgpu_shard.argtypes = [vp, i32, C.POINTER(ll), C.POINTER(ll)]
+    L.i2_mgpu_set_results_target.argtypes = [vp, i32, C.POINTER(vp)]
+    L.i2_mgpu_run.argtypes = [vp, i32, i32, C.POINTER(Stats)]
+    L.i2_mgpu_checksums.argtypes = [vp, C.POINTER(C.c_double)]
+    L.i2_mgpu_gather.argtypes = [vp, i32, i32, i32, vp]
+    L.i2_mgpu_fetch.argtypes = [vp, i32, i32, vp, vp, vp]
+    L.i2_mgpu_refinements.argtypes = [vp, i32, vp]
+    L.i2_mgpu_apply_prepare.argtypes = [vp, vp, i32, vp, i32, i32, C.POINTER(i32)]
+    L.i2_mgpu_apply.argtypes = [vp, i32, vp, vp, C.POINTER(Stats)]
+    L.i2_mgpu_apply_result.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp)]
+    L.i2_apply_prepare.argtypes = [vp, i32, i32]
+    L.i2_apply.argtypes = [vp, i32, vp, vp, vp, C.POINTER(Stats)]
+    L.i2_apply_rounds.argtypes = [vp, i32, vp]
+    L.i2_apply_last_rounds.argtypes = [vp, C.POINTER(i32), i32]
+    L.i2_apply_finish.argtypes = [vp, i32, vp, vp, vp, C.POINTER(Stats)]
     for name in EXPORTS:
-        if name != "i2_error_string":
+        if name not in ("i2_error_string", "i2_mgpu_context"):
             getattr(L, name).restype = i32
     _lib = L
     return L
@@ -141,13 +178,17 @@ class Context:
     """One integrator context on one CUDA device (mirrors the lifetime of the reference's
     Mesh3D + NumericalIntegrator3D + EvaluatorJ3DK trio)."""
 
-    def __init__(self, device: int = 0, math_mode: int = MATH_FAST):
+    def __init__(self, device: int = 0, math_mode: int = MATH_FAST, borrowed=None):
         import torch
         self.torch = torch
         self.L = load_library()
         self.device = device
-        h = C.c_void_p()
-        _check(self.L.i2_create(C.byref(h), device))
+        self.owned = borrowed is None
+        if borrowed is None:
+            h = C.c_void_p()
+            _check(self.L.i2_create(C.byref(h), device))
+        else:
+            h = C.c_void_p(borrowed)        # a context owned by a MultiGpu handle
         self.h = h
         _check(self.L.i2_set_math_mode(self.h, math_mode))
         # run on torch's current stream: tensors handed to the library are produced/consumed by torch ops on that
@@ -161,7 +202,8 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
-            self.L.i2_destroy(self.h)
+            if self.owned:
+                self.L.i2_destroy(self.h)
             self.h = None
 
     def __del__(self):
@@ -220,7 +262,11 @@ class Context:
         _check(self.L.i2_add_reversed_pairs(self.h, _ptr(t), n))
         return t
 
-    def integrate_class(self, cls, tasks, level=0, want_stats=True, refinements=None, out=None):
+    def integrate_pairs(self, cls, tasks, level=0, want_stats=True, refinements=None, out=None):
+        """like integrate_class for a runAllPairs-shaped list [n/2 pairs ; n/2 reversed pairs] (i2_integrate_pairs)"""
+        return self.integrate_class(cls, tasks, level, want_stats, refinements, out, pairs=True)
+
+    def integrate_class(self, cls, tasks, level=0, want_stats=True, refinements=None, out=None, pairs=False):
         """tasks: int32[n,3] device tensor. -> dict(integrals[n,4], results[n,3], refinements, converged, stats)"""
         torch = self.torch
         n = tasks.shape[0]
@@ -236,9 +282,9 @@ class Context:
                 refinements = torch.zeros((self.nc,), dtype=torch.uint8, device=dev)
             conv = torch.zeros((n,), dtype=torch.uint8, device=dev)
         st = Stats()
-        _check(self.L.i2_integrate_class(self.h, cls, _ptr(tasks), n, level, _ptr(integrals), _ptr(results),
-                                         _ptr(refinements) if level < 0 else C.c_void_p(0), _ptr(conv),
-                                         C.byref(st) if want_stats else None))
+        fn, count = (self.L.i2_integrate_pairs, n // 2) if pairs else (self.L.i2_integrate_class, n)
+        _check(fn(self.h, cls, _ptr(tasks), count, level, _ptr(integrals), _ptr(results),
+                  _ptr(refinements) if level < 0 else C.c_void_p(0), _ptr(conv), C.byref(st) if want_stats else None))
         return dict(integrals=integrals, results=results, refinements=refinements, converged=conv,
                     stats=st.as_dict() if want_stats else None)
 
@@ -289,6 +335,30 @@ class Context:
         _check(self.L.i2_apply_regular_adaptive(self.h, int(row_lo), int(row_hi), _ptr(weights), _ptr(out), _ptr(other), _ptr(ref),
                                                 C.byref(st) if want_stats else None))
         return dict(out=out, other=other, refinements=ref, stats=st.as_dict() if want_stats else None)
+
+    def apply_prepare(self, row_lo, row_hi):
+        _check(self.L.i2_apply_prepare(self.h, int(row_lo), int(row_hi)))
+        self._apply_rows = (int(row_lo), int(row_hi))
+
+    def apply(self, level, weights=None, want_stats=True, split=None):
+        """The whole operator for the prepared row block: out[i] = sum_j w_j J(K_i,K_j) over all classes (i2_apply).
+        split: callable(last_rounds) -> last_rounds, run between the two halves (what a multi-GPU caller all-reduces)."""
+        torch = self.torch
+        lo, hi = self._apply_rows
+        dev = f"cuda:{self.device}"
+        out = torch.empty((hi - lo, 3), dtype=torch.float64, device=dev)
+        ref = torch.zeros((3, hi - lo), dtype=torch.uint8, device=dev)
+        st = (Stats * 3)()
+        if split is None:
+            _check(self.L.i2_apply(self.h, int(level), _ptr(weights), _ptr(out), _ptr(ref), st if want_stats else None))
+        else:
+            _check(self.L.i2_apply_rounds(self.h, int(level), _ptr(weights)))
+            a = (C.c_int * 3)()
+            _check(self.L.i2_apply_last_rounds(self.h, a, 0))
+            new = split([int(x) for x in a])
+            _check(self.L.i2_apply_last_rounds(self.h, (C.c_int * 3)(*new), 1))
+            _check(self.L.i2_apply_finish(self.h, int(level), _ptr(weights), _ptr(out), _ptr(ref), st if want_stats else None))
+        return dict(out=out, refinements=ref, stats=[x.as_dict() for x in st] if want_stats else None)
 
     def symmetry_error(self, results):
         torch = self.torch
@@ -376,6 +446,38 @@ class Context:
         _check(self.L.i2_host_run(self.h, level, arr(h_tasks), arr(h_results), arr(h_errors), arr(h_refinements), st))
         return [s.as_dict() for s in st]
 
+    def host_run_rounds(self, level):
+        _check(self.L.i2_host_run_rounds(self.h, int(level)))
+
+    def host_last_rounds(self, set_to=None):
+        a = (C.c_int * 3)(*(set_to if set_to is not None else (0, 0, 0)))
+        _check(self.L.i2_host_last_rounds(self.h, a, 1 if set_to is not None else 0))
+        return [int(x) for x in a]
+
+    def host_refinements(self, set_to=None):
+        r = np.ascontiguousarray(set_to, dtype=np.uint8) if set_to is not None else np.empty((3, self.nc), dtype=np.uint8)
+        _check(self.L.i2_host_refinements(self.h, r.ctypes.data, 1 if set_to is not None else 0))
+        return r
+
+    def host_run_finalize(self, level, check=False):
+        _check(self.L.i2_host_run_finalize(self.h, int(level), 1 if check else 0))
+
+    def host_fetch(self, cls, tasks=True, results=True, errors=False):
+        n = self.host_shard()[1][cls]
+        t = np.empty((n, 3), dtype=np.int32) if tasks else None
+        r = np.empty((n, 3), dtype=np.float64) if results else None
+        e = np.empty((n,), dtype=np.float64) if errors else None
+        _check(self.L.i2_host_fetch(self.h, int(cls), t.ctypes.data if tasks else None, r.ctypes.data if results else None,
+                                    e.ctypes.data if errors else None))
+        return dict(tasks=t, results=r, errors=e)
+
+    def host_row_costs(self, upper_only=True):
+        """(predicted adaptive cost per row, first regular forward slot of every row [nc+1]) — see i2_host_row_costs"""
+        cost = np.empty(self.nc, dtype=np.float64)
+        first = np.empty(self.nc + 1, dtype=np.uint64)
+        _check(self.L.i2_host_row_costs(self.h, 1 if upper_only else 0, cost.ctypes.data, first.ctypes.data))
+        return cost, first
+
     def host_checksums(self):
         a = (C.c_double * 12)()
         _check(self.L.i2_host_checksums(self.h, a))
@@ -386,3 +488,128 @@ class Context:
         r = (C.c_void_p * 3)()
         _check(self.L.i2_host_device_views(self.h, t, r))
         return list(t), list(r)
+
+
+class MultiGpu:
+    """The multi-GPU layer of the C ABI (i2_mgpu_*): the task lists of runAllPairs sharded over the GPUs of one box.
+    MultiGpu(local_gpus=N)                       one process drives N GPUs (the CLI / host-class mode)
+    MultiGpu(device=d, rank=r, world=w, uid=..)  one process per GPU (torchrun); uid = MultiGpu.unique_id() of rank 0"""
+
+    def __init__(self, local_gpus=None, device=0, rank=0, world=1, uid=None, math_mode=MATH_FAST):
+        self.L = load_library()
+        h = C.c_void_p()
+        if local_gpus is not None:
+            _check(self.L.i2_mgpu_create_local(C.byref(h), int(local_gpus), None))
+        else:
+            _check(self.L.i2_mgpu_create_rank(C.byref(h), int(device), int(rank), int(world), uid))
+        self.h = h
+        w, nl, fr = C.c_int(), C.c_int(), C.c_int()
+        _check(self.L.i2_mgpu_info(self.h, C.byref(w), C.byref(nl), C.byref(fr)))
+        self.world, self.n_local, self.first_rank = int(w.value), int(nl.value), int(fr.value)
+        devs = list(range(self.n_local)) if local_gpus is not None else [int(device)]
+        self.contexts = [Context(devs[k], math_mode, borrowed=self.L.i2_mgpu_context(self.h, k)) for k in range(self.n_local)]
+        self.nc = 0
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _check(load_library().i2_mgpu_unique_id(buf))
+        return buf.raw
+
+    def close(self):
+        if getattr(self, "h", None):
+            for c in self.contexts:
+                c.close()
+            self.L.i2_mgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def prepare(self, vertices, cells, level=0):
+        v = np.ascontiguousarray(vertices, dtype=np.float64)
+        c = np.ascontiguousarray(cells, dtype=np.int32)
+        cnt = (C.c_longlong * 3)()
+        _check(self.L.i2_mgpu_prepare(self.h, v.ctypes.data, v.shape[0], c.ctypes.data, c.shape[0], int(level), cnt))
+        self.nc = c.shape[0]
+        for ctx in self.contexts:
+            ctx.nc = self.nc
+        return [int(x) for x in cnt]
+
+    def shard(self, rank):
+        a, b = (C.c_longlong * 3)(), (C.c_longlong * 3)()
+        _check(self.L.i2_mgpu_shard(self.h, int(rank), a, b))
+        return [int(x) for x in a], [int(x) for x in b]
+
+    def run(self, level, check=False, want_stats=False):
+        st = (Stats * 3)()
+        _check(self.L.i2_mgpu_run(self.h, int(level), 1 if check else 0, st if want_stats else None))
+        return [s.as_dict() for s in st] if want_stats else None
+
+    def synchronize(self):
+        _check(self.L.i2_mgpu_synchronize(self.h))
+
+    def checksums(self):
+        a = (C.c_double * 12)()
+        _check(self.L.i2_mgpu_checksums(self.h, a))
+        return np.array(list(a)).reshape(3, 4)
+
+    def fetch(self, local_index, cls, tasks=True, results=True, errors=False):
+        """row-striped export of one local GPU's shard -> dict of numpy arrays in the shard's own order"""
+        n = self.shard(self.first_rank + local_index)[1][cls]
+        out = {}
+        t = np.empty((n, 3), dtype=np.int32) if tasks else None
+        r = np.empty((n, 3), dtype=np.float64) if results else None
+        e = np.empty((n,), dtype=np.float64) if errors else None
+        _check(self.L.i2_mgpu_fetch(self.h, int(local_index), int(cls), t.ctypes.data if tasks else None, r.ctypes.data if results else None,
+                                    e.ctypes.data if errors else None))
+        out.update(tasks=t, results=r, errors=e)
+        return out
+
+    def gather(self, cls, what, root, dst):
+        """result (what=0, float64[n,3]) or task (what=1, int32[n,3]) shards of a class concatenated in rank order into the device
+        tensor `dst` on GPU `root` (None on processes that do not own the root)"""
+        _check(self.L.i2_mgpu_gather(self.h, int(cls), int(what), int(root), _ptr(dst)))
+
+    def set_results_target(self, local_index, ptrs):
+        arr = (C.c_void_p * 3)(*[_ptr(p) for p in ptrs]) if ptrs is not None else None
+        _check(self.L.i2_mgpu_set_results_target(self.h, int(local_index), arr))
+
+    def apply_prepare(self, vertices, cells, level=0):
+        v = np.ascontiguousarray(vertices, dtype=np.float64)
+        c = np.ascontiguousarray(cells, dtype=np.int32)
+        cuts = (C.c_int * (self.world + 1))()
+        _check(self.L.i2_mgpu_apply_prepare(self.h, v.ctypes.data, v.shape[0], c.ctypes.data, c.shape[0], int(level), cuts))
+        self.nc = c.shape[0]
+        for ctx in self.contexts:
+            ctx.nc = self.nc
+        self.row_cuts = [int(x) for x in cuts]
+        return self.row_cuts
+
+    def apply(self, level, weights=None, want_out=True, want_stats=False):
+        w = np.ascontiguousarray(weights, dtype=np.float64) if weights is not None else None
+        out = np.empty((self.nc, 3), dtype=np.float64) if want_out else None
+        st = (Stats * 3)()
+        _check(self.L.i2_mgpu_apply(self.h, int(level), w.ctypes.data if w is not None else None, out.ctypes.data if want_out else None,
+                                    st if want_stats else None))
+        return out, ([x.as_dict() for x in st] if want_stats else None)
+
+    def apply_result(self, local_index=0):
+        """(device tensor view float64[nc,3] of the full vector on local GPU k, uint8[3, rows of its block])"""
+        import torch
+        a, b = C.c_void_p(), C.c_void_p()
+        _check(self.L.i2_mgpu_apply_result(self.h, int(local_index), C.byref(a), C.byref(b)))
+        g = self.first_rank + local_index
+        rows = self.row_cuts[g + 1] - self.row_cuts[g]
+        dev = f"cuda:{self.contexts[local_index].device}"
+        full = torch.as_tensor(_RawCudaBuffer(a.value, (self.nc, 3), "<f8"), device=dev)
+        ref = torch.as_tensor(_RawCudaBuffer(b.value, (3, max(rows, 1)), "|u1"), device=dev)[:, :rows]
+        return full, ref
+
+    def refinements(self, cls):
+        r = np.empty((self.nc,), dtype=np.uint8)
+        _check(self.L.i2_mgpu_refinements(self.h, int(cls), r.ctypes.data))
+        return r

@@ -1,7 +1,6 @@
 // C-ABI entry points of libintegrator2_b200.so (declared in include/i2_abi.h).
 // Host-side orchestration only: every numerical step is a kernel in i2_kernels.cu; there is no CPU fallback.
-#include "../../include/i2_abi.h"
-#include "i2_kernels.cuh"
+#include "i2_context.h"
 
 #include <climits>
 #include <cstdio>
@@ -15,68 +14,6 @@ using namespace i2;
         cudaError_t e__ = (call);                       \
         if (e__ != cudaSuccess) return (int)e__;        \
     } while (0)
-
-struct i2_context {
-    int device = 0;
-    int numSMs = 148;
-    cudaStream_t stream = nullptr;
-    cudaStream_t copyStream = nullptr;
-    bool ownStream = false;
-    int mathMode = I2_MATH_FAST;
-    bool haveQuad = false;
-
-    // borrowed mesh arrays + owned SoA pack
-    const double *verts = nullptr;
-    const int *cells = nullptr;
-    int nv = 0, nc = 0;
-    double *tri = nullptr;
-    int stride = 0;
-    size_t triCap = 0;
-
-    // work queue scratch, one set per neighbour class so that the three classes can run concurrently (owned, grown on demand)
-    struct ClassScratch {
-        double *bufB = nullptr;
-        size_t bufBCap = 0;
-        int *rest[2] = {nullptr, nullptr};   // [0] = dense list of unconverged slots (input order), [1] = per-CTA staging segments
-        size_t restCap = 0;
-        int *blockCnt = nullptr;             // per-CTA counts of the deterministic compaction
-        size_t blockCntCap = 0;
-        unsigned char *cellFlag = nullptr;
-        size_t cellFlagCap = 0;
-        QueueState *qs = nullptr;
-    } scr[3];
-    // i2_integrate_all / i2_host_run: the two adjacent classes run on side streams next to the regular class
-    cudaStream_t side[2] = {nullptr, nullptr};
-    cudaEvent_t forkEv = nullptr, sideDone[2] = {nullptr, nullptr};
-
-    // matrix-free path scratch (per-chunk partial row sums)
-    double *partial = nullptr;
-    size_t partialCap = 0;
-    unsigned char *depthBuf = nullptr;   // list-free adaptive path: per (column chunk, row) refinement depth
-    size_t depthCap = 0;
-
-    // classification scratch
-    unsigned long long *rowCounts = nullptr;
-    size_t rowCap = 0;
-
-    // host-entry state (i2_host_prepare / i2_host_run)
-    double *hVerts = nullptr, *hNormals = nullptr, *hMeasures = nullptr;
-    int *hCells = nullptr;
-    int *hTasks[3] = {nullptr, nullptr, nullptr};
-    double *hIntegrals[3] = {nullptr, nullptr, nullptr};
-    double *hResults[3] = {nullptr, nullptr, nullptr};
-    double *hErrors[3] = {nullptr, nullptr, nullptr};
-    unsigned char *hRefinements[3] = {nullptr, nullptr, nullptr};
-    long long hCount[3] = {0, 0, 0};
-    // multi-GPU use of the host-entry path: this context integrates slots [hLo, hLo + hN) of every class
-    int shardRank = 0, shardWorld = 1;
-    long long hLo[3] = {0, 0, 0}, hN[3] = {0, 0, 0};
-    size_t capVerts = 0, capCells = 0, capNormals = 0, capMeasures = 0, capTasks[3] = {0, 0, 0}, capIntegrals[3] = {0, 0, 0},
-           capResults[3] = {0, 0, 0}, capRefinements[3] = {0, 0, 0}, capErrors[3] = {0, 0, 0};
-    cudaEvent_t chunkDone[2] = {nullptr, nullptr};
-    bool profiling = false;
-    cudaEvent_t prof[3] = {nullptr, nullptr, nullptr};
-};
 
 namespace {
 
@@ -97,9 +34,22 @@ void freeHostState(i2_context *c) {
     fr(c->hVerts, c->capVerts); fr(c->hNormals, c->capNormals); fr(c->hMeasures, c->capMeasures); fr(c->hCells, c->capCells);
     for (int k = 0; k < 3; ++k) {
         fr(c->hTasks[k], c->capTasks[k]); fr(c->hIntegrals[k], c->capIntegrals[k]); fr(c->hResults[k], c->capResults[k]);
-        fr(c->hErrors[k], c->capErrors[k]); fr(c->hRefinements[k], c->capRefinements[k]);
-        c->hCount[k] = 0;
+        fr(c->hErrors[k], c->capErrors[k]);
+        c->hRefinements[k] = nullptr;
+        c->hCount[k] = c->hN[k] = c->hHalf[k] = c->hLo[k] = 0;
     }
+    fr(c->hRefAll, c->capRefAll);
+    for (int k = 0; k < 2; ++k) fr(c->adjFull[k], c->capAdjFull[k]);
+    fr(c->incScratch, c->incCap); fr(c->rowOff, c->rowOffCap); fr(c->rowCost, c->rowCostCap);
+    c->hPrepared = false;
+}
+
+// Column chunks of the list-free kernels: a FIXED width, so that the order in which a row's partial sums are formed and added
+// does not depend on how many rows a call (or a GPU of a multi-GPU run) was given — row sums are bitwise partition-invariant
+// when the row blocks start at multiples of 32.  Small meshes get narrower chunks to fill the GPU.
+int apply_chunks(int nc) {
+    const int width = nc >= (1 << 16) ? 2048 : (nc >= (1 << 13) ? 512 : 256);
+    return (nc + width - 1) / width;
 }
 
 PackedMesh packed(const i2_context *c) {
@@ -123,6 +73,7 @@ const char *i2_error_string(int code) {
     case I2_E_NOQUAD: return "i2: no quadrature rule set (i2_set_quadrature)";
     case I2_E_LEVEL: return "i2: refinement level out of range";
     case I2_E_TOOBIG: return "i2: count exceeds 32-bit task slots";
+    case I2_E_NCCL: return "i2: NCCL unavailable or failed (multi-GPU layer)";
     default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "i2: unknown error";
     }
 }
@@ -180,6 +131,14 @@ int i2_destroy(i2_context *c) {
     if (c->rowCounts) cudaFree(c->rowCounts);
     if (c->partial) cudaFree(c->partial);
     if (c->depthBuf) cudaFree(c->depthBuf);
+    if (c->ap.scratch2) cudaFree(c->ap.scratch2);
+    if (c->ap.refCells) cudaFree(c->ap.refCells);
+    if (c->ap.regular) cudaFree(c->ap.regular);
+    for (int k = 0; k < 2; ++k) {
+        if (c->ap.tasks[k]) cudaFree(c->ap.tasks[k]);
+        if (c->ap.integrals[k]) cudaFree(c->ap.integrals[k]);
+        if (c->ap.results[k]) cudaFree(c->ap.results[k]);
+    }
     if (c->ownStream && c->stream) cudaStreamDestroy(c->stream);
     if (c->copyStream) cudaStreamDestroy(c->copyStream);
     delete c;
@@ -235,6 +194,8 @@ int i2_set_mesh(i2_context *c, const double *verts, int nv, const int *cells, in
     if (!c || nv < 0 || nc < 0 || (nc > 0 && (!verts || !cells || !normals || !measures))) return I2_E_BADARG;
     I2_CUDA(cudaSetDevice(c->device));
     c->verts = verts; c->cells = cells; c->nv = nv; c->nc = nc;
+    c->incidenceValid = false;
+    c->ap.prepared = false;
     c->stride = (nc + 31) & ~31;  // keep every component row 256-byte aligned
     int rc = ensure(&c->tri, &c->triCap, (size_t)PK_COUNT * (size_t)c->stride);
     if (rc) return rc;
@@ -257,6 +218,7 @@ int i2_classify_count(i2_context *c, const int *cells, int nc, long long counts[
     if (!c || !counts || nc < 0 || (nc > 0 && !cells)) return I2_E_BADARG;
     I2_CUDA(cudaSetDevice(c->device));
     counts[0] = counts[1] = counts[2] = 0;
+    c->rowCountsNc = -1;
     if (nc == 0) return 0;
     int rc = ensure(&c->rowCounts, &c->rowCap, (size_t)3 * nc);
     if (rc) return rc;
@@ -275,11 +237,13 @@ int i2_classify_count(i2_context *c, const int *cells, int nc, long long counts[
     I2_CUDA(cudaMemcpyAsync(c->rowCounts, h.data(), h.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
     I2_CUDA(cudaStreamSynchronize(c->stream));
     for (int k = 0; k < 3; ++k) counts[k] = (long long)run[k];
+    c->rowCountsNc = nc;
     return 0;
 }
 
 int i2_classify_fill(i2_context *c, const int *cells, int nc, int *simple, int *attached, int *notn) {
     if (!c || nc < 0 || (nc > 0 && (!cells || !c->rowCounts))) return I2_E_BADARG;
+    if (nc > 0 && c->rowCountsNc != nc) return I2_E_BADARG;   // the offsets must come from i2_classify_count of the same mesh
     I2_CUDA(cudaSetDevice(c->device));
     launch_classify_fill(cells, nc, c->rowCounts, simple, attached, notn, c->stream);
     I2_CUDA(cudaGetLastError());
@@ -309,19 +273,21 @@ int check_class_args(const i2_context *c, int cls, const int *tasks, long long n
     return 0;
 }
 
-// enqueues the whole of one class on stream s (no synchronisation); uses the class's own scratch
-int enqueue_class(i2_context *c, int cls, const int *tasks, long long n, int level, double *integrals, double *results,
-                  unsigned char *refinements, unsigned char *converged, cudaStream_t s, bool profile) {
+// integration rounds of one class on stream s (no synchronisation); uses the class's own scratch.  At a fixed level with the
+// grouped regular kernel the final assembly is fused (*fusedOut = true: the class is complete); otherwise enqueue_finalize
+// must follow.  half > 0: the list is [pairs ; reversed pairs] with `half` pairs (see k_regular_grouped).
+int enqueue_rounds(i2_context *c, int cls, const int *tasks, long long n, long long half, int level, double *integrals, double *results,
+                   unsigned char *refinements, unsigned char *converged, cudaStream_t s, bool profile, bool *fusedOut) {
     i2_context::ClassScratch &sc = c->scr[cls];
     const PackedMesh pm = packed(c);
     I2_CUDA(cudaMemsetAsync(sc.qs, 0, sizeof(QueueState), s));
-    bool fused = false;
+    *fusedOut = false;
 
     if (level >= 0) {
         if (profile) I2_CUDA(cudaEventRecord(c->prof[0], s));
         // regular pairs with the grouped kernel: the final assembly is fused into the integrate kernel
-        fused = (cls == 2 && c->mathMode == I2_MATH_FAST);
-        launch_integrate(cls, c->mathMode, pm, tasks, nullptr, nullptr, n, level, integrals, fused ? results : nullptr, c->numSMs, s);
+        *fusedOut = (cls == 2 && c->mathMode == I2_MATH_FAST);
+        launch_integrate(cls, c->mathMode, pm, tasks, nullptr, nullptr, n, half, level, integrals, *fusedOut ? results : nullptr, c->numSMs, s);
         if (profile) I2_CUDA(cudaEventRecord(c->prof[1], s));
     } else {
         int rc = ensure(&sc.bufB, &sc.bufBCap, (size_t)4 * n);
@@ -340,7 +306,7 @@ int enqueue_class(i2_context *c, int cls, const int *tasks, long long n, int lev
         I2_CUDA(cudaMemsetAsync(sc.cellFlag, 0, c->nc, s));
 
         // round 0: every task on the original control panel; every control panel present in the list is marked
-        launch_integrate(cls, c->mathMode, pm, tasks, nullptr, nullptr, n, 0, integrals, nullptr, c->numSMs, s);
+        launch_integrate(cls, c->mathMode, pm, tasks, nullptr, nullptr, n, half, 0, integrals, nullptr, c->numSMs, s);
         launch_flag_cells(tasks, n, sc.cellFlag, s);
         launch_bump(sc.cellFlag, refinements, c->nc, s);
         // rounds 1..5 are enqueued unconditionally; a round whose device-side task count is 0 does nothing.
@@ -349,14 +315,31 @@ int enqueue_class(i2_context *c, int cls, const int *tasks, long long n, int lev
             const double *prev = (m & 1) ? integrals : sc.bufB;
             const int *listIn = m == 1 ? nullptr : sc.rest[0];
             const int *countIn = m == 1 ? nullptr : &sc.qs->count[m - 1];
-            launch_integrate(cls, c->mathMode, pm, tasks, listIn, countIn, n, m, cur, nullptr, c->numSMs, s);
+            launch_integrate(cls, c->mathMode, pm, tasks, listIn, countIn, n, m == 1 ? half : 0, m, cur, nullptr, c->numSMs, s);
             launch_compare(cur, prev, tasks, listIn, countIn, n, sc.rest[1], sc.blockCnt, sc.rest[0], &sc.qs->count[m], sc.cellFlag, converged, sc.qs, m,
                            c->numSMs, s);
             launch_bump(sc.cellFlag, refinements, c->nc, s);
         }
     }
-    if (!fused) launch_finalize(cls, pm, c->verts, tasks, n, integrals, sc.bufB, sc.qs, results, sc.qs, s);
     I2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// closed-form singular parts + final assembly; the result buffer of the adaptive ping-pong is selected by the class's
+// QueueState::lastRound on the device (a multi-GPU caller overwrites it with the maximum over the ranks first)
+int enqueue_finalize(i2_context *c, int cls, const int *tasks, long long n, double *integrals, double *results, cudaStream_t s) {
+    i2_context::ClassScratch &sc = c->scr[cls];
+    launch_finalize(cls, packed(c), c->verts, tasks, n, integrals, sc.bufB, sc.qs, results, sc.qs, s);
+    I2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int enqueue_class(i2_context *c, int cls, const int *tasks, long long n, int level, double *integrals, double *results,
+                  unsigned char *refinements, unsigned char *converged, cudaStream_t s, bool profile, long long half = 0) {
+    bool fused = false;
+    int rc = enqueue_rounds(c, cls, tasks, n, half, level, integrals, results, refinements, converged, s, profile, &fused);
+    if (!rc && !fused) rc = enqueue_finalize(c, cls, tasks, n, integrals, results, s);
+    if (rc) return rc;
     if (profile && level >= 0) I2_CUDA(cudaEventRecord(c->prof[2], s));
     return 0;
 }
@@ -375,15 +358,32 @@ void fill_stats(const QueueState &h, long long n, int level, i2_stats *stats) {
 
 }  // namespace
 
+namespace {
+int integrate_class_impl(i2_context *c, int cls, const int *tasks, long long n, long long half, int level, double *integrals, double *results,
+                         unsigned char *refinements, unsigned char *converged, i2_stats *stats);
+}
+
 int i2_integrate_class(i2_context *c, int cls, const int *tasks, long long n, int level, double *integrals, double *results,
                        unsigned char *refinements, unsigned char *converged, i2_stats *stats) {
+    return integrate_class_impl(c, cls, tasks, n, 0, level, integrals, results, refinements, converged, stats);
+}
+
+int i2_integrate_pairs(i2_context *c, int cls, const int *tasks, long long nHalf, int level, double *integrals, double *results,
+                       unsigned char *refinements, unsigned char *converged, i2_stats *stats) {
+    if (nHalf < 0) return I2_E_BADARG;
+    return integrate_class_impl(c, cls, tasks, 2 * nHalf, nHalf, level, integrals, results, refinements, converged, stats);
+}
+
+namespace {
+int integrate_class_impl(i2_context *c, int cls, const int *tasks, long long n, long long half, int level, double *integrals, double *results,
+                         unsigned char *refinements, unsigned char *converged, i2_stats *stats) {
     if (!c) return I2_E_BADARG;
     if (stats) std::memset(stats, 0, sizeof(*stats));
     int rc = check_class_args(c, cls, tasks, n, level, integrals, results);
     if (rc || n == 0) return rc;
     I2_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
-    rc = enqueue_class(c, cls, tasks, n, level, integrals, results, refinements, converged, s, c->profiling);
+    rc = enqueue_class(c, cls, tasks, n, level, integrals, results, refinements, converged, s, c->profiling, half);
     if (rc) return rc;
     if (stats) {
         QueueState h;
@@ -393,6 +393,7 @@ int i2_integrate_class(i2_context *c, int cls, const int *tasks, long long n, in
     }
     return 0;
 }
+}  // namespace
 
 int i2_integrate_all(i2_context *c, const int *const tasks[3], const long long n[3], int level, double *const integrals[3],
                      double *const results[3], unsigned char *const refinements[3], unsigned char *const converged[3], i2_stats stats[3]) {
@@ -442,12 +443,7 @@ int i2_apply_regular(i2_context *c, int rowLo, int rowHi, const double *weights,
     if (!out) return I2_E_BADARG;
     I2_CUDA(cudaSetDevice(c->device));
     const int rows = rowHi - rowLo;
-    // enough CTAs for a few waves of 4 CTAs/SM: split the columns when there are few row blocks
-    const int rowBlocks = (rows + kThreads - 1) / kThreads;
-    int chunks = (c->numSMs * 4 * 2 + rowBlocks - 1) / rowBlocks;
-    if (chunks < 1) chunks = 1;
-    const int maxChunks = (c->nc + 255) / 256;
-    if (chunks > maxChunks) chunks = maxChunks;
+    const int chunks = apply_chunks(c->nc);
     int rc = ensure(&c->partial, &c->partialCap, (size_t)chunks * rows * 3);
     if (rc) return rc;
     launch_apply_regular(packed(c), rowLo, rowHi, 0, c->nc, chunks, weights, c->partial, out, c->stream);
@@ -466,12 +462,7 @@ int i2_apply_regular_adaptive(i2_context *c, int rowLo, int rowHi, const double 
     if (!out) return I2_E_BADARG;
     I2_CUDA(cudaSetDevice(c->device));
     const int rows = rowHi - rowLo;
-    // 4 lanes per row -> 32 rows per CTA; enough CTAs for a few waves of 3 CTAs/SM: split the columns when there are few row blocks
-    const int rowBlocks = (rows + kThreads / 4 - 1) / (kThreads / 4);
-    int chunks = (c->numSMs * 3 * 2 + rowBlocks - 1) / rowBlocks;
-    if (chunks < 1) chunks = 1;
-    const int maxChunks = (c->nc + 255) / 256;
-    if (chunks > maxChunks) chunks = maxChunks;
+    const int chunks = apply_chunks(c->nc);   // 4 lanes per row -> 32 rows per CTA, grid = row blocks x column chunks
     // scratch: 8 doubles of header (6 x 64-bit round counters, the class's last round) + per-chunk partial sums
     int rc = ensure(&c->partial, &c->partialCap, (size_t)8 + (size_t)chunks * rows * 6);
     if (!rc) rc = ensure(&c->depthBuf, &c->depthCap, (size_t)chunks * rows);
@@ -500,6 +491,177 @@ int i2_apply_regular_adaptive(i2_context *c, int rowLo, int rowHi, const double 
     return 0;
 }
 
+extern "C++" int i2::ensure_incidence(i2_context *c) {
+    if (c->incidenceValid) return 0;
+    if (!c->cells || c->nc <= 0 || c->nv <= 0) return I2_E_NOMESH;
+    int rc = ensure(&c->incScratch, &c->incCap, incidence_scratch_ints(c->nv, c->nc));
+    if (!rc) rc = ensure(&c->rowOff, &c->rowOffCap, (size_t)3 * (c->nc + 1) + 3);
+    if (rc) return rc;
+    launch_incidence(c->cells, c->nv, c->nc, c->incScratch, c->rowOff, c->rowOff + (size_t)3 * (c->nc + 1), c->stream);
+    I2_CUDA(cudaGetLastError());
+    c->incidenceValid = true;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// the whole operator for a block of rows: out[i] = sum_j w_j J(K_i, K_j) over ALL neighbour classes; the regular class
+// list-free (i2_apply_regular[_adaptive]), the two adjacent classes from row-major lists built by vertex incidence
+// ---------------------------------------------------------------------------------------------------------
+int i2_apply_prepare(i2_context *c, int rowLo, int rowHi) {
+    if (!c || rowLo < 0 || rowHi < rowLo) return I2_E_BADARG;
+    if (!c->tri) return I2_E_NOMESH;
+    if (rowHi > c->nc) return I2_E_BADARG;
+    I2_CUDA(cudaSetDevice(c->device));
+    i2_context::ApplyState &ap = c->ap;
+    ap.prepared = false;
+    int rc = i2::ensure_incidence(c);
+    if (!rc) rc = ensure(&ap.scratch2, &ap.scratch2Cap, rows_scratch_ints(c->nc));
+    if (!rc) rc = ensure(&ap.refCells, &ap.refCellsCap, (size_t)2 * c->nc);
+    if (rc) return rc;
+    cudaStream_t s = c->stream;
+    launch_partners_both(c->cells, c->nv, c->nc, c->incScratch, ap.scratch2, s);
+    I2_CUDA(cudaGetLastError());
+    const int *offS = ap.scratch2 + 2 * (size_t)c->nc, *offA = offS + (c->nc + 1);
+    int h[4];
+    I2_CUDA(cudaMemcpyAsync(&h[0], offS + rowLo, sizeof(int), cudaMemcpyDeviceToHost, s));
+    I2_CUDA(cudaMemcpyAsync(&h[1], offS + rowHi, sizeof(int), cudaMemcpyDeviceToHost, s));
+    I2_CUDA(cudaMemcpyAsync(&h[2], offA + rowLo, sizeof(int), cudaMemcpyDeviceToHost, s));
+    I2_CUDA(cudaMemcpyAsync(&h[3], offA + rowHi, sizeof(int), cudaMemcpyDeviceToHost, s));
+    I2_CUDA(cudaStreamSynchronize(s));
+    ap.n[0] = h[1] - h[0];
+    ap.n[1] = h[3] - h[2];
+    for (int k = 0; k < 2; ++k) {
+        rc = ensure(&ap.tasks[k], &ap.capTasks[k], (size_t)3 * ap.n[k]);
+        if (!rc) rc = ensure(&ap.integrals[k], &ap.capIntegrals[k], (size_t)4 * ap.n[k]);
+        if (!rc) rc = ensure(&ap.results[k], &ap.capResults[k], (size_t)3 * ap.n[k]);
+        if (rc) return rc;
+    }
+    launch_partners_fill_rows(c->cells, c->nv, c->nc, c->incScratch, ap.scratch2, rowLo, rowHi, ap.tasks[0], ap.tasks[1], s);
+    I2_CUDA(cudaGetLastError());
+    ap.rowLo = rowLo;
+    ap.rowHi = rowHi;
+    ap.prepared = true;
+    return 0;
+}
+
+int i2_apply_rounds(i2_context *c, int level, const double *weights) {
+    if (!c) return I2_E_BADARG;
+    if (!c->tri || !c->ap.prepared) return I2_E_NOMESH;
+    if (!c->haveQuad) return I2_E_NOQUAD;
+    if (level > 0) return I2_E_LEVEL;   // the list-free regular kernel exists at level 0 and under error control
+    I2_CUDA(cudaSetDevice(c->device));
+    i2_context::ApplyState &ap = c->ap;
+    cudaStream_t s = c->stream;
+    const int rows = ap.rowHi - ap.rowLo;
+    if (rows == 0) return 0;
+    if (level < 0) I2_CUDA(cudaMemsetAsync(ap.refCells, 0, (size_t)2 * c->nc, s));
+    // the two adjacent classes of the block on the side streams, next to the regular class
+    I2_CUDA(cudaEventRecord(c->forkEv, s));
+    for (int k = 0; k < 2; ++k) {
+        cudaStream_t st = c->side[k];
+        I2_CUDA(cudaStreamWaitEvent(st, c->forkEv, 0));
+        if (ap.n[k] > 0) {
+            bool fused = false;
+            const int rc = enqueue_rounds(c, k, ap.tasks[k], ap.n[k], 0, level, ap.integrals[k], ap.results[k],
+                                          level < 0 ? ap.refCells + (size_t)k * c->nc : nullptr, nullptr, st, false, &fused);
+            if (rc) return rc;
+        }
+        I2_CUDA(cudaEventRecord(c->sideDone[k], st));
+    }
+    if (level < 0) {
+        const int chunks = apply_chunks(c->nc);
+        int rc = ensure(&c->partial, &c->partialCap, (size_t)8 + (size_t)chunks * rows * 6);
+        if (!rc) rc = ensure(&c->depthBuf, &c->depthCap, (size_t)chunks * rows);
+        if (rc) return rc;
+        ap.chunks = chunks;
+        I2_CUDA(cudaMemsetAsync(c->partial, 0, 8 * sizeof(double), s));
+        launch_apply_regular_adaptive(packed(c), ap.rowLo, ap.rowHi, 0, c->nc, chunks, weights, c->partial + 8, c->depthBuf,
+                                      reinterpret_cast<int *>(c->partial + 6), reinterpret_cast<unsigned long long *>(c->partial), nullptr, nullptr,
+                                      nullptr, s);
+    } else {
+        const int chunks = apply_chunks(c->nc);
+        int rc = ensure(&c->partial, &c->partialCap, (size_t)chunks * rows * 3);
+        if (!rc) rc = ensure(&ap.regular, &ap.regularCap, (size_t)rows * 3);
+        if (rc) return rc;
+        launch_apply_regular(packed(c), ap.rowLo, ap.rowHi, 0, c->nc, chunks, weights, c->partial, ap.regular, s);
+    }
+    I2_CUDA(cudaGetLastError());
+    for (int k = 0; k < 2; ++k) I2_CUDA(cudaStreamWaitEvent(s, c->sideDone[k], 0));
+    return 0;
+}
+
+int i2_apply_last_rounds(i2_context *c, int last[3], int set) {
+    if (!c || !last) return I2_E_BADARG;
+    if (!c->ap.prepared || !c->partial) return I2_E_NOMESH;
+    I2_CUDA(cudaSetDevice(c->device));
+    int *dev[3] = {&c->scr[0].qs->lastRound, &c->scr[1].qs->lastRound, reinterpret_cast<int *>(c->partial + 6)};
+    for (int k = 0; k < 3; ++k) {
+        if (set) I2_CUDA(cudaMemcpyAsync(dev[k], &last[k], sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        else I2_CUDA(cudaMemcpyAsync(&last[k], dev[k], sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    }
+    I2_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int i2_apply_finish(i2_context *c, int level, const double *weights, double *out, unsigned char *refinements, i2_stats stats[3]) {
+    if (!c) return I2_E_BADARG;
+    if (stats) std::memset(stats, 0, 3 * sizeof(i2_stats));
+    if (!c->tri || !c->ap.prepared) return I2_E_NOMESH;
+    if (level > 0) return I2_E_LEVEL;
+    I2_CUDA(cudaSetDevice(c->device));
+    i2_context::ApplyState &ap = c->ap;
+    cudaStream_t s = c->stream;
+    const int rows = ap.rowHi - ap.rowLo;
+    if (rows == 0) return 0;
+    if (!out) return I2_E_BADARG;
+    if (level < 0)
+        launch_reduce_partials_adaptive(c->partial + 8, c->depthBuf, rows, ap.chunks, reinterpret_cast<int *>(c->partial + 6), out, nullptr,
+                                        refinements ? refinements + 2 * (size_t)rows : nullptr, s);
+    else
+        I2_CUDA(cudaMemcpyAsync(out, ap.regular, sizeof(double) * 3 * rows, cudaMemcpyDeviceToDevice, s));
+    const int *offS = ap.scratch2 + 2 * (size_t)c->nc, *offA = offS + (c->nc + 1);
+    for (int k = 0; k < 2; ++k) {
+        if (ap.n[k] > 0) {
+            const int rc = enqueue_finalize(c, k, ap.tasks[k], ap.n[k], ap.integrals[k], ap.results[k], s);
+            if (rc) return rc;
+            launch_row_scatter(ap.tasks[k], ap.results[k], k == 0 ? offS : offA, ap.rowLo, rows, weights, out, s);
+        }
+        if (level < 0 && refinements) launch_take_rows(ap.refCells + (size_t)k * c->nc, ap.rowLo, rows, refinements + (size_t)k * rows, s);
+    }
+    I2_CUDA(cudaGetLastError());
+    if (stats) {
+        QueueState q[2];
+        unsigned long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int k = 0; k < 2; ++k) {
+            std::memset(&q[k], 0, sizeof(QueueState));
+            if (ap.n[k] > 0) I2_CUDA(cudaMemcpyAsync(&q[k], c->scr[k].qs, sizeof(QueueState), cudaMemcpyDeviceToHost, s));
+        }
+        if (level < 0) I2_CUDA(cudaMemcpyAsync(h, c->partial, sizeof(h), cudaMemcpyDeviceToHost, s));
+        I2_CUDA(cudaStreamSynchronize(s));
+        for (int k = 0; k < 2; ++k)
+            if (ap.n[k] > 0) fill_stats(q[k], ap.n[k], level, &stats[k]);
+        if (level < 0) {
+            int L;
+            std::memcpy(&L, &h[6], sizeof(int));
+            stats[2].last_round = L;
+            stats[2].integrated[0] = (long long)h[0];
+            long long before = (long long)h[0];
+            for (int m = 1; m <= L && m <= MAX_REFINE_LEVEL; ++m) {
+                stats[2].integrated[m] = before << (2 * m);
+                stats[2].unconverged[m] = (long long)h[m];
+                before = (long long)h[m];
+            }
+        }
+    }
+    return 0;
+}
+
+int i2_apply(i2_context *c, int level, const double *weights, double *out, unsigned char *refinements, i2_stats stats[3]) {
+    int rc = i2_apply_rounds(c, level, weights);
+    if (!rc) rc = i2_apply_finish(c, level, weights, out, refinements, stats);
+    return rc;
+}
+
 int i2_symmetry_error(i2_context *c, const double *results, long long nHalf, double *errors) {
     if (!c || nHalf < 0 || (nHalf > 0 && (!results || !errors))) return I2_E_BADARG;
     I2_CUDA(cudaSetDevice(c->device));
@@ -511,60 +673,143 @@ int i2_symmetry_error(i2_context *c, const double *results, long long nHalf, dou
 // ---------------------------------------------------------------------------------------------------------
 // host-buffer entry points
 // ---------------------------------------------------------------------------------------------------------
-int i2_host_prepare(i2_context *c, const double *hv, int nv, const int *hc, int nc, long long taskCounts[3]) {
-    if (!c || !hv || !hc || nv <= 0 || nc <= 0 || !taskCounts) return I2_E_BADARG;
+namespace {
+inline long long align32(long long x) { return x & ~31LL; }
+inline double *results_of(i2_context *c, int k) { return c->hResultsTarget[k] ? c->hResultsTarget[k] : c->hResults[k]; }
+}  // namespace
+
+// phase A of i2_host_prepare: upload, geometry, SoA pack, classification by vertex incidence -> pairs per class
+extern "C++" int i2::host_prepare_mesh(i2_context *c, const double *hv, int nv, const int *hc, int nc, long long pairs[3]) {
+    if (!c || !hv || !hc || nv <= 0 || nc <= 0 || !pairs) return I2_E_BADARG;
     I2_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = c->stream;
+    // whatever an earlier prepare left behind is stale from here on (a failure below must not leave old lists next to a new mesh)
+    c->hPrepared = false;
+    for (int k = 0; k < 3; ++k) c->hCount[k] = c->hN[k] = c->hHalf[k] = c->hLo[k] = 0;
     // device buffers are kept between calls and only grow (cudaMalloc/cudaFree of multi-GB buffers costs milliseconds)
     int rc = ensure(&c->hVerts, &c->capVerts, (size_t)3 * nv);
     if (!rc) rc = ensure(&c->hCells, &c->capCells, (size_t)3 * nc);
     if (!rc) rc = ensure(&c->hNormals, &c->capNormals, (size_t)3 * nc);
     if (!rc) rc = ensure(&c->hMeasures, &c->capMeasures, (size_t)nc);
+    if (!rc) rc = ensure(&c->hRefAll, &c->capRefAll, (size_t)3 * nc);
     if (rc) return rc;
+    for (int k = 0; k < 3; ++k) c->hRefinements[k] = c->hRefAll + (size_t)k * nc;
     I2_CUDA(cudaMemcpyAsync(c->hVerts, hv, sizeof(double) * 3 * nv, cudaMemcpyHostToDevice, s));
     I2_CUDA(cudaMemcpyAsync(c->hCells, hc, sizeof(int) * 3 * nc, cudaMemcpyHostToDevice, s));
     rc = i2_mesh_geometry(c, c->hVerts, nv, c->hCells, nc, c->hNormals, nullptr, c->hMeasures);
     if (rc) return rc;
     rc = i2_set_mesh(c, c->hVerts, nv, c->hCells, nc, c->hNormals, c->hMeasures);
     if (rc) return rc;
-    long long pairs[3];
-    rc = i2_classify_count(c, c->hCells, nc, pairs);
+    // classification by vertex incidence: per-row partner counts -> first slot of every row in the three lists, totals
+    rc = i2::ensure_incidence(c);
     if (rc) return rc;
-    for (int k = 0; k < 3; ++k) {
-        if (2 * pairs[k] > INT_MAX) return I2_E_TOOBIG;
-        c->hCount[k] = 2 * pairs[k];
-        taskCounts[k] = c->hCount[k];
-        rc = ensure(&c->hTasks[k], &c->capTasks[k], (size_t)3 * c->hCount[k]);
-        if (!rc) rc = ensure(&c->hIntegrals[k], &c->capIntegrals[k], (size_t)4 * c->hCount[k]);
-        if (!rc) rc = ensure(&c->hResults[k], &c->capResults[k], (size_t)3 * c->hCount[k]);
-        if (!rc) rc = ensure(&c->hRefinements[k], &c->capRefinements[k], (size_t)nc);
-        if (rc) return rc;
-    }
-    rc = i2_classify_fill(c, c->hCells, nc, c->hTasks[0], c->hTasks[1], c->hTasks[2]);
-    if (rc) return rc;
-    for (int k = 0; k < 3; ++k) {
-        rc = i2_add_reversed_pairs(c, c->hTasks[k], pairs[k]);
-        if (rc) return rc;
-    }
-    for (int k = 0; k < 3; ++k) {   // contiguous equal-count shard of this context (the whole list unless i2_host_set_shard was called)
-        const long long base = c->hCount[k] / c->shardWorld, rem = c->hCount[k] % c->shardWorld;
-        c->hLo[k] = base * c->shardRank + (c->shardRank < rem ? c->shardRank : rem);
-        c->hN[k] = base + (c->shardRank < rem ? 1 : 0);
-    }
+    unsigned long long *totalsDev = c->rowOff + (size_t)3 * (nc + 1);
+    unsigned long long totals[3];
+    I2_CUDA(cudaMemcpyAsync(totals, totalsDev, sizeof(totals), cudaMemcpyDeviceToHost, s));
     I2_CUDA(cudaStreamSynchronize(s));
+    for (int k = 0; k < 3; ++k) {
+        pairs[k] = (long long)totals[k];
+        c->hCount[k] = 2 * pairs[k];
+    }
+    c->hNv = nv;
     return 0;
+}
+
+// phase B: this context's shard of the three ordered task lists (needs host_prepare_mesh; ranges from i2_host_set_shard or
+// host_set_forward_ranges)
+extern "C++" int i2::host_prepare_lists(i2_context *c) {
+    if (!c || !c->hVerts || c->nc <= 0) return I2_E_NOMESH;
+    I2_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const int nc = c->nc, nv = c->hNv;
+    int rc = 0;
+    long long pairs[3];
+    for (int k = 0; k < 3; ++k) {
+        pairs[k] = c->hCount[k] / 2;
+        if (2 * pairs[k] > INT_MAX) return I2_E_TOOBIG;
+    }
+    // this context's shard: the pairs with forward slots [lo, hi) of every class, in both orders; bounds are multiples of 32 so
+    // that the warp groups of the shard are warp groups of the whole list (results do not depend on the partition)
+    long long lo[3], hi[3];
+    for (int k = 0; k < 3; ++k) {
+        if (c->explicitRanges) {
+            lo[k] = align32(c->rangeLo[k] < pairs[k] ? c->rangeLo[k] : pairs[k]);
+            hi[k] = c->rangeHi[k] >= pairs[k] ? pairs[k] : align32(c->rangeHi[k]);
+        } else {
+            lo[k] = align32(pairs[k] * c->shardRank / c->shardWorld);
+            hi[k] = c->shardRank == c->shardWorld - 1 ? pairs[k] : align32(pairs[k] * (c->shardRank + 1) / c->shardWorld);
+        }
+        if (hi[k] < lo[k]) hi[k] = lo[k];
+        const long long n = 2 * (hi[k] - lo[k]);
+        rc = ensure(&c->hTasks[k], &c->capTasks[k], (size_t)3 * n);
+        if (!rc) rc = ensure(&c->hIntegrals[k], &c->capIntegrals[k], (size_t)4 * n);
+        if (!rc) rc = ensure(&c->hResults[k], &c->capResults[k], (size_t)3 * n);
+        if (rc) return rc;
+    }
+    // adjacent classes: the whole ordered lists are small (~12 N and ~3 N tasks); a shard copies its two pieces out of them
+    int *adj[2];
+    bool whole[2];
+    for (int k = 0; k < 2; ++k) {
+        whole[k] = lo[k] == 0 && hi[k] == pairs[k];
+        adj[k] = c->hTasks[k];
+        if (!whole[k]) {
+            rc = ensure(&c->adjFull[k], &c->capAdjFull[k], (size_t)6 * pairs[k]);
+            if (rc) return rc;
+            adj[k] = c->adjFull[k];
+        }
+    }
+    launch_partners_fill(c->hCells, nv, nc, c->incScratch, c->rowOff, pairs[0] ? adj[0] : nullptr, pairs[1] ? adj[1] : nullptr, true, s);
+    for (int k = 0; k < 2; ++k) {
+        const long long h = hi[k] - lo[k];
+        if (whole[k] || h == 0) continue;
+        I2_CUDA(cudaMemcpyAsync(c->hTasks[k], adj[k] + 3 * lo[k], sizeof(int) * 3 * h, cudaMemcpyDeviceToDevice, s));
+        I2_CUDA(cudaMemcpyAsync(c->hTasks[k] + 3 * h, adj[k] + 3 * (pairs[k] + lo[k]), sizeof(int) * 3 * h, cudaMemcpyDeviceToDevice, s));
+    }
+    // regular class: only this shard's slots are materialised, pairs and reversed pairs by one kernel
+    launch_regular_fill(c->hCells, nc, c->rowOff, (unsigned long long)lo[2], (unsigned long long)hi[2], c->hTasks[2],
+                        c->hTasks[2] + 3 * (hi[2] - lo[2]), c->numSMs, s);
+    I2_CUDA(cudaGetLastError());
+    I2_CUDA(cudaStreamSynchronize(s));
+    for (int k = 0; k < 3; ++k) {
+        c->hLo[k] = lo[k];
+        c->hHalf[k] = hi[k] - lo[k];
+        c->hN[k] = 2 * c->hHalf[k];
+    }
+    c->hPrepared = true;
+    return 0;
+}
+
+int i2_host_prepare(i2_context *c, const double *hv, int nv, const int *hc, int nc, long long taskCounts[3]) {
+    if (!taskCounts) return I2_E_BADARG;
+    long long pairs[3];
+    int rc = i2::host_prepare_mesh(c, hv, nv, hc, nc, pairs);
+    if (rc) return rc;
+    for (int k = 0; k < 3; ++k) taskCounts[k] = 2 * pairs[k];
+    return i2::host_prepare_lists(c);
 }
 
 int i2_host_set_shard(i2_context *c, int rank, int world) {
     if (!c || world < 1 || rank < 0 || rank >= world) return I2_E_BADARG;
     c->shardRank = rank;
     c->shardWorld = world;
+    c->explicitRanges = false;
+    return 0;
+}
+
+extern "C++" int i2::host_set_forward_ranges(i2_context *c, const long long lo[3], const long long hi[3]) {
+    if (!c || !lo || !hi) return I2_E_BADARG;
+    for (int k = 0; k < 3; ++k) {
+        if (lo[k] < 0 || hi[k] < lo[k]) return I2_E_BADARG;
+        c->rangeLo[k] = lo[k];
+        c->rangeHi[k] = hi[k];
+    }
+    c->explicitRanges = true;
     return 0;
 }
 
 int i2_host_shard(i2_context *c, long long first[3], long long count[3]) {
     if (!c || !first || !count) return I2_E_BADARG;
-    if (!c->hVerts) return I2_E_NOMESH;
+    if (!c->hPrepared) return I2_E_NOMESH;
     for (int k = 0; k < 3; ++k) {
         first[k] = c->hLo[k];
         count[k] = c->hN[k];
@@ -572,14 +817,32 @@ int i2_host_shard(i2_context *c, long long first[3], long long count[3]) {
     return 0;
 }
 
+int i2_host_row_costs(i2_context *c, int upper_only, double *h_cost, unsigned long long *h_row_first_regular) {
+    if (!c) return I2_E_BADARG;
+    if (!c->hVerts || !c->rowOff || !c->tri || c->nc <= 0) return I2_E_NOMESH;   // needs the mesh phase of the prepare only
+    I2_CUDA(cudaSetDevice(c->device));
+    const int nc = c->nc;
+    if (h_cost) {
+        int rc = ensure(&c->rowCost, &c->rowCostCap, (size_t)nc);
+        if (rc) return rc;
+        launch_row_cost(packed(c), upper_only != 0, c->rowCost, c->stream);
+        I2_CUDA(cudaGetLastError());
+        I2_CUDA(cudaMemcpyAsync(h_cost, c->rowCost, sizeof(double) * nc, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (h_row_first_regular)
+        I2_CUDA(cudaMemcpyAsync(h_row_first_regular, c->rowOff + 2 * (size_t)(nc + 1), sizeof(unsigned long long) * (nc + 1), cudaMemcpyDeviceToHost, c->stream));
+    I2_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 int i2_host_checksums(i2_context *c, double sums[12]) {
     if (!c || !sums) return I2_E_BADARG;
-    if (!c->hVerts) return I2_E_NOMESH;
+    if (!c->hPrepared) return I2_E_NOMESH;
     I2_CUDA(cudaSetDevice(c->device));
     double *d = nullptr;
     I2_CUDA(cudaMalloc((void **)&d, sizeof(double) * 12));
     I2_CUDA(cudaMemsetAsync(d, 0, sizeof(double) * 12, c->stream));
-    for (int k = 0; k < 3; ++k) launch_checksum(c->hResults[k] + 3 * c->hLo[k], c->hN[k], d + 4 * k, c->numSMs, c->stream);
+    for (int k = 0; k < 3; ++k) launch_checksum(results_of(c, k), c->hN[k], d + 4 * k, c->numSMs, c->stream);
     I2_CUDA(cudaMemcpyAsync(sums, d, sizeof(double) * 12, cudaMemcpyDeviceToHost, c->stream));
     I2_CUDA(cudaStreamSynchronize(c->stream));
     cudaFree(d);
@@ -590,90 +853,174 @@ int i2_host_device_views(i2_context *c, const int *tasks[3], const double *resul
     if (!c) return I2_E_BADARG;
     for (int k = 0; k < 3; ++k) {
         if (tasks) tasks[k] = c->hTasks[k];
-        if (results) results[k] = c->hResults[k];
+        if (results) results[k] = results_of(c, k);
     }
+    return 0;
+}
+
+// Integration rounds of the three classes of this context's shard: the two adjacent classes (short, latency-bound chains of
+// kernels) on the side streams, the regular class on the context's stream, joined at the end.  At a fixed level the classes are
+// complete afterwards (finalize on the same streams); under error control the finalize step is separate (host_run_finalize),
+// so that a multi-GPU caller can agree on the last round first.
+extern "C++" int i2::host_run_rounds(i2_context *c, int level) {
+    if (!c) return I2_E_BADARG;
+    if (!c->hPrepared) return I2_E_NOMESH;
+    if (!c->haveQuad) return I2_E_NOQUAD;
+    if (level > 12) return I2_E_LEVEL;
+    I2_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    if (level < 0) I2_CUDA(cudaMemsetAsync(c->hRefAll, 0, (size_t)3 * c->nc, s));
+    I2_CUDA(cudaEventRecord(c->forkEv, s));
+    for (int k = 0; k < 3; ++k) {
+        cudaStream_t st = k < 2 ? c->side[k] : s;
+        if (k < 2) I2_CUDA(cudaStreamWaitEvent(st, c->forkEv, 0));
+        if (c->hN[k] > 0) {
+            bool fused = false;
+            const bool prof = k == 2 && c->profiling && level >= 0;   // i2_set_profiling: device time of the regular class's kernels
+            int rc = enqueue_rounds(c, k, c->hTasks[k], c->hN[k], c->hHalf[k], level, c->hIntegrals[k], results_of(c, k),
+                                    level < 0 ? c->hRefinements[k] : nullptr, nullptr, st, prof, &fused);
+            if (!rc && level >= 0 && !fused) rc = enqueue_finalize(c, k, c->hTasks[k], c->hN[k], c->hIntegrals[k], results_of(c, k), st);
+            if (rc) return rc;
+            if (prof) I2_CUDA(cudaEventRecord(c->prof[2], st));
+        }
+        if (k < 2) I2_CUDA(cudaEventRecord(c->sideDone[k], st));
+    }
+    for (int k = 0; k < 2; ++k) I2_CUDA(cudaStreamWaitEvent(s, c->sideDone[k], 0));   // join
+    return 0;
+}
+
+extern "C++" int i2::host_run_finalize(i2_context *c, int level, bool wantErrors) {
+    if (!c) return I2_E_BADARG;
+    if (!c->hPrepared) return I2_E_NOMESH;
+    I2_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    for (int k = 0; k < 3; ++k) {
+        if (c->hN[k] == 0) continue;
+        if (level < 0) {
+            const int rc = enqueue_finalize(c, k, c->hTasks[k], c->hN[k], c->hIntegrals[k], results_of(c, k), s);
+            if (rc) return rc;
+        }
+        if (wantErrors) {
+            // the shard holds every pair in both orders (slot t and hHalf + t): the (i,j)/(j,i) defect is local
+            const int rc = ensure(&c->hErrors[k], &c->capErrors[k], (size_t)c->hN[k]);
+            if (rc) return rc;
+            launch_symmetry_error(results_of(c, k), c->hHalf[k], c->hErrors[k], s);
+            I2_CUDA(cudaGetLastError());
+        }
+    }
+    return 0;
+}
+
+// "bring your own communicator": the two halves of i2_host_run with access to what has to be agreed between the shards
+int i2_host_run_rounds(i2_context *c, int level) { return i2::host_run_rounds(c, level); }
+int i2_host_run_finalize(i2_context *c, int level, int check) { return i2::host_run_finalize(c, level, check != 0); }
+
+int i2_host_last_rounds(i2_context *c, int last[3], int set) {
+    if (!c || !last) return I2_E_BADARG;
+    if (!c->hPrepared) return I2_E_NOMESH;
+    I2_CUDA(cudaSetDevice(c->device));
+    for (int k = 0; k < 3; ++k) {
+        if (set) I2_CUDA(cudaMemcpyAsync(&c->scr[k].qs->lastRound, &last[k], sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        else I2_CUDA(cudaMemcpyAsync(&last[k], &c->scr[k].qs->lastRound, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    }
+    I2_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int i2_host_refinements(i2_context *c, unsigned char *ref, int set) {
+    if (!c || !ref) return I2_E_BADARG;
+    if (!c->hPrepared) return I2_E_NOMESH;
+    I2_CUDA(cudaSetDevice(c->device));
+    if (set) I2_CUDA(cudaMemcpyAsync(c->hRefAll, ref, (size_t)3 * c->nc, cudaMemcpyHostToDevice, c->stream));
+    else I2_CUDA(cudaMemcpyAsync(ref, c->hRefAll, (size_t)3 * c->nc, cudaMemcpyDeviceToHost, c->stream));
+    I2_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int i2_host_fetch(i2_context *c, int cls, int *hTasks, double *hResults, double *hErrors) {
+    if (!c || cls < 0 || cls > 2) return I2_E_BADARG;
+    if (!c->hPrepared) return I2_E_NOMESH;
+    I2_CUDA(cudaSetDevice(c->device));
+    const long long n = c->hN[cls];
+    if (n > 0) {
+        if (hTasks) I2_CUDA(cudaMemcpyAsync(hTasks, c->hTasks[cls], sizeof(int) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+        if (hResults) I2_CUDA(cudaMemcpyAsync(hResults, results_of(c, cls), sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, c->stream));
+        if (hErrors) {
+            if (!c->hErrors[cls]) return I2_E_BADARG;   // the last run did not compute the defects
+            I2_CUDA(cudaMemcpyAsync(hErrors, c->hErrors[cls], sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+        }
+    }
+    I2_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
 int i2_host_run(i2_context *c, int level, int *const hTasks[3], double *const hResults[3], double *const hErrors[3],
                 unsigned char *const hRefinements[3], i2_stats hStats[3]) {
     if (!c) return I2_E_BADARG;
-    if (!c->hVerts) return I2_E_NOMESH;
+    if (!c->hPrepared) return I2_E_NOMESH;
     if (!c->haveQuad) return I2_E_NOQUAD;
     if (level > 12) return I2_E_LEVEL;
     I2_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = c->stream, cs = c->copyStream;
     if (hStats) std::memset(hStats, 0, 3 * sizeof(i2_stats));
+    for (int k = 0; k < 3; ++k) c->hResultsTarget[k] = nullptr;   // the single-context entry point always uses its own buffers
+    bool wantErrors = false;
+    for (int k = 0; k < 3; ++k) wantErrors = wantErrors || (hErrors && hErrors[k]);
+    const long long n2 = c->hN[2];
+    const bool copyOut2 = (hResults && hResults[2]) || (hTasks && hTasks[2]);
 
-    // one whole class on stream st: integration, optional (i,j)/(j,i) defect, device-to-host copies; no synchronisation
-    // device views of this context's shard of class k
-    auto dTasks = [&](int k) { return c->hTasks[k] + 3 * c->hLo[k]; };
-    auto dIntegrals = [&](int k) { return c->hIntegrals[k] + 4 * c->hLo[k]; };
-    auto dResults = [&](int k) { return c->hResults[k] + 3 * c->hLo[k]; };
-    auto whole = [&](int k, cudaStream_t st) -> int {
+    auto copies = [&](int k, cudaStream_t st) -> int {
         const long long n = c->hN[k];
-        int rc = enqueue_class(c, k, dTasks(k), n, level, dIntegrals(k), dResults(k), level < 0 ? c->hRefinements[k] : nullptr,
-                               nullptr, st, false);
-        if (rc) return rc;
-        if (hErrors && hErrors[k]) {
-            if (c->shardWorld > 1) return I2_E_BADARG;   // the (i,j)/(j,i) defect pairs slot t with slot n/2 + t: whole lists only
-            rc = ensure(&c->hErrors[k], &c->capErrors[k], (size_t)n);
-            if (rc) return rc;
-            launch_symmetry_error(c->hResults[k], n / 2, c->hErrors[k], st);
-            I2_CUDA(cudaGetLastError());
-            I2_CUDA(cudaMemcpyAsync(hErrors[k], c->hErrors[k], sizeof(double) * n, cudaMemcpyDeviceToHost, st));
-        }
-        if (hResults && hResults[k])
-            I2_CUDA(cudaMemcpyAsync(hResults[k], dResults(k), sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, st));
-        if (hTasks && hTasks[k])
-            I2_CUDA(cudaMemcpyAsync(hTasks[k], dTasks(k), sizeof(int) * 3 * n, cudaMemcpyDeviceToHost, st));
-        if (level < 0 && hRefinements && hRefinements[k])
-            I2_CUDA(cudaMemcpyAsync(hRefinements[k], c->hRefinements[k], c->nc, cudaMemcpyDeviceToHost, st));
+        if (n == 0) return 0;
+        if (hErrors && hErrors[k]) I2_CUDA(cudaMemcpyAsync(hErrors[k], c->hErrors[k], sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+        if (hResults && hResults[k]) I2_CUDA(cudaMemcpyAsync(hResults[k], c->hResults[k], sizeof(double) * 3 * n, cudaMemcpyDeviceToHost, st));
+        if (hTasks && hTasks[k]) I2_CUDA(cudaMemcpyAsync(hTasks[k], c->hTasks[k], sizeof(int) * 3 * n, cudaMemcpyDeviceToHost, st));
         return 0;
     };
 
-    // fork: the adjacent classes run on the side streams, concurrently with the regular class on the context's stream
-    I2_CUDA(cudaEventRecord(c->forkEv, s));
-    for (int k = 0; k < 2; ++k) {
-        cudaStream_t st = c->side[k];
-        I2_CUDA(cudaStreamWaitEvent(st, c->forkEv, 0));
-        if (level < 0) I2_CUDA(cudaMemsetAsync(c->hRefinements[k], 0, c->nc, st));
-        if (c->hN[k] > 0) {
-            const int rc = whole(k, st);
-            if (rc) return rc;
-        }
-        I2_CUDA(cudaEventRecord(c->sideDone[k], st));
-    }
-    {
-        const int k = 2;
-        const long long n = c->hN[k];
-        if (level < 0) I2_CUDA(cudaMemsetAsync(c->hRefinements[k], 0, c->nc, s));
-        const bool wantErr = hErrors && hErrors[k];
-        if (n > 0 && level >= 0 && !wantErr) {
-            // fixed level: tasks are independent -> integrate chunk by chunk, copy each finished chunk on the copy stream
-            const long long chunkTasks = 1LL << 24;  // 16 Mi tasks: 384 MiB of Point3 per chunk
-            const bool copyOut = (hResults && hResults[k]) || (hTasks && hTasks[k]);
-            int turn = 0;
-            for (long long off = 0; off < n; off += copyOut ? chunkTasks : n) {
-                const long long m = !copyOut ? n : ((n - off < chunkTasks) ? (n - off) : chunkTasks);
-                int rc = enqueue_class(c, k, dTasks(k) + 3 * off, m, level, dIntegrals(k) + 4 * off, dResults(k) + 3 * off,
-                                       nullptr, nullptr, s, false);
+    if (level >= 0 && !wantErrors && copyOut2 && n2 > 0) {
+        // fixed level, per-pair results wanted on the host: tasks are independent -> the regular class is integrated chunk by
+        // chunk and every finished chunk travels on the copy stream while the next one computes.  Chunks are cut inside each of
+        // the two segments at multiples of 32 tasks, so they reproduce the warp groups (and the bits) of the unchunked run.
+        I2_CUDA(cudaEventRecord(c->forkEv, s));
+        for (int k = 0; k < 2; ++k) {
+            cudaStream_t st = c->side[k];
+            I2_CUDA(cudaStreamWaitEvent(st, c->forkEv, 0));
+            if (c->hN[k] > 0) {
+                int rc = enqueue_class(c, k, c->hTasks[k], c->hN[k], level, c->hIntegrals[k], c->hResults[k], nullptr, nullptr, st, false, c->hHalf[k]);
+                if (!rc) rc = copies(k, st);
                 if (rc) return rc;
-                if (!copyOut) break;
+            }
+            I2_CUDA(cudaEventRecord(c->sideDone[k], st));
+        }
+        const long long chunkTasks = 1LL << 24;  // 16 Mi tasks: 384 MiB of Point3 per chunk
+        int turn = 0;
+        for (int seg = 0; seg < 2; ++seg) {
+            const long long segLo = seg ? c->hHalf[2] : 0, segHi = seg ? n2 : c->hHalf[2];
+            for (long long off = segLo; off < segHi; off += chunkTasks) {
+                const long long m = segHi - off < chunkTasks ? segHi - off : chunkTasks;
+                int rc = enqueue_class(c, 2, c->hTasks[2] + 3 * off, m, level, c->hIntegrals[2] + 4 * off, c->hResults[2] + 3 * off, nullptr,
+                                       nullptr, s, false);
+                if (rc) return rc;
                 I2_CUDA(cudaEventRecord(c->chunkDone[turn], s));
                 I2_CUDA(cudaStreamWaitEvent(cs, c->chunkDone[turn], 0));
                 turn ^= 1;
-                if (hResults && hResults[k])
-                    I2_CUDA(cudaMemcpyAsync(hResults[k] + 3 * off, dResults(k) + 3 * off, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost, cs));
-                if (hTasks && hTasks[k])
-                    I2_CUDA(cudaMemcpyAsync(hTasks[k] + 3 * off, dTasks(k) + 3 * off, sizeof(int) * 3 * m, cudaMemcpyDeviceToHost, cs));
+                if (hResults && hResults[2])
+                    I2_CUDA(cudaMemcpyAsync(hResults[2] + 3 * off, c->hResults[2] + 3 * off, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost, cs));
+                if (hTasks && hTasks[2])
+                    I2_CUDA(cudaMemcpyAsync(hTasks[2] + 3 * off, c->hTasks[2] + 3 * off, sizeof(int) * 3 * m, cudaMemcpyDeviceToHost, cs));
             }
-        } else if (n > 0) {
-            const int rc = whole(k, s);
-            if (rc) return rc;
         }
+        for (int k = 0; k < 2; ++k) I2_CUDA(cudaStreamWaitEvent(s, c->sideDone[k], 0));   // join
+    } else {
+        int rc = i2::host_run_rounds(c, level);
+        if (!rc) rc = i2::host_run_finalize(c, level, wantErrors);
+        for (int k = 0; k < 3 && !rc; ++k) rc = copies(k, s);
+        if (rc) return rc;
+        if (level < 0 && hRefinements)
+            for (int k = 0; k < 3; ++k)
+                if (hRefinements[k]) I2_CUDA(cudaMemcpyAsync(hRefinements[k], c->hRefinements[k], c->nc, cudaMemcpyDeviceToHost, s));
     }
-    for (int k = 0; k < 2; ++k) I2_CUDA(cudaStreamWaitEvent(s, c->sideDone[k], 0));   // join
     QueueState h[3];
     if (hStats)
         for (int k = 0; k < 3; ++k)

@@ -21,7 +21,7 @@
 
 namespace i2 {
 
-long long g_launchCount = 0;
+std::atomic<long long> g_launchCount{0};
 
 // Gauss rule in constant memory: (L_x, L_y, L_z, w) per point, broadcast to all lanes.
 __constant__ double c_gauss[MAX_GAUSS_POINTS * 4];
@@ -349,8 +349,12 @@ static __device__ __forceinline__ int raise_flag(int flagged, const PointTerms &
 // only raises a sticky flag, and ONE __all_sync per group of equal weights decides whether the warp redoes the group point
 // by point in the careful form.
 // MS = distance (in doubles) between consecutive components of the staged points (kThreads when every thread has its own set)
+// vmask = the lanes that decide together (the whole warp, or the 16 lanes of one task in the list-driven round 2 of the
+// adaptive queue, where the two tasks that share a warp depend on which other tasks are still unconverged: a task's
+// result must not depend on its warp-mate, or it would change with the partition of the list over GPUs)
 template <bool EDGELEN, bool RESID, bool DERIVE = false, bool PROJ = false, int MS = kThreads>
-static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, const TriJ &T, double &a1, double &a2, double &a3, double &a4) {
+static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, const TriJ &T, double &a1, double &a2, double &a3, double &a4,
+                                                    const unsigned vmask = 0xffffffffu) {
     a1 = 0.0; a2 = 0.0; a3 = 0.0; a4 = 0.0;
     const int ngroups = c_ngroups;
     int g = 0;
@@ -381,8 +385,8 @@ static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, c
         g = gEnd;
         const double w = c_gauss[4 * gStart + 3], w2 = w + w;
         double th;
-        if (__all_sync(0xffffffffu, !flagged)) {
-            const int am = __reduce_min_sync(0xffffffffu, angle_margin(zi, zr));   // far-field tiers, taken by the whole warp
+        if (__all_sync(vmask, !flagged)) {
+            const int am = __reduce_min_sync(vmask, angle_margin(zi, zr));   // far-field tiers, taken by the whole warp
             if (am >= kAngleFar) th = atan_series<4, RESID>(zi, zr);
             else if (am >= kAngleTiny) th = atan_series<9, RESID>(zi, zr);
             else th = atan2_fast<RESID>(zi, zr);
@@ -400,7 +404,7 @@ static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, c
         }
         // far-field tiers, taken by the whole warp: all three ratios close enough to 1 -> no mantissa surgery, shorter series
         const double sa = pn1 + pd1, da_ = pn1 - pd1, sb = pn2 + pd2, db_ = pn2 - pd2, sc_ = pn3 + pd3, dc_ = pn3 - pd3;
-        const int rm = __reduce_min_sync(0xffffffffu, min(ratio_margin(sa, da_), min(ratio_margin(sb, db_), ratio_margin(sc_, dc_))));
+        const int rm = __reduce_min_sync(vmask, min(ratio_margin(sa, da_), min(ratio_margin(sb, db_), ratio_margin(sc_, dc_))));
         if (rm >= kMarginVeryFar) {
             a1 = fma(w2, atanh_series<3, RESID>(sa, da_), a1);
             a2 = fma(w2, atanh_series<3, RESID>(sb, db_), a2);
@@ -437,8 +441,9 @@ static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, c
 template <int MINB, int VAR>
 __global__ void __launch_bounds__(kThreads, MINB)
 k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__restrict__ list, const int *__restrict__ countDev,
-                  long long countHost, int level, double *__restrict__ out, double *__restrict__ results) {
+                  long long countHost, long long half, int level, double *__restrict__ out, double *__restrict__ results) {
     __shared__ double smM[MAX_GAUSS_POINTS * 3 * kThreads];
+    __shared__ double smJ[kThreads / 32][96];   // one warp's 32 results, staged for 16-byte coalesced stores
     const long long count = countDev ? (long long)*countDev : countHost;
     constexpr bool EDGELEN = (VAR & 1) != 0, RESID = (VAR & 2) == 0, LEVEL0 = (VAR & 4) != 0, DERIVE = (VAR & 8) != 0 && EDGELEN;
     constexpr bool PROJ = (VAR & 16) != 0 && DERIVE;
@@ -453,6 +458,8 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
     __shared__ double red[kThreads / 32][4];
 
     // per-lane partial (Psi, Theta) of task (i, j) over this lane's children; iStaged remembers whose Gauss points sit in smem
+    // list-driven rounds with two tasks per warp: each task's 16 lanes vote on their own (see grouped_eval)
+    const unsigned vmask = (list && G == 16) ? (lane < 16 ? 0x0000ffffu : 0xffff0000u) : 0xffffffffu;
     auto lane_work = [&](int i, int j, int sub, int &iStaged) -> d4 {
         double Si = __ldg(tri + PK_S * stride + i);
         for (int l = 0; l < level; ++l) Si *= 0.25;
@@ -479,7 +486,7 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
                 iStaged = perLane > 1 ? -1 : i;
             }
             double a1, a2, a3, a4;
-            grouped_eval<EDGELEN, RESID, DERIVE, PROJ>(myM, ng, T, a1, a2, a3, a4);
+            grouped_eval<EDGELEN, RESID, DERIVE, PROJ>(myM, ng, T, a1, a2, a3, a4, vmask);
             if (LEVEL0) { s1 = Si * a1; s2 = Si * a2; s3 = Si * a3; s4 = Si * a4; }
             else { s1 = fma(Si, a1, s1); s2 = fma(Si, a2, s2); s3 = fma(Si, a3, s3); s4 = fma(Si, a4, s4); }
         }
@@ -494,6 +501,29 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
             results[3 * (long long)slot] = J.x; results[3 * (long long)slot + 1] = J.y; results[3 * (long long)slot + 2] = J.z;
         }
     };
+    // the same for a warp whose 32 lanes hold the 32 consecutive slots slot0 .. slot0+31 (level 0, no list): the 768 bytes of
+    // results leave as 48 16-byte stores instead of 96 strided 8-byte ones — full sectors, which is what a store into another
+    // GPU's memory over NVLink (multi-GPU export, i2_peer_*) needs to reach the link's bandwidth
+    auto store_warp = [&](int slot0, int j, d4 total) {
+        double2 *o = reinterpret_cast<double2 *>(out + 4 * (long long)(slot0 + lane));
+        o[0] = make_double2(total.x, total.y);
+        o[1] = make_double2(total.z, total.w);
+        const d3 J = assemble_J(total, ld3(tri + PK_N * stride, stride, j), 0.0, false);
+        double *sj = smJ[warp];
+        sj[3 * lane] = J.x; sj[3 * lane + 1] = J.y; sj[3 * lane + 2] = J.z;
+        __syncwarp();
+        double *dst = results + 3 * (long long)slot0;
+        const int mis = (int)((reinterpret_cast<unsigned long long>(dst) >> 3) & 1ull);   // first element not 16-byte aligned: peel it
+#pragma unroll
+        for (int k = lane; k < 48; k += 32) {
+            const int e = mis + 2 * k;
+            if (e + 1 < 96) *reinterpret_cast<double2 *>(dst + e) = make_double2(sj[e], sj[e + 1]);
+        }
+        if (mis && lane == 0) dst[0] = sj[0];
+        if (mis && lane == 1) dst[95] = sj[95];
+        __syncwarp();
+    };
+    const bool vecStores = results && !list && G == 1;
 
     if (G <= 32) {
         // A warp walks a contiguous chunk of kChunkIters x (32/G) tasks: lists are sorted by control panel i, so a lane meets
@@ -504,18 +534,28 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
         const long long warpId = ((long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
         const long long warpStride = ((long long)gridDim.x * kThreads) >> 5;
         const long long chunkTasks = (long long)groupsPerWarp * kChunkIters;
+        // `half` > 0: the list is two segments, slots [0, half) and [half, count) (pairs and reversed pairs of
+        // Evaluator3D::runAllPairs); the second segment starts a new warp iteration, so which tasks decide together depends
+        // only on a task's position inside its segment — a shard made of 32-aligned pieces of both segments
+        // (i2_host_set_shard, i2_mgpu_*) reproduces the unsharded run bit for bit.
+        const long long H = list ? 0 : half;
+        const long long P1 = (H + groupsPerWarp - 1) / groupsPerWarp * groupsPerWarp;   // first segment, padded to whole iterations
+        const long long padded = P1 + (count - H);
         int iStaged = -1;
-        for (long long chunk = warpId; chunk * chunkTasks < count; chunk += warpStride)
+        for (long long chunk = warpId; chunk * chunkTasks < padded; chunk += warpStride)
             for (int it = 0; it < kChunkIters; ++it) {
                 const long long base = chunk * chunkTasks + (long long)it * groupsPerWarp;
-                if (base >= count) break;
-                long long r = base + lane / G;
-                const bool active = r < count;
-                if (!active) r = count - 1;   // tail lanes recompute the last task (no write) so that warp votes stay full-mask
+                if (base >= padded) break;
+                const long long q = base + lane / G;
+                long long r = q < P1 ? q : H + (q - P1);
+                const long long segEnd = q < P1 ? H : count;
+                const bool active = r < segEnd;
+                if (!active) r = segEnd - 1;   // tail lanes recompute the segment's last task (no write) so that warp votes stay full-mask
                 const int slot = list ? __ldg(list + r) : (int)r;
                 const int i = __ldg(tasks + 3 * (long long)slot), j = __ldg(tasks + 3 * (long long)slot + 1);
                 const d4 total = warp_sum(lane_work(i, j, sub, iStaged), G);
-                if (active && sub == 0) store(slot, j, total);
+                if (vecStores && __all_sync(0xffffffffu, active)) store_warp(slot - lane, j, total);
+                else if (active && sub == 0) store(slot, j, total);
             }
     } else {
         // deep refinement: the lanes of one task span G/32 warps of the CTA (see LaneLayout)
@@ -669,6 +709,7 @@ void launch_apply_regular(const PackedMesh &pm, int rowLo, int rowHi, int colLo,
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kAdRows = kThreads / 4;
 constexpr int kAdTileJ = 16;
+constexpr size_t kAdaptiveSmemBytes = sizeof(double) * (MAX_GAUSS_POINTS * 3 * (kThreads + kAdRows) + kAdTileJ * kTileStride);
 
 struct ApplyAdaptiveOut {
     double *partial;             // [chunks][rows][6]: accE.xyz, accO.xyz
@@ -910,11 +951,17 @@ void launch_apply_regular_adaptive(const PackedMesh &pm, int rowLo, int rowHi, i
     const int colChunk = (cols + chunks - 1) / chunks;
     dim3 grid((rows + kAdRows - 1) / kAdRows, chunks);
     ApplyAdaptiveOut o{partial6, depth, lastRound, counts6};
-    constexpr size_t smem = sizeof(double) * (MAX_GAUSS_POINTS * 3 * (kThreads + kAdRows) + kAdTileJ * kTileStride);
-    static const cudaError_t attr = cudaFuncSetAttribute(k_apply_regular_adaptive<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    (void)attr;
+    constexpr size_t smem = kAdaptiveSmemBytes;
     ++g_launchCount;
     k_apply_regular_adaptive<3><<<grid, kThreads, smem, s>>>(pm, rowLo, rowHi, colLo, colHi, colChunk, weights, o);
+    if (out3) launch_reduce_partials_adaptive(partial6, depth, rows, chunks, lastRound, out3, other3, refinements, s);
+}
+
+// second half of the list-free adaptive pass: picks, per row, the candidate selected by the parity of *lastRound — a multi-GPU
+// caller runs the first half with out3 == nullptr, agrees on the last round (maximum over the GPUs) and then calls this
+void launch_reduce_partials_adaptive(const double *partial6, const unsigned char *depth, int rows, int chunks, const int *lastRound, double *out3,
+                                     double *other3, unsigned char *refinements, cudaStream_t s) {
+    if (rows <= 0) return;
     ++g_launchCount;
     k_reduce_partials_adaptive<<<(rows * 3 + 255) / 256, 256, 0, s>>>(partial6, depth, rows, chunks, lastRound, out3, other3, refinements);
 }
@@ -924,7 +971,7 @@ static int g_minBlocks = [] { const char *e = getenv("I2_MINBLOCKS"); return e ?
 static int g_variant = [] { const char *e = getenv("I2_VARIANT"); return e ? atoi(e) : 27; }();
 
 void launch_integrate(int cls, int mathMode, const PackedMesh &pm, const int *tasks, const int *list, const int *countDev,
-                      long long countHost, int level, double *out4, double *fusedResults3, int numSMs, cudaStream_t s) {
+                      long long countHost, long long half, int level, double *out4, double *fusedResults3, int numSMs, cudaStream_t s) {
     if (!countDev && countHost <= 0) return;
     const int children = 1 << (2 * level);
     const int G = children < kThreads ? children : kThreads;   // LaneLayout
@@ -947,7 +994,7 @@ void launch_integrate(int cls, int mathMode, const PackedMesh &pm, const int *ta
         // the LEVEL0 specialisation (bit 2) is chosen automatically
         const int var = (g_variant & 3) | (level == 0 ? 4 : 0) | (g_variant & 24);
         ++g_launchCount;
-#define I2_LAUNCH_GROUPED(MB, V) k_regular_grouped<MB, V><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4, fusedResults3)
+#define I2_LAUNCH_GROUPED(MB, V) k_regular_grouped<MB, V><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, half, level, out4, fusedResults3)
 #define I2_PICK_VAR(MB)                                                                                              \
         switch (var) {                                                                                           \
         case 0: I2_LAUNCH_GROUPED(MB, 0); break; case 1: I2_LAUNCH_GROUPED(MB, 1); break;                       \
@@ -981,7 +1028,8 @@ cudaError_t preload_kernels() {
     I2_TOUCH(k_apply_regular<4>);
     I2_TOUCH(k_apply_regular_adaptive<3>);
 #undef I2_TOUCH
-    return cudaSuccess;
+    // function attributes are per device: opt in to > 48 KB of dynamic shared memory on the device of the calling context
+    return cudaFuncSetAttribute(k_apply_regular_adaptive<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAdaptiveSmemBytes);
 }
 
 // ---------------------------------------------------------------------------------------------------------

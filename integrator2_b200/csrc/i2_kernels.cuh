@@ -1,6 +1,7 @@
 // Kernel-side declarations shared by i2_kernels.cu (device code) and i2_abi.cu (C-ABI entry points).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include "i2_vec.cuh"
 
 namespace i2 {
@@ -36,7 +37,7 @@ struct QueueState {
     int orientationWarnings;
 };
 
-extern long long g_launchCount;       // kernels launched by the launch_* wrappers (bench.py's gpu_launches)
+extern std::atomic<long long> g_launchCount;       // kernels launched by the launch_* wrappers (bench.py's gpu_launches)
 constexpr int kThreads = 128;          // CTA size of the integrate kernels
 
 // math mode of the regular-pair point function
@@ -48,14 +49,18 @@ void launch_geometry(const double *verts, const int *cells, int nc, double *norm
                      cudaStream_t s);
 // regular part of `count` tasks at uniform refinement `level`; list==nullptr -> task slots 0..count-1,
 // otherwise slots list[0..*countDev-1] (device-side count, persistent grid)
+// half > 0 (only with list == nullptr): the tasks are two segments [0, half) and [half, count) whose warp groups are formed
+// independently (pairs / reversed pairs of runAllPairs), see k_regular_grouped
 void launch_integrate(int cls, int mathMode, const PackedMesh &pm, const int *tasks, const int *list, const int *countDev,
-                      long long countHost, int level, double *out4, double *fusedResults3, int numSMs, cudaStream_t s);
+                      long long countHost, long long half, int level, double *out4, double *fusedResults3, int numSMs, cudaStream_t s);
 void launch_apply_regular(const PackedMesh &pm, int rowLo, int rowHi, int colLo, int colHi, int chunks, const double *weights,
                           double *partial, double *out3, cudaStream_t s);
 // list-free regular class with the Runge loop per pair (see k_apply_regular_adaptive)
 void launch_apply_regular_adaptive(const PackedMesh &pm, int rowLo, int rowHi, int colLo, int colHi, int chunks, const double *weights,
                                    double *partial6, unsigned char *depth, int *lastRound, unsigned long long *counts6, double *out3,
                                    double *other3, unsigned char *refinements, cudaStream_t s);
+void launch_reduce_partials_adaptive(const double *partial6, const unsigned char *depth, int rows, int chunks, const int *lastRound, double *out3,
+                                     double *other3, unsigned char *refinements, cudaStream_t s);
 void launch_checksum(const double *results3, long long n, double *sums4, int numSMs, cudaStream_t s);
 // Runge comparison of round `round` + deterministic compaction of the unconverged slots: staging = int[capacity of the list]
 // (per-CTA segments), blockCnt = int[kCompareMaxBlocks], listOut = dense list in input order, *countOut = its length
@@ -75,6 +80,23 @@ void launch_classify_fill(const int *cells, int nc, const unsigned long long *ro
                           int *not3, cudaStream_t s);
 void launch_split_uniform(const double *vin, int nvIn, const int *cin, int ncIn, const double *min, double *vout, int *cout,
                           double *mout, cudaStream_t s);
+// classification by vertex incidence + sharded task lists (i2_prepare.cu)
+size_t incidence_scratch_ints(int nv, int nc);
+// incidence, per-row partner counts, rowOff[3][nc + 1] (first slot of every row per class, last entry = total), totals[3]
+void launch_incidence(const int *cells, int nv, int nc, int *scratch, unsigned long long *rowOff, unsigned long long *totals, cudaStream_t s);
+void launch_partners_fill(const int *cells, int nv, int nc, const int *scratch, const unsigned long long *rowOff, int *simple, int *attached,
+                          bool reversed, cudaStream_t s);
+void launch_regular_fill(const int *cells, int nc, const unsigned long long *rowOff, unsigned long long fLo, unsigned long long fHi, int *out,
+                         int *outRev, int numSMs, cudaStream_t s);
+void launch_row_cost(const PackedMesh &pm, bool upperOnly, double *cost, cudaStream_t s);
+// row-major adjacent lists for the operator apply (all partners j != i of the rows of a block, sorted by (i, j))
+size_t rows_scratch_ints(int nc);
+void launch_partners_both(const int *cells, int nv, int nc, const int *scratch, int *scratch2, cudaStream_t s);
+void launch_partners_fill_rows(const int *cells, int nv, int nc, const int *scratch, const int *scratch2, int rowLo, int rowHi, int *simple,
+                               int *attached, cudaStream_t s);
+void launch_row_scatter(const int *tasks, const double *results, const int *off, int rowLo, int rows, const double *weights, double *out,
+                        cudaStream_t s);
+void launch_take_rows(const unsigned char *perCell, int rowLo, int rows, unsigned char *out, cudaStream_t s);
 void launch_selftest_math(int op, const double *a, const double *b, long long n, double *out, cudaStream_t s);
 cudaError_t upload_math_tables(cudaStream_t s);
 cudaError_t preload_kernels();

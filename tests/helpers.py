@@ -1,7 +1,7 @@
 """Shared helpers of the parity tests: error measures and the conditioning-aware tolerance.
 
 Tolerance statement (DESIGN.md "Parity"): per ordered pair
-    |J_new - J_ref|_1  <=  1e-12 * |J_ref|_1  +  K * noise_ij ,   K = 8
+    |J_new - J_ref|_1  <=  1e-12 * |J_ref|_1  +  K * noise_ij ,   K = 2
 where noise_ij is a first-order bound of the rounding noise of the REFERENCE's own formula
 (thetaPsi, /root/reference/src/evaluators/evaluatorJ3DK.cu:266-313) for that pair.  The second term is needed
 because the reference evaluates ln[l_a(1+cos)/(l_b(1+cos))] and a triple product of unit vectors: both lose
@@ -11,9 +11,41 @@ noise_ij << 1e-12 |J| and the test is the plain 1e-12 relative bound of BASELINE
 """
 import numpy as np
 
+import json
+import os
+
 U = 2.0 ** -53
-K_NOISE = 8.0
+K_NOISE = 2.0
 REL_TOL = 1e-12
+
+# every parity check records what it observed (how much of the tolerance was used, what fraction meets the plain 1e-12 bound):
+# written by tests/conftest.py at the end of a GPU session to gpurun_out/r02_parity.json (copied to profiles/ for the record)
+PARITY_LOG = {}
+
+
+def record_parity(label, stats):
+    if label:
+        PARITY_LOG[label] = stats
+
+
+def write_parity_log():
+    if not PARITY_LOG:
+        return None
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out_dir = os.path.join(root, "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    path = os.path.join(out_dir, "r02_parity.json")
+    old = {}
+    if os.path.exists(path):
+        try:
+            old = json.load(open(path))
+        except Exception:  # noqa: BLE001
+            old = {}
+    old.update(PARITY_LOG)
+    old["_tolerance"] = {"statement": "|J_new - J_ref|_1 <= 1e-12 |J_ref|_1 + K noise_ij", "K_NOISE_regular": K_NOISE,
+                         "K_PERTURB_adjacent": K_PERTURB}
+    json.dump(old, open(path, "w"), indent=1, sort_keys=True)
+    return path
 
 QF13_XY = None
 
@@ -30,18 +62,33 @@ def rel_err_l1(a, b):
     return np.abs(a - b).sum(1) / np.maximum(np.abs(b).sum(1), 1e-300)
 
 
-def reference_noise_bound(vertices, cells, tasks):
-    """First-order rounding-noise bound (absolute, on |J|_1) of the reference formula for regular pairs."""
-    L, w = _qf()
+def reference_noise_bound(vertices, cells, tasks, level=0):
+    """First-order rounding-noise bound (absolute, on |J|_1) of the reference formula for regular pairs; at a refinement level
+    > 0 the bound is the sum of the bounds of the 4^level children of the control panel (their own Gauss points and areas)."""
     i, j = tasks[:, 0], tasks[:, 1]
     VI = vertices[cells[i]]          # [n,3,3]
     VJ = vertices[cells[j]]
+    if level > 0:
+        kids = [VI]
+        for _ in range(level):       # children as the reference creates them (src/NumericalIntegrator3d.cu:55-65)
+            nxt = []
+            for T in kids:
+                A, B, C = T[:, 0], T[:, 1], T[:, 2]
+                ma, mb, mc = 0.5 * (B + C), 0.5 * (C + A), 0.5 * (A + B)
+                nxt += [np.stack([mc, B, ma], 1), np.stack([ma, C, mb], 1), np.stack([mb, A, mc], 1), np.stack([ma, mb, mc], 1)]
+            kids = nxt
+        return sum(_noise_bound_panels(T, VJ) for T in kids)
+    return _noise_bound_panels(VI, VJ)
+
+
+def _noise_bound_panels(VI, VJ):
+    L, w = _qf()
     A, B, C = VJ[:, 0], VJ[:, 1], VJ[:, 2]
     Si = 0.5 * np.linalg.norm(np.cross(VI[:, 1] - VI[:, 0], VI[:, 2] - VI[:, 0]), axis=1)
     def unit(v):
         return v / np.linalg.norm(v, axis=1, keepdims=True)
     ta, tb, tc = unit(C - B), unit(A - C), unit(B - A)
-    acc = np.zeros(tasks.shape[0])
+    acc = np.zeros(VI.shape[0])
     for g in range(L.shape[0]):
         M = L[g, 0] * VI[:, 0] + L[g, 1] * VI[:, 1] + L[g, 2] * VI[:, 2]
         oa, ob, oc = unit(M - A), unit(M - B), unit(M - C)
@@ -67,6 +114,7 @@ def check_regular_parity(vertices, cells, tasks, J_new, J_ref, label=""):
     stats = dict(n=int(tasks.shape[0]), rel_median=float(np.median(rel)), rel_p99=float(np.quantile(rel, 0.99)),
                  rel_max=float(rel.max()), frac_within_1e12=float((rel <= REL_TOL).mean()),
                  worst_ratio_to_allowed=float((err / allowed).max()))
+    record_parity(label, stats)
     bad = np.nonzero(err > allowed)[0]
     assert bad.size == 0, f"{label}: {bad.size} pairs outside tolerance, worst {stats}; first bad task {tasks[bad[0]]}"
     return stats
@@ -126,7 +174,7 @@ def perturbation_noise(oracle, vertices, cells, cls, tasks, level, trials=8, see
     return worst, base
 
 
-K_PERTURB = 32.0
+K_PERTURB = 8.0
 
 
 def check_parity_perturbation(oracle, vertices, cells, cls, tasks, level, J_new, J_ref=None, label="", max_outliers=0):
@@ -140,10 +188,11 @@ def check_parity_perturbation(oracle, vertices, cells, cls, tasks, level, J_new,
     ref = np.abs(J_ref).sum(1)
     allowed = REL_TOL * ref + K_PERTURB * noise
     rel = err / np.maximum(ref, 1e-300)
-    stats = dict(n=int(tasks.shape[0]), rel_median=float(np.median(rel)), rel_max=float(rel.max()),
+    stats = dict(n=int(tasks.shape[0]), rel_median=float(np.median(rel)), rel_p99=float(np.quantile(rel, 0.99)), rel_max=float(rel.max()),
                  frac_within_1e12=float((rel <= REL_TOL).mean()), worst_ratio_to_allowed=float((err / allowed).max()))
     bad = np.nonzero(err > allowed)[0]
     stats["outliers"] = int(bad.size)
+    record_parity(label, stats)
     assert bad.size <= max_outliers, f"{label}: {bad.size} pairs outside tolerance {stats}; first bad task {tasks[bad[0]]}"
     if bad.size:
         assert rel[bad].max() < 1e-5, f"{label}: outlier too large {stats}"

@@ -8,7 +8,7 @@ from conftest import ROOT
 
 def _declared():
     text = open(os.path.join(ROOT, "include", "i2_abi.h")).read()
-    return sorted(set(re.findall(r"^(?:int|const char \*)\s*\*?\s*(i2_[a-z0-9_]+)\s*\(", text, flags=re.M)))
+    return sorted(set(re.findall(r"^(?:int|const char \*|i2_context \*)\s*\*?\s*(i2_[a-z0-9_]+)\s*\(", text, flags=re.M)))
 
 
 def test_header_declares_the_hot_path_entry_points():
@@ -59,7 +59,7 @@ def test_ctypes_binding_matches_the_header_prototypes():
     L = abi.load_library()
     text = open(os.path.join(ROOT, "include", "i2_abi.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    protos = re.findall(r"(?:int|const char \*)\s*\*?\s*(i2_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S)
+    protos = re.findall(r"(?:int|const char \*|i2_context \*)\s*\*?\s*(i2_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S)
     assert len(protos) == len(_declared())
     for name, params in protos:
         params = " ".join(params.split())

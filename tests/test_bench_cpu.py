@@ -42,3 +42,12 @@ def test_reference_arm_prints_the_contract_line_without_a_gpu():
     assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
     assert np.isfinite(line["value"]) and line["value"] > 0
+
+
+def test_reference_command_never_passes_a_negative_level():
+    """Automatic error control is the ABSENCE of -r in the reference CLI (tests/integrator3D/main.cu:114-123)."""
+    import bench
+    assert bench.reference_command("bin", "m.dat", 1.0, 0) == ["bin", "-f", "m.dat", "-r", "0"]
+    assert bench.reference_command("bin", "m.dat", 0.0005, 2) == ["bin", "-f", "m.dat", "-s", "0.0005", "-r", "2"]
+    adaptive = bench.reference_command("bin", "m.dat", 0.0005, -1)
+    assert "-r" not in adaptive and adaptive == ["bin", "-f", "m.dat", "-s", "0.0005"]

@@ -121,7 +121,7 @@ def test_oracle_matches_reference_regular_pairs_with_noise_model(oracle, name):
     J = G[f"{name}.not.J"]
     mine = om.run_class(2, t, level_of(name))["results"]
     err = np.abs(mine - J).sum(1)
-    allowed = REL_TOL * np.abs(J).sum(1) + K_NOISE * reference_noise_bound(m.vertices, m.cells, t)
+    allowed = REL_TOL * np.abs(J).sum(1) + K_NOISE * reference_noise_bound(m.vertices, m.cells, t, level_of(name))
     assert (err <= allowed).all(), (name, float((err / allowed).max()))
 
 

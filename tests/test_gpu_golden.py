@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from conftest import ROOT
-from helpers import K_NOISE, REL_TOL, check_parity_perturbation, reference_noise_bound
+from helpers import K_NOISE, REL_TOL, check_parity_perturbation, record_parity, reference_noise_bound
 from test_golden_reference import CLS, G, META, TWO_TRI, dump_mesh, level_of, parse_rounds
 
 pytestmark = pytest.mark.gpu
@@ -45,11 +45,15 @@ def test_gpu_matches_reference_larger_meshes(ctx, oracle, name):
     r, J, t = _run(ctx, name, 2, level)
     Jr = G[f"{name}.not.J"]
     err = np.abs(J - Jr).sum(1)
-    allowed = REL_TOL * np.abs(Jr).sum(1) + K_NOISE * reference_noise_bound(m.vertices, m.cells, t)
+    allowed = REL_TOL * np.abs(Jr).sum(1) + K_NOISE * reference_noise_bound(m.vertices, m.cells, t, max(level, 0))
+    rel = err / np.abs(Jr).sum(1)
+    record_parity(f"{name} not vs reference dump", dict(n=int(t.shape[0]), rel_median=float(np.median(rel)), rel_p99=float(np.quantile(rel, 0.99)),
+                                                        rel_max=float(rel.max()), frac_within_1e12=float((rel <= REL_TOL).mean()),
+                                                        worst_ratio_to_allowed=float((err / allowed).max())))
     assert (err <= allowed).all(), (name, float((err / allowed).max()))
     for c in (0, 1):
         r, J, t = _run(ctx, name, c, level)
-        check_parity_perturbation(oracle, m.vertices, m.cells, c, t, level, J, J_ref=G[f"{name}.{CLS[c]}.J"], label=f"{name} {CLS[c]}")
+        check_parity_perturbation(oracle, m.vertices, m.cells, c, t, level, J, J_ref=G[f"{name}.{CLS[c]}.J"], label=f"{name} {CLS[c]} vs reference dump")
 
 
 @pytest.mark.parametrize("name", [n for n in TWO_TRI if n.endswith("_r0")])
@@ -109,6 +113,9 @@ def test_gpu_is_as_accurate_as_the_reference_against_exact(ctx, oracle, name):
     e_ref = np.abs(G[f"{name}.not.J"] - exact).sum(1) / scale
     print(name, "median gpu %.2e ref %.2e | p99 gpu %.2e ref %.2e | max gpu %.2e ref %.2e" %
           (np.median(e_gpu), np.median(e_ref), np.quantile(e_gpu, .99), np.quantile(e_ref, .99), e_gpu.max(), e_ref.max()))
+    record_parity(f"{name} not: distance to the exact (113-bit) value, product vs reference",
+                  dict(n=int(t.shape[0]), median=[float(np.median(e_gpu)), float(np.median(e_ref))], p99=[float(np.quantile(e_gpu, .99)), float(np.quantile(e_ref, .99))],
+                       max=[float(e_gpu.max()), float(e_ref.max())], frac_within_1e12=[float((e_gpu <= 1e-12).mean()), float((e_ref <= 1e-12).mean())]))
     assert np.median(e_gpu) <= 1.5 * np.median(e_ref) + 1e-15
     assert np.quantile(e_gpu, 0.99) <= 3.0 * np.quantile(e_ref, 0.99) + 1e-14
     assert np.quantile(e_gpu, 0.999) <= 5.0 * np.quantile(e_ref, 0.999) + 1e-13

@@ -6,7 +6,7 @@ bit-exact; FP64 results satisfy |dJ|_1 <= 1e-12 |J|_1 + 8 * noise_ij (helpers.py
 import numpy as np
 import pytest
 
-from helpers import check_parity_perturbation, check_regular_parity, reference_noise_bound, rel_err_l1
+from helpers import K_NOISE, check_parity_perturbation, check_regular_parity, reference_noise_bound, rel_err_l1
 from integrator2_b200.meshio import load_fixture
 
 pytestmark = pytest.mark.gpu
@@ -121,7 +121,7 @@ def test_adaptive_error_control(ctx, oracle, name, scale):
         for k in range(1, L + 1):
             d = abs(st["unconverged"][k] - int(rs[2 + 2 * k]))
             ties = max(ties, d)
-            assert d <= max(8, 0.15 * int(rs[2 + 2 * k])), (name, cls, k, st, rs.tolist())
+            assert d <= max(5, 4e-3 * int(rs[2 + 2 * k])), (name, cls, k, st, rs.tolist())
         if name == "G1":
             assert ties == 0
         refm = r["refinements"].cpu().numpy()
@@ -131,7 +131,7 @@ def test_adaptive_error_control(ctx, oracle, name, scale):
         rel_mean = err / np.maximum(refn, refn.mean())
         if cls == 2:
             # the level-0 noise model is only indicative for refined levels: bound the fraction beyond it
-            allowed = 1e-12 * refn + 8.0 * reference_noise_bound(m.vertices, m.cells, tasks)
+            allowed = 1e-12 * refn + K_NOISE * reference_noise_bound(m.vertices, m.cells, tasks)
             assert float((err > 4.0 * allowed).mean()) < 5e-5, (name, cls)
             outside = int((rel_mean > 1e-6).sum())
         else:
@@ -168,7 +168,7 @@ def test_host_buffer_entry_points(ctx, oracle):
         assert np.array_equal(ht[cls].numpy(), om.tasks(cls))
     ctx.set_mesh(m.vertices, m.cells)
     for cls in range(3):
-        r = ctx.integrate_class(cls, ht[cls].cuda(), 0)
+        r = ctx.integrate_pairs(cls, ht[cls].cuda(), 0)      # the list is runAllPairs-shaped: pairs ; reversed pairs
         assert np.array_equal(r["results"].cpu().numpy(), hr[cls].numpy()), cls
     # with the (i,j)/(j,i) defect and in adaptive mode
     href = [torch.zeros((m.n_cells,), dtype=torch.uint8, pin_memory=True) for _ in range(3)]
@@ -178,9 +178,13 @@ def test_host_buffer_entry_points(ctx, oracle):
     c2.close()
 
 
-def test_host_buffer_shards_tile_the_lists(ctx):
-    """i2_host_set_shard: the shards of a 3-way split (three contexts on one GPU standing in for three ranks) tile every
-    class without gaps or overlaps and reproduce the unsharded host run row by row, fixed level and adaptive."""
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_shards_reproduce_the_unsharded_run_bitwise(ctx, world):
+    """i2_host_set_shard: rank r owns the pairs with forward slots [lo_r, hi_r) (multiples of 32) in both orders.  The shards
+    tile every class and reproduce the unsharded run BIT FOR BIT — tasks, results and (i,j)/(j,i) defects, at fixed levels
+    and under error control — because warp groups are formed per half of the list from multiples of 32 and the list-driven
+    rounds of the work queue vote per task.  Several contexts on one GPU stand in for the ranks; what i2_mgpu_run exchanges
+    with NCCL (max of the last rounds and of the per-cell refinement counters) is exchanged by hand here."""
     import torch
     from integrator2_b200 import abi
     m = load_fixture("s5m", 0.0005)
@@ -189,36 +193,47 @@ def test_host_buffer_shards_tile_the_lists(ctx):
     assert whole.host_shard() == ([0, 0, 0], counts)
     ht = [torch.empty((n, 3), dtype=torch.int32, pin_memory=True) for n in counts]
     hr = [torch.empty((n, 3), dtype=torch.float64, pin_memory=True) for n in counts]
-    for level in (0, -1):
-        whole.host_run(level, ht, hr)
-        full_sums = whole.host_checksums()
-        world, nxt, sums = 3, [0, 0, 0], np.zeros((3, 4))
-        for rank in range(world):
-            c = abi.Context(0)
-            c.host_set_shard(rank, world)
-            assert c.host_prepare(m.vertices, m.cells) == counts
+    he = [torch.empty((n,), dtype=torch.float64, pin_memory=True) for n in counts]
+    href = [torch.zeros((m.n_cells,), dtype=torch.uint8, pin_memory=True) for _ in range(3)]
+    shards = []
+    for rank in range(world):
+        c = abi.Context(0)
+        c.host_set_shard(rank, world)
+        assert c.host_prepare(m.vertices, m.cells) == counts
+        shards.append(c)
+    # the forward ranges tile [0, pairs) and are 32-aligned
+    for k in range(3):
+        nxt = 0
+        for rank, c in enumerate(shards):
             first, cnt = c.host_shard()
-            assert first == nxt
-            st = [torch.empty((n, 3), dtype=torch.int32, pin_memory=True) for n in cnt]
-            sr = [torch.empty((n, 3), dtype=torch.float64, pin_memory=True) for n in cnt]
-            c.host_run(level, st, sr)
+            assert first[k] == nxt and first[k] % 32 == 0 and cnt[k] % 2 == 0
+            nxt += cnt[k] // 2
+        assert nxt == counts[k] // 2
+    for level in (0, 1, 2, -1):
+        stats = whole.host_run(level, ht, hr, he, href if level < 0 else None)
+        for c in shards:
+            c.host_run_rounds(level)
+        if level < 0:
+            L = np.max([c.host_last_rounds() for c in shards], axis=0).tolist()
+            assert L == [st["last_round"] for st in stats]
+            refs = np.max([c.host_refinements() for c in shards], axis=0)
+            for c in shards:
+                c.host_last_rounds(L)
+                c.host_refinements(refs)
             for k in range(3):
-                assert torch.equal(st[k], ht[k][first[k]:first[k] + cnt[k]]), (level, rank, k)
-                a, b = sr[k].numpy(), hr[k][first[k]:first[k] + cnt[k]].numpy()
-                # same kernels; the warp-mates of a pair change with the shard's first slot and the far-field tier of the group
-                # logs is chosen per warp, so ill-conditioned pairs see a different sample of the rounding noise: the tolerance
-                # statement of helpers.py applies (regular class), 1e-11 for the adjacent classes (no warp-wide decisions)
-                err, ref = np.abs(a - b).sum(1), np.abs(b).sum(1)
-                if k == 2:
-                    allowed = 1e-12 * ref + 8.0 * reference_noise_bound(m.vertices, m.cells, st[k].numpy())
-                else:
-                    allowed = 1e-11 * ref
-                assert float((err > allowed).mean()) <= (0.0 if level >= 0 else 1e-4), (level, rank, k, float((err / np.maximum(ref, 1e-300)).max()))
-            sums += c.host_checksums()
-            nxt = [first[k] + cnt[k] for k in range(3)]
-            c.close()
-        assert nxt == counts
-        assert (np.abs(sums - full_sums) <= 1e-9 * full_sums[:, 3:4]).all()     # signed sums cancel: scale = sum |J|_1 of the class
+                assert np.array_equal(refs[k], href[k].numpy()), (level, k)
+        for c in shards:
+            c.host_run_finalize(level, check=True)
+        for rank, c in enumerate(shards):
+            first, cnt = c.host_shard()
+            for k in range(3):
+                f = c.host_fetch(k, errors=True)
+                h, lo, P = cnt[k] // 2, first[k], counts[k] // 2
+                for name, whole_arr in (("tasks", ht[k].numpy()), ("results", hr[k].numpy()), ("errors", he[k].numpy())):
+                    assert np.array_equal(f[name][:h], whole_arr[lo:lo + h]), (level, rank, k, name, "pairs")
+                    assert np.array_equal(f[name][h:], whole_arr[P + lo:P + lo + h]), (level, rank, k, name, "reversed pairs")
+    for c in shards:
+        c.close()
     whole.close()
 
 
