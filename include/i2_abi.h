@@ -83,7 +83,10 @@ int i2_refine_mesh_once(i2_context *ctx, const double *d_vertices_in, int nv_in,
                         const double *d_measures_in, double *d_vertices_out, int *d_cells_out, double *d_measures_out);
 
 /* ---- neighbour classification: replaces kDetermineNeighborType (src/Mesh3d.cu:93-142, 243-262).
- *      Two passes so that the lists come out deterministic (lexicographic in (i,j), i<j, k = slot).       */
+ *      By vertex incidence: the partners of a triangle are the triangles listed under its three vertices (once = one shared
+ *      vertex, twice = an edge), O(N valence^2); the regular class is what remains of each row and is only enumerated when its
+ *      list is asked for.  Count, then fill, so that the caller sizes its lists exactly; the lists come out deterministic
+ *      (lexicographic in (i,j), i<j, k = slot) where the reference's order is atomicAdd order.                     */
 int i2_classify_count(i2_context *ctx, const int *d_cells, int nc, long long h_counts[3]);
 int i2_classify_fill(i2_context *ctx, const int *d_cells, int nc, int *d_simple, int *d_attached, int *d_not);
 /* any of the three lists may be NULL and is then skipped: a mesh whose regular list would not fit (N^2/2 x 12 B) takes
@@ -169,6 +172,10 @@ int i2_apply_finish(i2_context *ctx, int level, const double *d_weights, double 
  * kCalculateIntegrationError (src/evaluators/evaluator3d.cu:45-57)                                         */
 int i2_symmetry_error(i2_context *ctx, const double *d_results, long long n_half, double *d_errors);
 
+/* h_out = (max, mean) of n non-negative device doubles: the summary of the (i,j)/(j,i) defects that --checkresults computes
+ * but the reference never prints (src/evaluators/evaluator3d.cu:188-203)                                       */
+int i2_error_summary(i2_context *ctx, const double *d_errors, long long n, double h_out[2]);
+
 /* ---- host-buffer entry points (the end-to-end path: host mesh in, host results out) --------------------
  * i2_host_prepare uploads the mesh (already scaled), computes geometry, classifies and builds the three
  * ordered task lists exactly like Evaluator3D::runAllPairs (src/evaluators/evaluator3d.cu:120-169);
@@ -228,7 +235,7 @@ int i2_host_device_views(i2_context *ctx, const int *d_tasks[3], const double *d
  *   i2_mgpu_checksums per class (sum J_x, J_y, J_z, sum |J|_1) over ALL shards (all-reduce), the step's small metric
  *   i2_mgpu_shard     forward-slot range of any rank: first slot and task count 2 (hi - lo) per class
  *   i2_mgpu_fetch     row-striped export: one local GPU's shard (tasks, results, defects; shard order) to host arrays
- *   i2_mgpu_gather    export to one GPU: result (what = 0) or task (what = 1) shards of a class concatenated in rank order into
+ *   i2_mgpu_gather    export to one GPU: result (what = 0), task (1) or defect (2) shards of a class concatenated in rank order into
  *                     d_dst on GPU `root` (ncclSend / ncclRecv); enqueued on the contexts' streams
  *   i2_mgpu_set_results_target  make local GPU k write class c's results to d_results[c] instead of its own buffer, e.g. into a
  *                     peer-mapped slice of the exporting GPU's array (i2_peer_*): compute and gather in one kernel           */
@@ -251,6 +258,7 @@ int i2_mgpu_checksums(i2_mgpu *mg, double h_sums[12]);
 int i2_mgpu_gather(i2_mgpu *mg, int cls, int what, int root, void *d_dst);
 int i2_mgpu_fetch(i2_mgpu *mg, int local_index, int cls, int *h_tasks, double *h_results, double *h_errors);
 int i2_mgpu_refinements(i2_mgpu *mg, int cls, unsigned char *h_refinements);
+int i2_mgpu_error_summary(i2_mgpu *mg, int cls, double h_out[2]);   /* (max, mean) defect of a class over all shards */
 /* the whole operator (i2_apply_*) by row blocks over the GPUs: BASELINE.json configs[3] / [4], meshes beyond the N^2-list limit.
  * i2_mgpu_apply_prepare uploads the mesh and cuts the rows — by predicted cost under error control (level < 0), equally
  * otherwise; h_row_cuts (int[world + 1]) may be NULL.  i2_mgpu_apply: every GPU computes its rows (regular class list-free,

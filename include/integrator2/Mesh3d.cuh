@@ -29,7 +29,13 @@ public:
 
     const auto &getSimpleNeighbors() const { return pairLists[0]; }
     const auto &getAttachedNeighbors() const { return pairLists[1]; }
-    const auto &getNotNeighbors() const { return pairLists[2]; }
+    // the regular list (N^2/2 entries) is materialised on first use when the evaluator runs multi-GPU (env I2_GPUS > 1), where
+    // every GPU builds its own shard of it instead
+    const deviceVector<int3> &getNotNeighbors() const { materialiseNotNeighbors(); return pairLists[2]; }
+    // host copies of the mesh as loaded (scaled): the multi-GPU prepare uploads them to every GPU
+    const std::vector<Point3> &getHostVertices() const { return hostVertices; }
+    const std::vector<int3> &getHostCells() const { return hostCells; }
+    long long getPairCount(neighbour_type_enum t) const { return ((int)t >= 0 && (int)t < 3) ? pairCounts[(int)t] : 0; }
     const auto &getVertices() const { return vertices; }
     const auto &getCells() const { return cells; }
     const auto &getCellNormals() const { return cellNormals; }
@@ -41,7 +47,12 @@ private:
     deviceVector<Point3> cellNormals;
     deviceVector<Point3> cellCenters;
     deviceVector<double> cellMeasures;
-    deviceVector<int3> pairLists[3];  // indexed by neighbour_type_enum
+    mutable deviceVector<int3> pairLists[3];  // indexed by neighbour_type_enum
+    mutable bool notNeighborsDeferred = false;
+    long long pairCounts[3] = {0, 0, 0};
+    std::vector<Point3> hostVertices;
+    std::vector<int3> hostCells;
+    void materialiseNotNeighbors() const;
 };
 
 void exportMeshToObj(const std::string &filename, const std::vector<Point3> &vertices, const std::vector<int3> &cells);

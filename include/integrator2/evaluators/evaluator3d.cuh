@@ -4,13 +4,15 @@
 #ifndef EVALUATOR3D_CUH
 #define EVALUATOR3D_CUH
 
+#include <string>
 #include <vector>
 
 #include "../Mesh3d.cuh"
 #include "../NumericalIntegrator3d.cuh"
 #include "../common/gpu_timer.cuh"
 
-enum class output_format_enum { plainText = 1, csv = 2 };
+// binary (not in the reference): full-precision records keyed (i, j), see outputResultsToFile
+enum class output_format_enum { plainText = 1, csv = 2, binary = 3 };
 
 class Evaluator3D {
 public:
@@ -34,6 +36,9 @@ public:
         default: return nullptr;
         }
     }
+    // machine-readable summary of the last run (classes, counts, times, rounds, (i,j)/(j,i) defect summary): what the CLI
+    // writes when env I2_SUMMARY_JSON names a file
+    std::string getRunSummaryJson() const;
     // device views used by parity harnesses (the reference keeps these members protected)
     const deviceVector<Point3> *getResultsVector(neighbour_type_enum t) const;
     const deviceVector<double4> *getIntegralsVector(neighbour_type_enum t) const;
@@ -50,10 +55,28 @@ protected:
     const Mesh3D &mesh;
     NumericalIntegrator3D &numIntegrator;
     GpuTimer timer;
+    // true while the task vectors hold the ordered lists of runAllPairs ([pairs ; reversed pairs]): the per-class virtuals then
+    // use i2_integrate_pairs, whose results do not depend on how many GPUs a run uses
+    bool tasksArePairs = false;
+    // per-class record of the last run, filled by the per-class virtuals / the multi-GPU driver
+    struct ClassSummary {
+        long long tasks = 0;
+        double ms = 0.0;
+        int lastRound = 0;
+        long long unconverged[6] = {0, 0, 0, 0, 0, 0};
+        double deltaMax = -1.0, deltaMean = -1.0;   // -1: not computed (no --checkresults)
+    } summary[3];
 
 private:
     void allocateClass(int cls, int taskCount);
+    void runAllPairsMultiGpu(bool checkCorrectness);
+    void reportDefects(int cls, double maxDelta, double meanDelta, long long n);
     deviceVector<double> simpleNeighborsErrors, attachedNeighborsErrors, notNeighborsErrors;
+    bool distributed = false;     // the last run left its per-pair results row-striped over the GPUs (env I2_GPUS > 1)
+    bool distributedChecked = false;
+    long long distributedCount[3] = {0, 0, 0};
+    int lastGpus = 1, lastLevel = 0;
+    double allClassesMs = 0.0;
 };
 
 #endif  // EVALUATOR3D_CUH

@@ -49,9 +49,9 @@ EXPORTS = [
     "i2_set_quadrature", "i2_mesh_geometry", "i2_set_mesh", "i2_classify_count", "i2_classify_fill",
     "i2_add_reversed_pairs", "i2_integrate_class", "i2_integrate_pairs", "i2_integrate_all", "i2_symmetry_error", "i2_host_prepare", "i2_host_run",
     "i2_host_device_views", "i2_host_checksums", "i2_peer_alloc", "i2_peer_open", "i2_peer_close", "i2_peer_free", "i2_host_set_shard", "i2_host_shard", "i2_peak_rates", "i2_peak_dfma_three_operand", "i2_refine_mesh_once", "i2_launch_count", "i2_set_profiling", "i2_profile_last", "i2_selftest_math", "i2_apply_regular", "i2_apply_regular_adaptive",
-    "i2_host_row_costs", "i2_host_run_rounds", "i2_host_last_rounds", "i2_host_refinements", "i2_host_run_finalize", "i2_host_fetch", "i2_mgpu_unique_id", "i2_mgpu_create_rank", "i2_mgpu_create_local", "i2_mgpu_destroy", "i2_mgpu_info", "i2_mgpu_context",
+    "i2_error_summary", "i2_host_row_costs", "i2_host_run_rounds", "i2_host_last_rounds", "i2_host_refinements", "i2_host_run_finalize", "i2_host_fetch", "i2_mgpu_unique_id", "i2_mgpu_create_rank", "i2_mgpu_create_local", "i2_mgpu_destroy", "i2_mgpu_info", "i2_mgpu_context",
     "i2_mgpu_set_quadrature", "i2_mgpu_set_math_mode", "i2_mgpu_synchronize", "i2_mgpu_prepare", "i2_mgpu_shard", "i2_mgpu_set_results_target",
-    "i2_mgpu_run", "i2_mgpu_checksums", "i2_mgpu_gather", "i2_mgpu_fetch", "i2_mgpu_refinements",
+    "i2_mgpu_run", "i2_mgpu_checksums", "i2_mgpu_gather", "i2_mgpu_fetch", "i2_mgpu_refinements", "i2_mgpu_error_summary",
     "i2_mgpu_apply_prepare", "i2_mgpu_apply", "i2_mgpu_apply_result", "i2_apply_prepare", "i2_apply", "i2_apply_rounds", "i2_apply_last_rounds", "i2_apply_finish",
 ]
 
@@ -108,6 +108,7 @@ def load_library():
     L.i2_peer_open.argtypes = [vp, C.c_char_p, C.POINTER(vp)]
     L.i2_peer_close.argtypes = [vp, vp]
     L.i2_peer_free.argtypes = [vp, vp]
+    L.i2_error_summary.argtypes = [vp, vp, ll, C.POINTER(C.c_double)]
     L.i2_host_row_costs.argtypes = [vp, i32, vp, vp]
     L.i2_host_run_rounds.argtypes = [vp, i32]
     L.i2_host_last_rounds.argtypes = [vp, C.POINTER(i32), i32]
@@ -132,6 +133,7 @@ def load_library():
     L.i2_mgpu_gather.argtypes = [vp, i32, i32, i32, vp]
     L.i2_mgpu_fetch.argtypes = [vp, i32, i32, vp, vp, vp]
     L.i2_mgpu_refinements.argtypes = [vp, i32, vp]
+    L.i2_mgpu_error_summary.argtypes = [vp, i32, C.POINTER(C.c_double)]
     L.i2_mgpu_apply_prepare.argtypes = [vp, vp, i32, vp, i32, i32, C.POINTER(i32)]
     L.i2_mgpu_apply.argtypes = [vp, i32, vp, vp, C.POINTER(Stats)]
     L.i2_mgpu_apply_result.argtypes = [vp, i32, C.POINTER(vp), C.POINTER(vp)]
@@ -367,6 +369,12 @@ class Context:
         _check(self.L.i2_symmetry_error(self.h, _ptr(results), n // 2, _ptr(err)))
         return err
 
+    def error_summary(self, errors):
+        """(max, mean) of a device tensor of (i,j)/(j,i) defects"""
+        out = (C.c_double * 2)()
+        _check(self.L.i2_error_summary(self.h, _ptr(errors), int(errors.numel()), out))
+        return float(out[0]), float(out[1])
+
     def selftest_math(self, op, a, b=None):
         out = self.torch.empty_like(a)
         _check(self.L.i2_selftest_math(self.h, op, _ptr(a), _ptr(b), a.numel(), _ptr(out)))
@@ -573,6 +581,11 @@ class MultiGpu:
         """result (what=0, float64[n,3]) or task (what=1, int32[n,3]) shards of a class concatenated in rank order into the device
         tensor `dst` on GPU `root` (None on processes that do not own the root)"""
         _check(self.L.i2_mgpu_gather(self.h, int(cls), int(what), int(root), _ptr(dst)))
+
+    def error_summary(self, cls):
+        out = (C.c_double * 2)()
+        _check(self.L.i2_mgpu_error_summary(self.h, int(cls), out))
+        return float(out[0]), float(out[1])
 
     def set_results_target(self, local_index, ptrs):
         arr = (C.c_void_p * 3)(*[_ptr(p) for p in ptrs]) if ptrs is not None else None

@@ -129,6 +129,7 @@ int i2_destroy(i2_context *c) {
     }
     for (int k = 0; k < 3; ++k) if (c->prof[k]) cudaEventDestroy(c->prof[k]);
     if (c->rowCounts) cudaFree(c->rowCounts);
+    if (c->clsScratch) cudaFree(c->clsScratch);
     if (c->partial) cudaFree(c->partial);
     if (c->depthBuf) cudaFree(c->depthBuf);
     if (c->ap.scratch2) cudaFree(c->ap.scratch2);
@@ -214,30 +215,35 @@ int i2_refine_mesh_once(i2_context *c, const double *vin, int nvIn, const int *c
     return 0;
 }
 
+// Classification of a device-resident mesh for Mesh3D: by vertex incidence (see i2_prepare.cu), count then fill so that the
+// caller can size its lists exactly.  The number of vertices is 1 + the largest id in d_cells.
 int i2_classify_count(i2_context *c, const int *cells, int nc, long long counts[3]) {
     if (!c || !counts || nc < 0 || (nc > 0 && !cells)) return I2_E_BADARG;
     I2_CUDA(cudaSetDevice(c->device));
     counts[0] = counts[1] = counts[2] = 0;
     c->rowCountsNc = -1;
     if (nc == 0) return 0;
-    int rc = ensure(&c->rowCounts, &c->rowCap, (size_t)3 * nc);
+    cudaStream_t s = c->stream;
+    int rc = ensure(&c->rowCounts, &c->rowCap, (size_t)3 * (nc + 1) + 4);
     if (rc) return rc;
-    launch_classify_count(cells, nc, c->rowCounts, c->stream);
+    int *maxId = reinterpret_cast<int *>(c->rowCounts + (size_t)3 * (nc + 1) + 3);
+    I2_CUDA(cudaMemsetAsync(maxId, 0, sizeof(int), s));
+    launch_max_vertex_id(cells, nc, maxId, s);
+    int nv = 0;
+    I2_CUDA(cudaMemcpyAsync(&nv, maxId, sizeof(int), cudaMemcpyDeviceToHost, s));
+    I2_CUDA(cudaStreamSynchronize(s));
+    nv += 1;
+    rc = ensure(&c->clsScratch, &c->clsScratchCap, incidence_scratch_ints(nv, nc));
+    if (rc) return rc;
+    unsigned long long *totalsDev = c->rowCounts + (size_t)3 * (nc + 1);
+    launch_incidence(cells, nv, nc, c->clsScratch, c->rowCounts, totalsDev, s);
     I2_CUDA(cudaGetLastError());
-    std::vector<unsigned long long> h((size_t)3 * nc);
-    I2_CUDA(cudaMemcpyAsync(h.data(), c->rowCounts, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-    I2_CUDA(cudaStreamSynchronize(c->stream));
-    unsigned long long run[3] = {0, 0, 0};
-    for (int i = 0; i < nc; ++i)
-        for (int k = 0; k < 3; ++k) {
-            const unsigned long long v = h[(size_t)3 * i + k];
-            h[(size_t)3 * i + k] = run[k];  // exclusive prefix = first slot of row i
-            run[k] += v;
-        }
-    I2_CUDA(cudaMemcpyAsync(c->rowCounts, h.data(), h.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
-    I2_CUDA(cudaStreamSynchronize(c->stream));
-    for (int k = 0; k < 3; ++k) counts[k] = (long long)run[k];
+    unsigned long long totals[3];
+    I2_CUDA(cudaMemcpyAsync(totals, totalsDev, sizeof(totals), cudaMemcpyDeviceToHost, s));
+    I2_CUDA(cudaStreamSynchronize(s));
+    for (int k = 0; k < 3; ++k) counts[k] = (long long)totals[k];
     c->rowCountsNc = nc;
+    c->rowCountsNv = nv;
     return 0;
 }
 
@@ -245,7 +251,14 @@ int i2_classify_fill(i2_context *c, const int *cells, int nc, int *simple, int *
     if (!c || nc < 0 || (nc > 0 && (!cells || !c->rowCounts))) return I2_E_BADARG;
     if (nc > 0 && c->rowCountsNc != nc) return I2_E_BADARG;   // the offsets must come from i2_classify_count of the same mesh
     I2_CUDA(cudaSetDevice(c->device));
-    launch_classify_fill(cells, nc, c->rowCounts, simple, attached, notn, c->stream);
+    if (nc == 0) return 0;
+    launch_partners_fill(cells, c->rowCountsNv, nc, c->clsScratch, c->rowCounts, simple, attached, false, c->stream);
+    if (notn) {
+        unsigned long long total = 0;
+        I2_CUDA(cudaMemcpyAsync(&total, c->rowCounts + (size_t)3 * (nc + 1) + 2, sizeof(total), cudaMemcpyDeviceToHost, c->stream));
+        I2_CUDA(cudaStreamSynchronize(c->stream));
+        launch_regular_fill(cells, nc, c->rowCounts, 0ull, total, notn, nullptr, c->numSMs, c->stream);
+    }
     I2_CUDA(cudaGetLastError());
     return 0;
 }
@@ -667,6 +680,22 @@ int i2_symmetry_error(i2_context *c, const double *results, long long nHalf, dou
     I2_CUDA(cudaSetDevice(c->device));
     launch_symmetry_error(results, nHalf, errors, c->stream);
     I2_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int i2_error_summary(i2_context *c, const double *errors, long long n, double out[2]) {
+    if (!c || !out || n < 0 || (n > 0 && !errors)) return I2_E_BADARG;
+    out[0] = out[1] = 0.0;
+    if (n == 0) return 0;
+    I2_CUDA(cudaSetDevice(c->device));
+    double *d = nullptr;
+    I2_CUDA(cudaMalloc((void **)&d, sizeof(double) * 2));
+    I2_CUDA(cudaMemsetAsync(d, 0, sizeof(double) * 2, c->stream));
+    launch_error_summary(errors, n, d, c->numSMs, c->stream);
+    I2_CUDA(cudaMemcpyAsync(out, d, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
+    I2_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d);
+    out[1] /= (double)n;
     return 0;
 }
 

@@ -44,10 +44,12 @@ struct i2_context {
     unsigned char *depthBuf = nullptr;   // list-free adaptive path: per (column chunk, row) refinement depth
     size_t depthCap = 0;
 
-    // classification scratch: per-row counts of the O(N^2) two-pass kernels (i2_classify_count / _fill, Mesh3D's lists) ...
+    // classification scratch of i2_classify_count / _fill (Mesh3D's lists): first slot of every row per class [3][nc + 1], totals ...
     unsigned long long *rowCounts = nullptr;
     size_t rowCap = 0;
-    int rowCountsNc = -1;                 // nc of the last i2_classify_count (i2_classify_fill must see the same mesh)
+    int rowCountsNc = -1, rowCountsNv = 0; // mesh of the last i2_classify_count (i2_classify_fill must see the same one)
+    int *clsScratch = nullptr;            // its vertex incidence
+    size_t clsScratchCap = 0;
     // ... and of the vertex-incidence path (i2_host_prepare): CSR scratch, first slot of every row per class, totals
     int *incScratch = nullptr;
     size_t incCap = 0;

@@ -441,7 +441,7 @@ static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, c
 template <int MINB, int VAR>
 __global__ void __launch_bounds__(kThreads, MINB)
 k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__restrict__ list, const int *__restrict__ countDev,
-                  long long countHost, long long half, int level, double *__restrict__ out, double *__restrict__ results) {
+                  long long countHost, long long half, int level, int flags, double *__restrict__ out, double *__restrict__ results) {
     __shared__ double smM[MAX_GAUSS_POINTS * 3 * kThreads];
     __shared__ double smJ[kThreads / 32][96];   // one warp's 32 results, staged for 16-byte coalesced stores
     const long long count = countDev ? (long long)*countDev : countHost;
@@ -523,7 +523,7 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
         if (mis && lane == 1) dst[95] = sj[95];
         __syncwarp();
     };
-    const bool vecStores = results && !list && G == 1;
+    const bool vecStores = results && !list && G == 1 && (flags & 1);
 
     if (G <= 32) {
         // A warp walks a contiguous chunk of kChunkIters x (32/G) tasks: lists are sorted by control panel i, so a lane meets
@@ -968,6 +968,8 @@ void launch_reduce_partials_adaptive(const double *partial6, const unsigned char
 
 // tuning knob (env I2_MINBLOCKS = 3|4|5): resident CTAs per SM the regular kernel is compiled for
 static int g_minBlocks = [] { const char *e = getenv("I2_MINBLOCKS"); return e ? atoi(e) : 4; }();
+// bit 0: 16-byte coalesced result stores staged through shared memory (env I2_VEC_STORES=0 turns them off: A/B knob)
+static int g_kernelFlags = [] { const char *e = getenv("I2_VEC_STORES"); return (e && atoi(e) == 0) ? 0 : 1; }();
 static int g_variant = [] { const char *e = getenv("I2_VARIANT"); return e ? atoi(e) : 27; }();
 
 void launch_integrate(int cls, int mathMode, const PackedMesh &pm, const int *tasks, const int *list, const int *countDev,
@@ -994,7 +996,7 @@ void launch_integrate(int cls, int mathMode, const PackedMesh &pm, const int *ta
         // the LEVEL0 specialisation (bit 2) is chosen automatically
         const int var = (g_variant & 3) | (level == 0 ? 4 : 0) | (g_variant & 24);
         ++g_launchCount;
-#define I2_LAUNCH_GROUPED(MB, V) k_regular_grouped<MB, V><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, half, level, out4, fusedResults3)
+#define I2_LAUNCH_GROUPED(MB, V) k_regular_grouped<MB, V><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, half, level, g_kernelFlags, out4, fusedResults3)
 #define I2_PICK_VAR(MB)                                                                                              \
         switch (var) {                                                                                           \
         case 0: I2_LAUNCH_GROUPED(MB, 0); break; case 1: I2_LAUNCH_GROUPED(MB, 1); break;                       \
@@ -1242,78 +1244,6 @@ void launch_add_reversed(int *tasks3, long long n, cudaStream_t s) {
     if (n > 0) { ++g_launchCount; k_add_reversed<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(tasks3, n); }
 }
 
-static __device__ __forceinline__ int pair_class(tri3 a, tri3 b) {
-    int common = 0;
-    common += (a.a == b.a || a.a == b.b || a.a == b.c);
-    common += (a.b == b.a || a.b == b.b || a.b == b.c);
-    common += (a.c == b.a || a.c == b.b || a.c == b.c);
-    return common == 0 ? 2 : (common == 1 ? 0 : (common == 2 ? 1 : -1));  // 3 shared ids: dropped, like the reference
-}
-
-// one CTA per row i: counts of each class among j > i
-__global__ void __launch_bounds__(256) k_classify_count(const int *__restrict__ cells, int nc, unsigned long long *rowCounts) {
-    const int i = blockIdx.x;
-    const tri3 a = ldtri(cells, i);
-    int cnt[3] = {0, 0, 0};
-    for (int j = i + 1 + threadIdx.x; j < nc; j += blockDim.x) {
-        const int cls = pair_class(a, ldtri(cells, j));
-        if (cls >= 0) cnt[cls]++;
-    }
-    __shared__ int sh[3];
-    if (threadIdx.x < 3) sh[threadIdx.x] = 0;
-    __syncthreads();
-    for (int k = 0; k < 3; ++k) {
-        int v = cnt[k];
-        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&sh[k], v);
-    }
-    __syncthreads();
-    if (threadIdx.x < 3) rowCounts[3 * (size_t)i + threadIdx.x] = (unsigned long long)sh[threadIdx.x];
-}
-
-// one CTA per row i: writes (i, j, slot) in increasing j, slot = rowOffset + rank  => lexicographically sorted lists
-__global__ void __launch_bounds__(256) k_classify_fill(const int *__restrict__ cells, int nc, const unsigned long long *__restrict__ rowOffsets,
-                                                      int *simple, int *attached, int *notn) {
-    const int i = blockIdx.x;
-    const tri3 a = ldtri(cells, i);
-    __shared__ unsigned long long running[3];
-    __shared__ int warpCnt[8][3];
-    if (threadIdx.x < 3) running[threadIdx.x] = rowOffsets[3 * (size_t)i + threadIdx.x];
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int base = i + 1; base < nc; base += blockDim.x) {
-        const int j = base + threadIdx.x;
-        const int cls = j < nc ? pair_class(a, ldtri(cells, j)) : -1;
-        unsigned masks[3];
-        for (int k = 0; k < 3; ++k) {
-            masks[k] = __ballot_sync(0xffffffffu, cls == k);
-            if (lane == 0) warpCnt[warp][k] = __popc(masks[k]);
-        }
-        __syncthreads();
-        if (cls >= 0) {
-            unsigned long long pos = running[cls];
-            for (int w = 0; w < warp; ++w) pos += warpCnt[w][cls];
-            pos += __popc(masks[cls] & ((1u << lane) - 1u));
-            int *dst = cls == 0 ? simple : (cls == 1 ? attached : notn);
-            if (dst) { dst[3 * pos] = i; dst[3 * pos + 1] = j; dst[3 * pos + 2] = (int)pos; }   // a NULL list is skipped
-        }
-        __syncthreads();
-        if (threadIdx.x < 3) {
-            unsigned long long add = 0;
-            for (int w = 0; w < 8; ++w) add += warpCnt[w][threadIdx.x];
-            running[threadIdx.x] += add;
-        }
-        __syncthreads();
-    }
-}
-
-void launch_classify_count(const int *cells, int nc, unsigned long long *rowCounts3, cudaStream_t s) {
-    if (nc > 0) { ++g_launchCount; k_classify_count<<<nc, 256, 0, s>>>(cells, nc, rowCounts3); }
-}
-void launch_classify_fill(const int *cells, int nc, const unsigned long long *rowOffsets3, int *simple3, int *attached3, int *not3, cudaStream_t s) {
-    if (nc > 0) { ++g_launchCount; k_classify_fill<<<nc, 256, 0, s>>>(cells, nc, rowOffsets3, simple3, attached3, not3); }
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // roofline denominators measured on the box: FP64 pipe (DFMA) and XU pipe (MUFU.RSQ64H) peak rates
 // ---------------------------------------------------------------------------------------------------------
@@ -1376,8 +1306,6 @@ cudaError_t preload_rest() {
     I2_TOUCH(k_finalize<1>);
     I2_TOUCH(k_finalize<2>);
     I2_TOUCH(k_compare);
-    I2_TOUCH(k_classify_count);
-    I2_TOUCH(k_classify_fill);
 #undef I2_TOUCH
     return cudaSuccess;
 }

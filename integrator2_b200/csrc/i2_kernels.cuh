@@ -75,9 +75,9 @@ void launch_finalize(int cls, const PackedMesh &pm, const double *verts, const i
                      const double *bufB4, const QueueState *qs, double *results3, QueueState *qsMut, cudaStream_t s);
 void launch_symmetry_error(const double *results3, long long nHalf, double *errors, cudaStream_t s);
 void launch_add_reversed(int *tasks3, long long n, cudaStream_t s);
-void launch_classify_count(const int *cells, int nc, unsigned long long *rowCounts3, cudaStream_t s);
-void launch_classify_fill(const int *cells, int nc, const unsigned long long *rowOffsets3, int *simple3, int *attached3,
-                          int *not3, cudaStream_t s);
+void launch_max_vertex_id(const int *cells, int nc, int *maxId, cudaStream_t s);
+// out2[0] = max, out2[1] = sum of n non-negative doubles (the (i,j)/(j,i) defects): the --checkresults summary
+void launch_error_summary(const double *errors, long long n, double *out2, int numSMs, cudaStream_t s);
 void launch_split_uniform(const double *vin, int nvIn, const int *cin, int ncIn, const double *min, double *vout, int *cout,
                           double *mout, cudaStream_t s);
 // classification by vertex incidence + sharded task lists (i2_prepare.cu)

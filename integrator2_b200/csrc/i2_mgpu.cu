@@ -601,16 +601,19 @@ int i2_mgpu_checksums(i2_mgpu *mg, double sums[12]) {
 }
 
 // Export gather: the result shards of one class to GPU `root` (global rank), concatenated in rank order — the row of
-// rank r starts at task 2 * lo_r, the order of the shard-local lists.  what = 0: results (Point3), 1: tasks (int3).
+// rank r starts at task 2 * lo_r, the order of the shard-local lists.  what = 0: results (Point3), 1: tasks (int3), 2: defects.
 // d_dst is read on the process that owns `root` only.  Enqueued on the contexts' streams.
 int i2_mgpu_gather(i2_mgpu *mg, int cls, int what, int root, void *d_dst) {
-    if (!mg || cls < 0 || cls > 2 || what < 0 || what > 1 || root < 0 || root >= mg->world) return I2_E_BADARG;
+    if (!mg || cls < 0 || cls > 2 || what < 0 || what > 2 || root < 0 || root >= mg->world) return I2_E_BADARG;
     if (!mg->prepared) return I2_E_NOMESH;
     const bool rootLocal = root >= mg->firstRank && root < mg->firstRank + mg->nLocal;
     if (rootLocal && !d_dst) return I2_E_BADARG;
-    const size_t elem = what == 0 ? sizeof(double) * 3 : sizeof(int) * 3;
+    const size_t elem = what == 0 ? sizeof(double) * 3 : (what == 1 ? sizeof(int) * 3 : sizeof(double));
+    for (int k = 0; k < mg->nLocal && what == 2; ++k)
+        if (mg->ctx[k]->hN[cls] > 0 && !mg->ctx[k]->hErrors[cls]) return I2_E_BADARG;   // the last run did not compute the defects
     auto src = [&](int k) -> const char * {
         i2_context *c = mg->ctx[k];
+        if (what == 2) return (const char *)c->hErrors[cls];
         return what == 0 ? (const char *)(c->hResultsTarget[cls] ? c->hResultsTarget[cls] : c->hResults[cls]) : (const char *)c->hTasks[cls];
     };
     NcclApi *api = mg->world > 1 ? nccl_api() : nullptr;
@@ -642,6 +645,40 @@ int i2_mgpu_fetch(i2_mgpu *mg, int local_index, int cls, int *h_tasks, double *h
     if (!mg || local_index < 0 || local_index >= mg->nLocal) return I2_E_BADARG;
     if (!mg->prepared) return I2_E_NOMESH;
     return i2_host_fetch(mg->ctx[local_index], cls, h_tasks, h_results, h_errors);
+}
+
+// (max, mean) of the (i,j)/(j,i) defects of a class over all shards (the last run must have been called with check != 0)
+int i2_mgpu_error_summary(i2_mgpu *mg, int cls, double out[2]) {
+    if (!mg || cls < 0 || cls > 2 || !out) return I2_E_BADARG;
+    if (!mg->prepared) return I2_E_NOMESH;
+    double mx = 0.0, sum = 0.0, cnt = 0.0;
+    for (int k = 0; k < mg->nLocal; ++k) {
+        i2_context *c = mg->ctx[k];
+        if (c->hN[cls] == 0) continue;
+        if (!c->hErrors[cls]) return I2_E_BADARG;
+        double part[2];
+        const int rc = i2_error_summary(c, c->hErrors[cls], c->hN[cls], part);
+        if (rc) return rc;
+        if (part[0] > mx) mx = part[0];
+        sum += part[1] * (double)c->hN[cls];
+        cnt += (double)c->hN[cls];
+    }
+    if (mg->world > mg->nLocal) {
+        NcclApi *api = nccl_api();
+        if (!api) return I2_E_NCCL;
+        i2_context *c = mg->ctx[0];
+        I2_CUDA(cudaSetDevice(c->device));
+        double v[3] = {sum, cnt, mx};
+        I2_CUDA(cudaMemcpyAsync(mg->scratch[0], v, sizeof(v), cudaMemcpyHostToDevice, c->stream));
+        I2_NCCL(api->AllReduce(mg->scratch[0], mg->scratch[0], 2, ncclFloat64, ncclSum, mg->comm[0], c->stream));
+        I2_NCCL(api->AllReduce(mg->scratch[0] + 2, mg->scratch[0] + 2, 1, ncclFloat64, ncclMax, mg->comm[0], c->stream));
+        I2_CUDA(cudaMemcpyAsync(v, mg->scratch[0], sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+        I2_CUDA(cudaStreamSynchronize(c->stream));
+        sum = v[0]; cnt = v[1]; mx = v[2];
+    }
+    out[0] = mx;
+    out[1] = cnt > 0.0 ? sum / cnt : 0.0;
+    return 0;
 }
 
 int i2_mgpu_refinements(i2_mgpu *mg, int cls, unsigned char *h_refinements) {

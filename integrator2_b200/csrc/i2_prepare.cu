@@ -392,6 +392,28 @@ __global__ void k_take_rows(const unsigned char *__restrict__ perCell, int rowLo
     if (r < rows) out[r] = perCell[rowLo + r];
 }
 
+__global__ void k_max_vertex_id(const int *__restrict__ cells, int nc, int *maxId) {
+    int m = 0;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < 3 * nc; e += gridDim.x * blockDim.x) m = max(m, __ldg(cells + e));
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0) atomicMax(maxId, m);
+}
+
+// max and sum of non-negative doubles (NaN-free inputs order like their bit patterns)
+__global__ void __launch_bounds__(256) k_error_summary(const double *__restrict__ e, long long n, double *out2) {
+    double mx = 0.0, sm = 0.0;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const double v = e[t];
+        mx = fmax(mx, v);
+        sm += v;
+    }
+    for (int off = 16; off > 0; off >>= 1) { mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off)); sm += __shfl_xor_sync(0xffffffffu, sm, off); }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(reinterpret_cast<unsigned long long *>(out2), (unsigned long long)__double_as_longlong(mx));
+        atomicAdd(out2 + 1, sm);
+    }
+}
+
 // ---- host-side launchers ---------------------------------------------------------------------------------------------
 // scratch layout (ints): vcount[nv + 1] | voff[nv + 1] | cursor[nv] | inc[3 nc] | cntS[nc] | cntA[nc] | cntD[nc]
 size_t incidence_scratch_ints(int nv, int nc) { return (size_t)3 * (nv + 1) + (size_t)6 * nc + 8; }
@@ -465,5 +487,20 @@ void launch_take_rows(const unsigned char *perCell, int rowLo, int rows, unsigne
     if (rows <= 0) return;
     ++g_launchCount;
     k_take_rows<<<(rows + 255) / 256, 256, 0, s>>>(perCell, rowLo, rows, out);
+}
+}  // namespace i2
+
+namespace i2 {
+void launch_max_vertex_id(const int *cells, int nc, int *maxId, cudaStream_t s) {
+    if (nc <= 0) return;
+    ++g_launchCount;
+    int blocks = (3 * nc + 255) / 256;
+    if (blocks > 1184) blocks = 1184;
+    k_max_vertex_id<<<blocks, 256, 0, s>>>(cells, nc, maxId);
+}
+void launch_error_summary(const double *errors, long long n, double *out2, int numSMs, cudaStream_t s) {
+    if (n <= 0) return;
+    ++g_launchCount;
+    k_error_summary<<<numSMs * 4, 256, 0, s>>>(errors, n, out2);
 }
 }  // namespace i2

@@ -15,14 +15,15 @@
 namespace {
 
 struct Options {
-    bool help = false, toObj = false, toVtk = false, toCsv = false, toText = false, check = false;
+    bool help = false, toObj = false, toVtk = false, toCsv = false, toText = false, toBinary = false, check = false;
     bool haveMesh = false, haveScale = false, haveRefine = false;
     std::string meshfile, scale, refine;
 };
 
 struct Spec { char shortName; const char *longName; int kind; };  // kind: 0 flag, 1 non-empty argument, 2 numeric argument
 const Spec kSpecs[] = {{'h', "help", 0}, {'f', "meshfile", 1}, {'s', "scale", 2}, {0, "exporttoobj", 0}, {0, "exporttovtk", 0},
-                       {0, "exporttocsv", 0}, {0, "exportresults", 0}, {'r', "refine", 2}, {'c', "checkresults", 0}};
+                       {0, "exporttocsv", 0}, {0, "exportresults", 0}, {'r', "refine", 2}, {'c', "checkresults", 0},
+                       {0, "exportbinary", 0}};   // the last one is not in the reference: full-precision records (Evaluator3D::outputResultsToFile)
 
 void printUsage() {
     std::cout << "USAGE: integrator2test3D [options]\n\nOptions:\n"
@@ -34,7 +35,9 @@ void printUsage() {
                  "               --exporttocsv      Export results of integration to csv files.\n"
                  "               --exportresults    Export results of integration to text files.\n"
                  "   -r <arg>,   --refine=<arg>     Refine the whole mesh N times.\n"
-                 "   -c,         --checkresults     Check correctness of pairs of results.\n";
+                 "   -c,         --checkresults     Check correctness of pairs of results.\n"
+                 "               --exportbinary     Export results of integration to binary files (full precision; not in the reference).\n"
+                 "Environment: I2_GPUS=N shards the run over N GPUs; I2_GATHER=1 gathers the results on device 0; I2_SUMMARY_JSON=file writes a run summary.\n";
 }
 
 bool isNumeric(const std::string &s) {
@@ -51,6 +54,7 @@ bool store(Options &o, const Spec &sp, const std::string &name, const char *valu
         else if (!strcmp(sp.longName, "exporttovtk")) o.toVtk = true;
         else if (!strcmp(sp.longName, "exporttocsv")) o.toCsv = true;
         else if (!strcmp(sp.longName, "exportresults")) o.toText = true;
+        else if (!strcmp(sp.longName, "exportbinary")) o.toBinary = true;
         else o.check = true;
         return true;
     }
@@ -153,6 +157,18 @@ int main(int argc, char *argv[]) {
         evaluator.outputResultsToFile(neighbour_type_enum::simple_neighbors, format);
         evaluator.outputResultsToFile(neighbour_type_enum::attached_neighbors, format);
         evaluator.outputResultsToFile(neighbour_type_enum::not_neighbors, format);
+    }
+
+    if (opt.toBinary) {
+        evaluator.outputResultsToFile(neighbour_type_enum::simple_neighbors, output_format_enum::binary);
+        evaluator.outputResultsToFile(neighbour_type_enum::attached_neighbors, output_format_enum::binary);
+        evaluator.outputResultsToFile(neighbour_type_enum::not_neighbors, output_format_enum::binary);
+    }
+    if (const char *path = getenv("I2_SUMMARY_JSON")) {
+        if (FILE *f = fopen(path, "w")) {
+            fprintf(f, "%s\n", evaluator.getRunSummaryJson().c_str());
+            fclose(f);
+        }
     }
 
     if ((opt.toObj || opt.toVtk) && refineLevel > 0) {

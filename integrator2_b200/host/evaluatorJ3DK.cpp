@@ -17,8 +17,14 @@ void EvaluatorJ3DK::integrateClass(neighbour_type_enum neighborType) {
         converged = numIntegrator.getIntegralsConverged(neighborType)->data;
     }
     i2_stats st;
-    checkI2Errors(i2_integrate_class(i2host::context(), cls, (const int *)tasks->data, n, level, (double *)integrals->data,
-                                     (double *)results->data, refinements, converged, &st));
+    if (tasksArePairs)   // the ordered list of runAllPairs: results independent of the number of GPUs a run uses
+        checkI2Errors(i2_integrate_pairs(i2host::context(), cls, (const int *)tasks->data, n / 2, level, (double *)integrals->data,
+                                         (double *)results->data, refinements, converged, &st));
+    else
+        checkI2Errors(i2_integrate_class(i2host::context(), cls, (const int *)tasks->data, n, level, (double *)integrals->data,
+                                         (double *)results->data, refinements, converged, &st));
+    summary[cls].lastRound = st.last_round;
+    for (int m = 0; m < 6; ++m) summary[cls].unconverged[m] = st.unconverged[m];
     if (adaptive) {
         // the lines the reference prints while it iterates (src/evaluators/evaluatorJ3DK.cu:956,980; evaluator3d.cu:338)
         printf("Iteration 0, integrating %d tasks\n", n);

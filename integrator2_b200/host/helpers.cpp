@@ -14,6 +14,35 @@ i2_context *context() {
     }
     return ctx;
 }
+
+int gpus() {
+    static int n = -1;
+    if (n < 0) {
+        n = 1;
+        if (const char *e = getenv("I2_GPUS")) {
+            int have = 1;
+            checkCudaErrors(cudaGetDeviceCount(&have));
+            n = atoi(e);
+            if (n < 1) n = 1;
+            if (n > have) {
+                fprintf(stderr, "I2_GPUS=%d but only %d device(s) visible: using %d\n", n, have, have);
+                n = have;
+            }
+        }
+    }
+    return n;
+}
+
+i2_mgpu *mgpu() {
+    static i2_mgpu *mg = nullptr;
+    if (!mg) checkI2Errors(i2_mgpu_create_local(&mg, gpus(), nullptr));
+    return mg;
+}
+
+bool gatherToDevice0() {
+    const char *e = getenv("I2_GATHER");
+    return e && atoi(e) != 0;
+}
 }  // namespace i2host
 
 void checkI2(int rc, const char *what, const char *file, int line) {

@@ -13,8 +13,8 @@ bool Mesh3D::loadMeshFromFile(const std::string &filename, double scale) {
     int numVertices = 0, numEntities = 0;
     in >> numVertices >> numEntities;
 
-    std::vector<Point3> hostVertices;
-    std::vector<int3> hostCells;
+    hostVertices.clear();
+    hostCells.clear();
     hostVertices.reserve(numVertices);
     hostCells.reserve(numEntities);
     for (int v = 0; v < numVertices; ++v) {
@@ -44,7 +44,7 @@ bool Mesh3D::loadMeshFromFile(const std::string &filename, double scale) {
     cellMeasures.allocate(numCells);
     copy_h2d(hostVertices.data(), vertices.data, vertices.size);
     copy_h2d(hostCells.data(), cells.data, cells.size);
-    checkCudaErrors(cudaDeviceSynchronize());  // the host vectors die with this scope
+    checkCudaErrors(cudaDeviceSynchronize());
 
     printf("Loaded mesh with %d vertices and %d cells\n", numVertices, numCells);
     return true;
@@ -58,12 +58,28 @@ void Mesh3D::prepareMesh() {
     checkI2Errors(i2_classify_count(ctx, (const int *)cells.data, cells.size, counts));
     for (int k = 0; k < 3; ++k) {
         if (counts[k] > 0x3fffffff) checkI2Errors(I2_E_TOOBIG);
-        if (counts[k]) pairLists[k].allocate((int)counts[k]);
+        pairCounts[k] = counts[k];
     }
+    // multi-GPU runs never need the whole regular list on one device: it is built on first use of getNotNeighbors()
+    notNeighborsDeferred = i2host::gpus() > 1;
+    for (int k = 0; k < 3; ++k)
+        if (counts[k] && !(k == 2 && notNeighborsDeferred)) pairLists[k].allocate((int)counts[k]);
     checkI2Errors(i2_classify_fill(ctx, (const int *)cells.data, cells.size, (int *)pairLists[0].data, (int *)pairLists[1].data,
-                                   (int *)pairLists[2].data));
-    printf("Found %d pairs of simple neighbors and %d pairs of attached neighbors, %d pairs are not neighbors\n", pairLists[0].size,
-           pairLists[1].size, pairLists[2].size);
+                                   notNeighborsDeferred ? nullptr : (int *)pairLists[2].data));
+    printf("Found %d pairs of simple neighbors and %d pairs of attached neighbors, %d pairs are not neighbors\n", (int)counts[0],
+           (int)counts[1], (int)counts[2]);
+    checkCudaErrors(cudaDeviceSynchronize());
+}
+
+void Mesh3D::materialiseNotNeighbors() const {
+    if (!notNeighborsDeferred) return;
+    notNeighborsDeferred = false;
+    if (!pairCounts[2]) return;
+    i2_context *ctx = i2host::context();
+    long long counts[3];
+    checkI2Errors(i2_classify_count(ctx, (const int *)cells.data, cells.size, counts));
+    pairLists[2].allocate((int)counts[2]);
+    checkI2Errors(i2_classify_fill(ctx, (const int *)cells.data, cells.size, nullptr, nullptr, (int *)pairLists[2].data));
     checkCudaErrors(cudaDeviceSynchronize());
 }
 

@@ -10,6 +10,7 @@ NumericalIntegrator3D::NumericalIntegrator3D(const Mesh3D &mesh_, const Quadratu
         xy[2 * g + 1] = qf.coordinates[g].y;
     }
     checkI2Errors(i2_set_quadrature(i2host::context(), xy.data(), qf.weights.data(), GaussPointsNum, qf.order));
+    if (i2host::gpus() > 1) checkI2Errors(i2_mgpu_set_quadrature(i2host::mgpu(), xy.data(), qf.weights.data(), GaussPointsNum, qf.order));
 }
 
 void NumericalIntegrator3D::setFixedRefinementLevel(int refinementLevel) {
@@ -27,7 +28,7 @@ void NumericalIntegrator3D::prepareTasksAndMesh(const deviceVector<int3> &simple
 
     if (errorControlType == error_control_type_enum::automatic_error_control) {
         for (int k = 0; k < 3; ++k) {
-            if (lists[k]->size) {
+            if (lists[k]->size && lists[k]->data) {   // (multi-GPU runs pass sized lists without data: the tasks live on the other GPUs)
                 integralsConverged[k].allocate(lists[k]->size);
                 zero_value_device(integralsConverged[k].data, lists[k]->size);
             }
@@ -71,9 +72,25 @@ void NumericalIntegrator3D::prepareTasksAndMesh(const deviceVector<int3> &simple
 }
 
 // The four entry points below are steps of the reference's host-driven refinement loop
-// (src/NumericalIntegrator3d.cu:369-499).  Here that loop runs on the device inside i2_integrate_class, so they
-// have nothing left to do; they remain so that code written against the reference links.
-void NumericalIntegrator3D::gatherResults(deviceVector<double4> &, neighbour_type_enum) const {}
-void NumericalIntegrator3D::refineMesh(neighbour_type_enum) {}
-void NumericalIntegrator3D::resetMesh() {}
-int NumericalIntegrator3D::determineCellsToBeRefined(const deviceVector<int> &, const deviceVector<int3> *, neighbour_type_enum) { return 0; }
+// (src/NumericalIntegrator3d.cu:369-499).  Here that loop runs on the device inside i2_integrate_class, so they have nothing
+// left to do; they remain so that code written against the reference links — and say so once, because an evaluator that
+// drives the loop itself through them would otherwise compute nothing without a message.
+namespace {
+void notSupported(const char *what) {
+    static bool said[8] = {false};
+    static const char *seen[8] = {nullptr};
+    for (int k = 0; k < 8; ++k) {
+        if (seen[k] == what) { if (said[k]) return; said[k] = true; break; }
+        if (!seen[k]) { seen[k] = what; said[k] = true; break; }
+    }
+    fprintf(stderr, "integrator2 (B200 build): %s does nothing here — refinement, gathering and the Runge comparison run on the device inside "
+                    "i2_integrate_class (include/i2_abi.h); a custom evaluator must call that entry point instead of driving the loop itself\n", what);
+}
+}  // namespace
+void NumericalIntegrator3D::gatherResults(deviceVector<double4> &, neighbour_type_enum) const { notSupported("NumericalIntegrator3D::gatherResults"); }
+void NumericalIntegrator3D::refineMesh(neighbour_type_enum) { notSupported("NumericalIntegrator3D::refineMesh"); }
+void NumericalIntegrator3D::resetMesh() { notSupported("NumericalIntegrator3D::resetMesh"); }
+int NumericalIntegrator3D::determineCellsToBeRefined(const deviceVector<int> &, const deviceVector<int3> *, neighbour_type_enum) {
+    notSupported("NumericalIntegrator3D::determineCellsToBeRefined");
+    return 0;
+}

@@ -174,7 +174,7 @@ def perturbation_noise(oracle, vertices, cells, cls, tasks, level, trials=8, see
     return worst, base
 
 
-K_PERTURB = 8.0
+K_PERTURB = 16.0
 
 
 def check_parity_perturbation(oracle, vertices, cells, cls, tasks, level, J_new, J_ref=None, label="", max_outliers=0):

@@ -66,8 +66,14 @@ def test_world_of_one_equals_the_single_context_run(level):
         assert stats[cls]["integrated"] == whole["stats"][cls]["integrated"]
         if level < 0:
             assert np.array_equal(mg.refinements(cls), whole["refinements"][cls])
-    assert np.allclose(mg.checksums(), whole["sums"], rtol=1e-12, atol=0)
+    _same_sums(mg.checksums(), whole["sums"])
     mg.close()
+
+
+def _same_sums(a, b):
+    """per-class (sum J_x, J_y, J_z, sum |J|_1): the signed sums cancel and are accumulated in a different order (atomics):
+    equal to rounding at the scale of sum |J|_1"""
+    assert (np.abs(a - b) <= 1e-11 * b[:, 3:4]).all(), (a, b)
 
 
 def _gpus():
@@ -94,7 +100,7 @@ def test_two_gpus_one_process_bitwise(level):
         assert stats[cls]["unconverged"] == whole["stats"][cls]["unconverged"]
         if level < 0:
             assert np.array_equal(mg.refinements(cls), whole["refinements"][cls])
-    assert np.allclose(mg.checksums(), whole["sums"], rtol=1e-12, atol=0)
+    _same_sums(mg.checksums(), whole["sums"])
     # export gather: shards concatenated in rank order on GPU 0, keys and values
     for cls in range(3):
         n = whole["counts"][cls]
@@ -172,7 +178,7 @@ def test_two_processes_one_gpu_each_bitwise(level, tmp_path):
     nxt = [0, 0, 0]
     for r, o in enumerate(outs):
         assert o["counts"].tolist() == whole["counts"]
-        assert np.allclose(o["sums"], whole["sums"], rtol=1e-12, atol=0)     # all-reduced: every rank holds the job's checksums
+        _same_sums(o["sums"], whole["sums"])     # all-reduced: every rank holds the job's checksums
         for cls in range(3):
             P, lo, h = whole["counts"][cls] // 2, int(o["first"][cls]), int(o["cnt"][cls]) // 2
             assert lo == nxt[cls]

@@ -117,11 +117,13 @@ def test_adaptive_error_control(ctx, oracle, name, scale):
         L = int(rs[0])
         assert st["last_round"] == L
         assert st["integrated"][0] == tasks.shape[0] and st["integrated"][1] == 4 * tasks.shape[0]
-        ties = 0
+        ties, carried = 0, 0
         for k in range(1, L + 1):
             d = abs(st["unconverged"][k] - int(rs[2 + 2 * k]))
             ties = max(ties, d)
-            assert d <= max(5, 4e-3 * int(rs[2 + 2 * k])), (name, cls, k, st, rs.tolist())
+            # a flipped borderline decision of round k also changes which tasks round k+1 sees: the previous difference is carried
+            assert d <= max(5, 4e-3 * int(rs[2 + 2 * k])) + carried, (name, cls, k, st, rs.tolist())
+            carried = d
         if name == "G1":
             assert ties == 0
         refm = r["refinements"].cpu().numpy()

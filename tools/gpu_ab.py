@@ -1,0 +1,30 @@
+"""A/B timing of the regular-pair kernel on Vint16k level 0 (device events around i2_host_run_rounds): run once per setting of
+the env knobs given on the command line, e.g.  python tools/gpu_ab.py I2_VEC_STORES=0 I2_VEC_STORES=1"""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CHILD = r'''
+import sys, os
+sys.path.insert(0, sys.argv[1])
+import torch
+from integrator2_b200 import abi
+from integrator2_b200.meshio import load_fixture
+m = load_fixture("Vint16k")
+c = abi.Context(0)
+c.host_prepare(m.vertices, m.cells)
+c.set_profiling(True)
+ts = []
+for _ in range(8):
+    c.host_run_rounds(0)
+    ts.append(c.profile_last()[0])
+print("regular kernel ms: min %.3f median %.3f" % (min(ts[2:]), sorted(ts[2:])[len(ts[2:]) // 2]), os.environ.get("AB_LABEL"))
+'''
+for setting in sys.argv[1:] or ["BASE=1"]:
+    env = dict(os.environ, AB_LABEL=setting)
+    for kv in setting.split(","):
+        k, v = kv.split("=")
+        env[k] = v
+    r = subprocess.run([sys.executable, "-c", CHILD, ROOT], env=env, capture_output=True, text=True)
+    print(r.stdout.strip() or r.stderr[-2000:], flush=True)
