@@ -301,6 +301,9 @@ int i2_selftest_math(i2_context *ctx, int op, const double *d_a, const double *d
 int i2_peak_rates(i2_context *ctx, double *dfma_tflops, double *mufu_gops);
 /* DFMA rate when every instruction reads three distinct 64-bit register operands (register-file bandwidth included) */
 int i2_peak_dfma_three_operand(i2_context *ctx, double *tflops);
+/* DFMA rate with int_per_dfma (0..3) independent integer instructions interleaved per DFMA: tells whether the dispatch port is
+ * free during the second cycle of a warp-wide FP64 instruction (rate unchanged) or not (rate drops)                          */
+int i2_peak_dfma_with_integer(i2_context *ctx, int int_per_dfma, double *tflops);
 
 #ifdef __cplusplus
 }

@@ -48,7 +48,7 @@ EXPORTS = [
     "i2_create", "i2_destroy", "i2_set_stream", "i2_synchronize", "i2_set_math_mode", "i2_error_string",
     "i2_set_quadrature", "i2_mesh_geometry", "i2_set_mesh", "i2_classify_count", "i2_classify_fill",
     "i2_add_reversed_pairs", "i2_integrate_class", "i2_integrate_pairs", "i2_integrate_all", "i2_symmetry_error", "i2_host_prepare", "i2_host_run",
-    "i2_host_device_views", "i2_host_checksums", "i2_peer_alloc", "i2_peer_open", "i2_peer_close", "i2_peer_free", "i2_host_set_shard", "i2_host_shard", "i2_peak_rates", "i2_peak_dfma_three_operand", "i2_refine_mesh_once", "i2_launch_count", "i2_set_profiling", "i2_profile_last", "i2_selftest_math", "i2_apply_regular", "i2_apply_regular_adaptive",
+    "i2_host_device_views", "i2_host_checksums", "i2_peer_alloc", "i2_peer_open", "i2_peer_close", "i2_peer_free", "i2_host_set_shard", "i2_host_shard", "i2_peak_rates", "i2_peak_dfma_three_operand", "i2_peak_dfma_with_integer", "i2_refine_mesh_once", "i2_launch_count", "i2_set_profiling", "i2_profile_last", "i2_selftest_math", "i2_apply_regular", "i2_apply_regular_adaptive",
     "i2_error_summary", "i2_host_row_costs", "i2_host_run_rounds", "i2_host_last_rounds", "i2_host_refinements", "i2_host_run_finalize", "i2_host_fetch", "i2_mgpu_unique_id", "i2_mgpu_create_rank", "i2_mgpu_create_local", "i2_mgpu_destroy", "i2_mgpu_info", "i2_mgpu_context",
     "i2_mgpu_set_quadrature", "i2_mgpu_set_math_mode", "i2_mgpu_synchronize", "i2_mgpu_prepare", "i2_mgpu_shard", "i2_mgpu_set_results_target",
     "i2_mgpu_run", "i2_mgpu_checksums", "i2_mgpu_gather", "i2_mgpu_fetch", "i2_mgpu_refinements", "i2_mgpu_error_summary",
@@ -101,6 +101,7 @@ def load_library():
     L.i2_set_profiling.argtypes = [vp, i32]
     L.i2_profile_last.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     L.i2_peak_dfma_three_operand.argtypes = [vp, C.POINTER(C.c_double)]
+    L.i2_peak_dfma_with_integer.argtypes = [vp, i32, C.POINTER(C.c_double)]
     L.i2_peak_rates.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.i2_host_set_shard.argtypes = [vp, i32, i32]
     L.i2_host_shard.argtypes = [vp, C.POINTER(ll), C.POINTER(ll)]
@@ -395,6 +396,11 @@ class Context:
         a, b = C.c_double(), C.c_double()
         _check(self.L.i2_peak_rates(self.h, C.byref(a), C.byref(b)))
         return float(a.value), float(b.value)
+
+    def peak_dfma_with_integer(self, n):
+        a = C.c_double()
+        _check(self.L.i2_peak_dfma_with_integer(self.h, int(n), C.byref(a)))
+        return float(a.value)
 
     def peak_dfma_three_operand(self):
         a = C.c_double()

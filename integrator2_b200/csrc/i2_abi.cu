@@ -1165,6 +1165,30 @@ int i2_peak_dfma_three_operand(i2_context *c, double *tflops) {
     return 0;
 }
 
+int i2_peak_dfma_with_integer(i2_context *c, int intPerDfma, double *tflops) {
+    if (!c || !tflops || intPerDfma < 0 || intPerDfma > 3) return I2_E_BADARG;
+    I2_CUDA(cudaSetDevice(c->device));
+    double *sink = nullptr;
+    I2_CUDA(cudaMalloc((void **)&sink, sizeof(double)));
+    cudaEvent_t e0, e1;
+    I2_CUDA(cudaEventCreate(&e0));
+    I2_CUDA(cudaEventCreate(&e1));
+    const int blocks = c->numSMs * 8, iters = 20000;
+    float ms = 0.f;
+    for (int rep = 0; rep < 3; ++rep) {
+        I2_CUDA(cudaEventRecord(e0, c->stream));
+        launch_peak_mix(intPerDfma, sink, iters, blocks, c->stream);
+        I2_CUDA(cudaEventRecord(e1, c->stream));
+        I2_CUDA(cudaEventSynchronize(e1));
+        I2_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    }
+    *tflops = (double)blocks * 256.0 * iters * 8.0 * 2.0 / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    return 0;
+}
+
 int i2_peak_rates(i2_context *c, double *dfmaTflops, double *mufuGops) {
     if (!c) return I2_E_BADARG;
     I2_CUDA(cudaSetDevice(c->device));

@@ -1274,6 +1274,27 @@ __global__ void __launch_bounds__(256) k_peak_dfma3(double *sink, const double *
     for (int k = 0; k < 8; ++k) r += a[k] + b[k];
     if (r == 123.456) sink[0] = r;
 }
+// DFMA chains interleaved with NI independent integer instructions per DFMA: does a warp-wide FP64 instruction (two cycles of
+// the sub-partition's FP64 pipe) also hold the DISPATCH port for two cycles, or can integer work issue in its shadow?
+template <int NI>
+__global__ void __launch_bounds__(256) k_peak_mix(double *sink, int iters, int seed) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    const int t = threadIdx.x * 2654435761u;   // per-thread values: keeps the integer work off the uniform datapath
+    int i0 = seed ^ t, i1 = i0 + 1, i2 = i0 + 2, i3 = i0 + 3, i4 = i0 + 4, i5 = i0 + 5, i6 = i0 + 6, i7 = i0 + 7;
+    for (int k = 0; k < iters; ++k) {
+#define I2_MIX(a, i)                                                           \
+        a = fma(a, m, c);                                                      \
+        if (NI >= 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(i) : "r"(t), "r"(k)); \
+        if (NI >= 2) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(i) : "r"(k), "r"(t)); \
+        if (NI >= 3) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(i) : "r"(t), "r"(seed));
+        I2_MIX(a0, i0) I2_MIX(a1, i1) I2_MIX(a2, i2) I2_MIX(a3, i3) I2_MIX(a4, i4) I2_MIX(a5, i5) I2_MIX(a6, i6) I2_MIX(a7, i7)
+#undef I2_MIX
+    }
+    const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    const int q = i0 ^ i1 ^ i2 ^ i3 ^ i4 ^ i5 ^ i6 ^ i7;
+    if (r == 123.456 || q == 0x7fffffff) sink[0] = r + q;
+}
 __global__ void __launch_bounds__(256) k_peak_mufu(double *sink, int iters) {
     double a0 = 1.5 + threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
     for (int k = 0; k < iters; ++k) {
@@ -1312,6 +1333,13 @@ cudaError_t preload_rest() {
 
 void launch_peak_dfma(double *sink, int iters, int blocks, cudaStream_t s) { ++g_launchCount; k_peak_dfma<<<blocks, 256, 0, s>>>(sink, iters); }
 void launch_peak_dfma3(double *sink, const double *seed, int iters, int blocks, cudaStream_t s) { ++g_launchCount; k_peak_dfma3<<<blocks, 256, 0, s>>>(sink, seed, iters); }
+void launch_peak_mix(int ni, double *sink, int iters, int blocks, cudaStream_t s) {
+    ++g_launchCount;
+    if (ni <= 0) k_peak_mix<0><<<blocks, 256, 0, s>>>(sink, iters, 12345);
+    else if (ni == 1) k_peak_mix<1><<<blocks, 256, 0, s>>>(sink, iters, 12345);
+    else if (ni == 2) k_peak_mix<2><<<blocks, 256, 0, s>>>(sink, iters, 12345);
+    else k_peak_mix<3><<<blocks, 256, 0, s>>>(sink, iters, 12345);
+}
 void launch_peak_mufu(double *sink, int iters, int blocks, cudaStream_t s) { ++g_launchCount; k_peak_mufu<<<blocks, 256, 0, s>>>(sink, iters); }
 
 }  // namespace i2

@@ -105,5 +105,6 @@ cudaError_t upload_quadrature(const double *Lxyzw, int n, double pow2p, cudaStre
 void launch_peak_dfma(double *sink, int iters, int blocks, cudaStream_t s);
 void launch_peak_dfma3(double *sink, const double *seed, int iters, int blocks, cudaStream_t s);
 void launch_peak_mufu(double *sink, int iters, int blocks, cudaStream_t s);
+void launch_peak_mix(int ni, double *sink, int iters, int blocks, cudaStream_t s);
 
 }  // namespace i2

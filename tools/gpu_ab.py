@@ -28,3 +28,12 @@ for setting in sys.argv[1:] or ["BASE=1"]:
         env[k] = v
     r = subprocess.run([sys.executable, "-c", CHILD, ROOT], env=env, capture_output=True, text=True)
     print(r.stdout.strip() or r.stderr[-2000:], flush=True)
+
+MIX = r'''
+import sys
+sys.path.insert(0, sys.argv[1])
+from integrator2_b200 import abi
+c = abi.Context(0)
+print("DFMA TFLOP/s with 0/1/2/3 independent LOP3 per DFMA:", [round(c.peak_dfma_with_integer(n), 2) for n in range(4)])
+'''
+print(subprocess.run([sys.executable, "-c", MIX, ROOT], capture_output=True, text=True).stdout.strip(), flush=True)
