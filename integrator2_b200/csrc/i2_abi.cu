@@ -290,7 +290,7 @@ int check_class_args(const i2_context *c, int cls, const int *tasks, long long n
 // grouped regular kernel the final assembly is fused (*fusedOut = true: the class is complete); otherwise enqueue_finalize
 // must follow.  half > 0: the list is [pairs ; reversed pairs] with `half` pairs (see k_regular_grouped).
 int enqueue_rounds(i2_context *c, int cls, const int *tasks, long long n, long long half, int level, double *integrals, double *results,
-                   unsigned char *refinements, unsigned char *converged, cudaStream_t s, bool profile, bool *fusedOut) {
+                   unsigned char *refinements, unsigned char *converged, cudaStream_t s, bool profile, bool *fusedOut, int kernelFlags = 0) {
     i2_context::ClassScratch &sc = c->scr[cls];
     const PackedMesh pm = packed(c);
     I2_CUDA(cudaMemsetAsync(sc.qs, 0, sizeof(QueueState), s));
@@ -300,7 +300,7 @@ int enqueue_rounds(i2_context *c, int cls, const int *tasks, long long n, long l
         if (profile) I2_CUDA(cudaEventRecord(c->prof[0], s));
         // regular pairs with the grouped kernel: the final assembly is fused into the integrate kernel
         *fusedOut = (cls == 2 && c->mathMode == I2_MATH_FAST);
-        launch_integrate(cls, c->mathMode, pm, tasks, nullptr, nullptr, n, half, level, integrals, *fusedOut ? results : nullptr, c->numSMs, s);
+        launch_integrate(cls, c->mathMode, pm, tasks, nullptr, nullptr, n, half, level, integrals, *fusedOut ? results : nullptr, c->numSMs, s, kernelFlags);
         if (profile) I2_CUDA(cudaEventRecord(c->prof[1], s));
     } else {
         int rc = ensure(&sc.bufB, &sc.bufBCap, (size_t)4 * n);
@@ -907,7 +907,8 @@ extern "C++" int i2::host_run_rounds(i2_context *c, int level) {
             bool fused = false;
             const bool prof = k == 2 && c->profiling && level >= 0;   // i2_set_profiling: device time of the regular class's kernels
             int rc = enqueue_rounds(c, k, c->hTasks[k], c->hN[k], c->hHalf[k], level, c->hIntegrals[k], results_of(c, k),
-                                    level < 0 ? c->hRefinements[k] : nullptr, nullptr, st, prof, &fused);
+                                    level < 0 ? c->hRefinements[k] : nullptr, nullptr, st, prof, &fused,
+                                    c->hResultsTarget[k] ? 1 : 0 /* results leave the GPU: full-sector stores */);
             if (!rc && level >= 0 && !fused) rc = enqueue_finalize(c, k, c->hTasks[k], c->hN[k], c->hIntegrals[k], results_of(c, k), st);
             if (rc) return rc;
             if (prof) I2_CUDA(cudaEventRecord(c->prof[2], st));

@@ -352,7 +352,7 @@ static __device__ __forceinline__ int raise_flag(int flagged, const PointTerms &
 // vmask = the lanes that decide together (the whole warp, or the 16 lanes of one task in the list-driven round 2 of the
 // adaptive queue, where the two tasks that share a warp depend on which other tasks are still unconverged: a task's
 // result must not depend on its warp-mate, or it would change with the partition of the list over GPUs)
-template <bool EDGELEN, bool RESID, bool DERIVE = false, bool PROJ = false, int MS = kThreads>
+template <bool EDGELEN, bool RESID, bool DERIVE = false, bool PROJ = false, int MS = kThreads, int UNR = kPointUnroll>
 static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, const TriJ &T, double &a1, double &a2, double &a3, double &a4,
                                                     const unsigned vmask = 0xffffffffu) {
     a1 = 0.0; a2 = 0.0; a3 = 0.0; a4 = 0.0;
@@ -372,7 +372,7 @@ static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, c
         PointTerms t = point();
         double pn1 = t.N1, pd1 = t.D1, pn2 = t.N2, pd2 = t.D2, pn3 = t.N3, pd3 = t.D3, zr = t.den, zi = t.num;
         int flagged = raise_flag<PROJ>(0, t, T, sq);
-#pragma unroll kPointUnroll
+#pragma unroll UNR
         while (pM != pEnd) {
             t = point();
             flagged = raise_flag<PROJ>(flagged, t, T, sq);
@@ -447,6 +447,7 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
     const long long count = countDev ? (long long)*countDev : countHost;
     constexpr bool EDGELEN = (VAR & 1) != 0, RESID = (VAR & 2) == 0, LEVEL0 = (VAR & 4) != 0, DERIVE = (VAR & 8) != 0 && EDGELEN;
     constexpr bool PROJ = (VAR & 16) != 0 && DERIVE;
+    constexpr int UNR = (VAR & 32) ? 1 : kPointUnroll;
     if (LEVEL0) level = 0;
     const LaneLayout lay(level);
     const int G = lay.G, perLane = lay.perLane;
@@ -486,7 +487,7 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
                 iStaged = perLane > 1 ? -1 : i;
             }
             double a1, a2, a3, a4;
-            grouped_eval<EDGELEN, RESID, DERIVE, PROJ>(myM, ng, T, a1, a2, a3, a4, vmask);
+            grouped_eval<EDGELEN, RESID, DERIVE, PROJ, kThreads, UNR>(myM, ng, T, a1, a2, a3, a4, vmask);
             if (LEVEL0) { s1 = Si * a1; s2 = Si * a2; s3 = Si * a3; s4 = Si * a4; }
             else { s1 = fma(Si, a1, s1); s2 = fma(Si, a2, s2); s3 = fma(Si, a3, s3); s4 = fma(Si, a4, s4); }
         }
@@ -968,12 +969,14 @@ void launch_reduce_partials_adaptive(const double *partial6, const unsigned char
 
 // tuning knob (env I2_MINBLOCKS = 3|4|5): resident CTAs per SM the regular kernel is compiled for
 static int g_minBlocks = [] { const char *e = getenv("I2_MINBLOCKS"); return e ? atoi(e) : 4; }();
-// bit 0: 16-byte coalesced result stores staged through shared memory (env I2_VEC_STORES=0 turns them off: A/B knob)
-static int g_kernelFlags = [] { const char *e = getenv("I2_VEC_STORES"); return (e && atoi(e) == 0) ? 0 : 1; }();
+// kernel flag bit 0: 16-byte coalesced result stores staged through shared memory.  Measured on Vint16k: 1.6 % SLOWER than the
+// strided 8-byte stores when the results stay in local HBM (L2 merges the partial sectors anyway), so the host asks for them only
+// when the results go to another GPU over NVLink (launch_integrate flags); env I2_VEC_STORES=1 forces them on (A/B knob)
+static int g_kernelFlags = [] { const char *e = getenv("I2_VEC_STORES"); return (e && atoi(e) != 0) ? 1 : 0; }();
 static int g_variant = [] { const char *e = getenv("I2_VARIANT"); return e ? atoi(e) : 27; }();
 
 void launch_integrate(int cls, int mathMode, const PackedMesh &pm, const int *tasks, const int *list, const int *countDev,
-                      long long countHost, long long half, int level, double *out4, double *fusedResults3, int numSMs, cudaStream_t s) {
+                      long long countHost, long long half, int level, double *out4, double *fusedResults3, int numSMs, cudaStream_t s, int flags) {
     if (!countDev && countHost <= 0) return;
     const int children = 1 << (2 * level);
     const int G = children < kThreads ? children : kThreads;   // LaneLayout
@@ -991,24 +994,23 @@ void launch_integrate(int cls, int mathMode, const PackedMesh &pm, const int *ta
     else if (mathMode == MATH_FAST_LIBDEVICE) { ++g_launchCount; k_integrate<2, MATH_FAST_LIBDEVICE, 4><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4); }
     else if (mathMode == MATH_FAST_POINTWISE) { ++g_launchCount; k_integrate<2, MATH_FAST_POINTWISE, 4><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, level, out4); }
     else {
-        // tuning knobs: I2_MINBLOCKS (3|4|5 resident CTAs/SM), I2_VARIANT (bit0 edge-length identity, bit1 no residual correction,
-        // bit3 derive d_b, d_c from d_a instead of reading B and C, bit4 projection form of the lengths/dots; default 27 = all);
+        // tuning knobs: I2_MINBLOCKS (3|4|5|6 resident CTAs/SM), I2_VARIANT (bit0 edge-length identity, bit1 no residual correction,
+        // bit3 derive d_b, d_c from d_a instead of reading B and C, bit4 projection form of the lengths/dots, bit5 point loop not
+        // unrolled; default 27 = bits 0,1,3,4);
         // the LEVEL0 specialisation (bit 2) is chosen automatically
-        const int var = (g_variant & 3) | (level == 0 ? 4 : 0) | (g_variant & 24);
+        const int var = (g_variant & 3) | (level == 0 ? 4 : 0) | (g_variant & 56);
         ++g_launchCount;
-#define I2_LAUNCH_GROUPED(MB, V) k_regular_grouped<MB, V><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, half, level, g_kernelFlags, out4, fusedResults3)
+#define I2_LAUNCH_GROUPED(MB, V) k_regular_grouped<MB, V><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, half, level, flags | g_kernelFlags, out4, fusedResults3)
 #define I2_PICK_VAR(MB)                                                                                              \
         switch (var) {                                                                                           \
-        case 0: I2_LAUNCH_GROUPED(MB, 0); break; case 1: I2_LAUNCH_GROUPED(MB, 1); break;                       \
-        case 2: I2_LAUNCH_GROUPED(MB, 2); break; case 3: I2_LAUNCH_GROUPED(MB, 3); break;                       \
-        case 4: I2_LAUNCH_GROUPED(MB, 4); break; case 5: I2_LAUNCH_GROUPED(MB, 5); break;                       \
-        case 6: I2_LAUNCH_GROUPED(MB, 6); break; case 7: I2_LAUNCH_GROUPED(MB, 7); break;                       \
-        case 11: I2_LAUNCH_GROUPED(MB, 11); break; case 15: I2_LAUNCH_GROUPED(MB, 15); break;                   \
+        case 7: I2_LAUNCH_GROUPED(MB, 7); break; case 15: I2_LAUNCH_GROUPED(MB, 15); break;                     \
         case 27: I2_LAUNCH_GROUPED(MB, 27); break; case 31: I2_LAUNCH_GROUPED(MB, 31); break;                   \
-        default: I2_LAUNCH_GROUPED(MB, 7); break;                                                                \
+        case 59: I2_LAUNCH_GROUPED(MB, 59); break; case 63: I2_LAUNCH_GROUPED(MB, 63); break;                   \
+        default: if (level == 0) I2_LAUNCH_GROUPED(MB, 31); else I2_LAUNCH_GROUPED(MB, 27); break;                       \
         }
         if (g_minBlocks == 3) { I2_PICK_VAR(3) }
         else if (g_minBlocks == 5) { I2_PICK_VAR(5) }
+        else if (g_minBlocks == 6) { I2_PICK_VAR(6) }
         else { I2_PICK_VAR(4) }
 #undef I2_PICK_VAR
 #undef I2_LAUNCH_GROUPED

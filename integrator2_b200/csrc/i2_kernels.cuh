@@ -52,7 +52,7 @@ void launch_geometry(const double *verts, const int *cells, int nc, double *norm
 // half > 0 (only with list == nullptr): the tasks are two segments [0, half) and [half, count) whose warp groups are formed
 // independently (pairs / reversed pairs of runAllPairs), see k_regular_grouped
 void launch_integrate(int cls, int mathMode, const PackedMesh &pm, const int *tasks, const int *list, const int *countDev,
-                      long long countHost, long long half, int level, double *out4, double *fusedResults3, int numSMs, cudaStream_t s);
+                      long long countHost, long long half, int level, double *out4, double *fusedResults3, int numSMs, cudaStream_t s, int flags = 0);
 void launch_apply_regular(const PackedMesh &pm, int rowLo, int rowHi, int colLo, int colHi, int chunks, const double *weights,
                           double *partial, double *out3, cudaStream_t s);
 // list-free regular class with the Runge loop per pair (see k_apply_regular_adaptive)
