@@ -532,32 +532,36 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
         // task saved); chunks are dealt round-robin to the warps of the grid.
         constexpr int kChunkIters = 16;
         const int groupsPerWarp = 32 / G, sub = lane & (G - 1);
-        const long long warpId = ((long long)blockIdx.x * kThreads + threadIdx.x) >> 5;
-        const long long warpStride = ((long long)gridDim.x * kThreads) >> 5;
-        const long long chunkTasks = (long long)groupsPerWarp * kChunkIters;
+        // 32-bit index arithmetic throughout (task counts fit an int: the reference's int3 slots); unsigned for the padded positions
+        const unsigned warpId = (blockIdx.x * kThreads + threadIdx.x) >> 5, warpStride = (gridDim.x * kThreads) >> 5;
+        const unsigned chunkTasks = (unsigned)groupsPerWarp * kChunkIters;
         // `half` > 0: the list is two segments, slots [0, half) and [half, count) (pairs and reversed pairs of
         // Evaluator3D::runAllPairs); the second segment starts a new warp iteration, so which tasks decide together depends
         // only on a task's position inside its segment — a shard made of 32-aligned pieces of both segments
         // (i2_host_set_shard, i2_mgpu_*) reproduces the unsharded run bit for bit.
-        const long long H = list ? 0 : half;
-        const long long P1 = (H + groupsPerWarp - 1) / groupsPerWarp * groupsPerWarp;   // first segment, padded to whole iterations
-        const long long padded = P1 + (count - H);
+        const int cnt = (int)count, H = list ? 0 : (int)half;
+        const unsigned P1 = (unsigned)(H + groupsPerWarp - 1) / groupsPerWarp * groupsPerWarp;   // first segment, padded to whole iterations
+        const unsigned padded = P1 + (unsigned)(cnt - H);
+        const int laneTask = lane / G;
         int iStaged = -1;
-        for (long long chunk = warpId; chunk * chunkTasks < padded; chunk += warpStride)
+        for (unsigned chunk = warpId; (unsigned long long)chunk * chunkTasks < padded; chunk += warpStride) {
+            const unsigned chunkBase = chunk * chunkTasks;
             for (int it = 0; it < kChunkIters; ++it) {
-                const long long base = chunk * chunkTasks + (long long)it * groupsPerWarp;
+                const unsigned base = chunkBase + (unsigned)(it * groupsPerWarp);
                 if (base >= padded) break;
-                const long long q = base + lane / G;
-                long long r = q < P1 ? q : H + (q - P1);
-                const long long segEnd = q < P1 ? H : count;
+                // a warp iteration never straddles the two segments (P1 is a multiple of the tasks per iteration)
+                const bool first = base < P1;
+                const int segEnd = first ? H : cnt;
+                int r = (int)(first ? base : base - P1 + (unsigned)H) + laneTask;
                 const bool active = r < segEnd;
                 if (!active) r = segEnd - 1;   // tail lanes recompute the segment's last task (no write) so that warp votes stay full-mask
-                const int slot = list ? __ldg(list + r) : (int)r;
+                const int slot = list ? __ldg(list + r) : r;
                 const int i = __ldg(tasks + 3 * (long long)slot), j = __ldg(tasks + 3 * (long long)slot + 1);
                 const d4 total = warp_sum(lane_work(i, j, sub, iStaged), G);
                 if (vecStores && __all_sync(0xffffffffu, active)) store_warp(slot - lane, j, total);
                 else if (active && sub == 0) store(slot, j, total);
             }
+        }
     } else {
         // deep refinement: the lanes of one task span G/32 warps of the CTA (see LaneLayout)
         const int tasksPerCTA = kThreads / G, sub = threadIdx.x & (G - 1), tIdx = threadIdx.x / G, warpsPerTask = G / 32;

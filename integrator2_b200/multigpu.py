@@ -1,4 +1,9 @@
-"""Multi-GPU sharding of the pair lists (one process per GPU, torch.distributed).
+"""Multi-GPU helpers on the Python side (one process per GPU, torch.distributed).
+
+The product's multi-GPU layer is native: i2_mgpu_* in include/i2_abi.h (integrator2_b200/abi.py: MultiGpu) shards the
+prepare, integrates, and runs NCCL inside the library.  What remains here: the host-side shard arithmetic (mirrored by tests),
+the cost model, PeerExport (CUDA IPC plumbing for the peer-store export) and `exchange_rounds`, the "bring your own
+communicator" variant of what i2_mgpu_run does between its two halves.
 
 The path shards naturally: every ordered pair (and every refined child of it) is independent
 (/root/reference has no multi-GPU code at all).  Each class's task list is cut into `world` contiguous shards of
@@ -81,6 +86,12 @@ def integrate_and_gather(ctx, cls, tasks_local, level, out_local, full, bounds, 
     n_local = int(tasks_local.shape[0])
     integrals, results = out_local
     works = []
+    if level < 0:
+        # error control: the value a converged task ends with depends on the parity of the LAST round of the list it was integrated
+        # with (the reference's result ping-pong) — a chunk would get its own last round.  One call per shard; a
+        # multi-GPU run that must reproduce the single-GPU values uses the C ABI's i2_mgpu_run (MultiGpu.run), which agrees on the
+        # last rounds across the GPUs before the final assembly.
+        chunks = 1
     n_max = max(hi - lo for lo, hi in bounds)
     step = max(1, -(-n_max // max(1, chunks)))           # same chunk grid on every rank
     main = torch.cuda.current_stream()
@@ -209,3 +220,34 @@ def cost_balanced_bounds(cost, world):
             cuts[r] = max(cuts[r], cuts[r - 1])
         return [(cuts[r], cuts[r + 1]) for r in range(world)]
     return shard_bounds(len(cost), world, cost)
+
+
+def forward_ranges(pairs: int, world: int):
+    """Forward-slot ranges [lo, hi) of the `world` shards of a class with `pairs` unordered pairs: equal counts, bounds at
+    multiples of 32 (the C side: i2_host_prepare / i2_mgpu_prepare).  Rank r owns those pairs in BOTH orders: its task list is
+    [pairs lo..hi ; their reversed pairs], 2 (hi - lo) tasks."""
+    cuts = [0] + [(pairs * r // world) & ~31 for r in range(1, world)] + [pairs]
+    for r in range(1, world + 1):
+        cuts[r] = max(cuts[r], cuts[r - 1])
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def exchange_rounds(ctx, level, check=False, group=None):
+    """What i2_mgpu_run does between i2_host_run_rounds and i2_host_run_finalize, with torch.distributed as the communicator
+    (any backend): under error control the shards agree on each class's last round and on the per-cell refinement counters
+    (element-wise maximum) before the final assembly.  `ctx` has run host_prepare with its shard set."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    ctx.host_run_rounds(level)
+    if level < 0 and dist.is_initialized() and dist.get_world_size(group) > 1:
+        last = torch.tensor(ctx.host_last_rounds(), dtype=torch.int32)
+        ref = torch.from_numpy(np.ascontiguousarray(ctx.host_refinements()))
+        if dist.get_backend(group) == "nccl":
+            dev = torch.device("cuda", torch.cuda.current_device())
+            last, ref = last.to(dev), ref.to(dev)
+        dist.all_reduce(last, op=dist.ReduceOp.MAX, group=group)
+        dist.all_reduce(ref, op=dist.ReduceOp.MAX, group=group)
+        ctx.host_last_rounds([int(x) for x in last.cpu().tolist()])
+        ctx.host_refinements(ref.cpu().numpy())
+    ctx.host_run_finalize(level, check)

@@ -121,3 +121,82 @@ def test_peer_export_bookkeeping_without_a_gpu():
     single = FakeCtx()
     e = PeerExport(single, 7, [(0, 7)], 0, 1)
     assert e.results_arg() == 1 << 20 and single.calls == [("alloc", 7)]
+
+
+def test_forward_ranges_tile_and_align():
+    from integrator2_b200.multigpu import forward_ranges
+    for pairs in (0, 5, 31, 32, 449, 143201825):
+        for world in (1, 2, 3, 8):
+            r = forward_ranges(pairs, world)
+            assert r[0][0] == 0 and r[-1][1] == pairs and len(r) == world
+            for (lo, hi), (lo2, _) in zip(r, r[1:]):
+                assert hi == lo2 and lo <= hi
+            assert all(lo % 32 == 0 for lo, _ in r)
+            if pairs >= 64 * world:      # balanced to within one warp group
+                sizes = [hi - lo for lo, hi in r]
+                assert max(sizes) - min(sizes) <= 64
+
+
+def _exchange_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from integrator2_b200.multigpu import exchange_rounds
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+
+    class FakeShard:
+        """records what exchange_rounds does to a context (no GPU here): local state in, agreed state out"""
+        def __init__(self):
+            self.nc = 4
+            self.last = [1, 3, 2] if rank == 0 else [4, 2, 2]
+            self.ref = np.array([[1, 2, 1, 0], [0, 0, 3, 1], [2, 2, 2, 2]], dtype=np.uint8) if rank == 0 else \
+                np.array([[2, 1, 1, 0], [1, 0, 1, 1], [2, 5, 2, 0]], dtype=np.uint8)
+            self.calls = []
+
+        def host_run_rounds(self, level):
+            self.calls.append(("rounds", level))
+
+        def host_last_rounds(self, set_to=None):
+            if set_to is not None:
+                self.last = list(set_to)
+            return list(self.last)
+
+        def host_refinements(self, set_to=None):
+            if set_to is not None:
+                self.ref = np.array(set_to, dtype=np.uint8)
+            return self.ref
+
+        def host_run_finalize(self, level, check=False):
+            self.calls.append(("finalize", level, check))
+
+    c = FakeShard()
+    exchange_rounds(c, -1, check=True)
+    q.put((rank, c.last, c.ref.tolist(), c.calls))
+    c2 = FakeShard()
+    exchange_rounds(c2, 0)            # fixed level: nothing to agree on
+    q.put((rank + 10, c2.last, c2.ref.tolist(), c2.calls))
+    dist.destroy_process_group()
+
+
+def test_exchange_rounds_world_size_2_gloo():
+    """The exchange step of a sharded run under error control (what i2_mgpu_run does with NCCL), with gloo and two processes:
+    every shard ends with the MAXIMUM of the last rounds and of the per-cell refinement counters, then finalizes."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(4):
+        k, last, ref, calls = q.get(timeout=120)
+        got[k] = (last, ref, calls)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in (0, 1):
+        assert got[r][0] == [4, 3, 2]
+        assert got[r][1] == [[2, 2, 1, 0], [1, 0, 3, 1], [2, 5, 2, 2]]
+        assert got[r][2] == [("rounds", -1), ("finalize", -1, True)]
+    assert got[10][0] == [1, 3, 2] and got[11][0] == [4, 2, 2]          # untouched at a fixed level
+    assert got[10][2] == [("rounds", 0), ("finalize", 0, False)]
