@@ -370,9 +370,14 @@ def main():
                   "what": f"{world - 1} ranks copy their regular-class result shard (torch copy_ = cudaMemcpy-class kernel) into rank 0's "
                           "peer-mapped array simultaneously: the NVLink ingest ceiling of one GPU on this box"}
         if rank == 0:
+            floor_ms = into0 / 1e9 / ingest["gb_per_s"] * 1e3      # the bytes alone at the copy ceiling, nothing else running
             for info in (gather_info, peer_info):
+                info["extra_ms_over_resident_step"] = info["ms_per_step"] - ms_step
                 info["ingest_gb_per_s"] = info["bytes_into_rank0_per_step"] / (info["ms_per_step"] * 1e-3) / 1e9
-                info["frac_of_copy_ceiling_if_nothing_else_ran"] = (info["bytes_into_rank0_per_step"] / 1e9 / ingest["gb_per_s"]) / (info["ms_per_step"] * 1e-3)
+                # lower bound of an export step: the slower of the resident step and the ingest of rank 0 at the copy ceiling
+                info["bound_ms"] = max(ms_step, floor_ms)
+                info["frac_of_bound"] = info["bound_ms"] / info["ms_per_step"]
+            ingest["ms_for_this_export_at_ceiling"] = floor_ms
         barrier()
         mg.set_results_target(0, None)
         del dst, src

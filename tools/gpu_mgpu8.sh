@@ -6,10 +6,8 @@ nvidia-smi -L > gpurun_out/e_gpus.txt
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1 --master-port 29512"
 timeout 900 $TR --nproc-per-node 8 bench.py --gpus 8 --no-cpu > gpurun_out/e_bench_n8.json 2> gpurun_out/e_bench_n8.err
 tail -c 3000 gpurun_out/e_bench_n8.json; tail -3 gpurun_out/e_bench_n8.err
-timeout 900 python bench.py --no-cpu > gpurun_out/e_bench_n1.json 2> gpurun_out/e_bench_n1.err
 timeout 900 $TR --nproc-per-node 4 bench.py --gpus 4 --no-cpu > gpurun_out/e_bench_n4.json 2> gpurun_out/e_bench_n4.err
 timeout 600 $TR --nproc-per-node 8 bench.py --gpus 8 --mesh s5m2 --scale 0.0005 --level -1 --no-cpu --no-largest > gpurun_out/e_bench_s5m2_ad_n8.json 2> gpurun_out/e_bench_s5m2_ad_n8.err
-timeout 600 python bench.py --mesh s5m2 --scale 0.0005 --level -1 --no-cpu --no-largest > gpurun_out/e_bench_s5m2_ad_n1.json 2> gpurun_out/e_bench_s5m2_ad_n1.err
 # the drop-in CLI on 8 GPUs vs 1 (its own wall-clock line)
 python - <<'PY'
 import sys
@@ -18,10 +16,10 @@ from integrator2_b200.meshio import load_fixture, write_dat
 write_dat("/tmp/Vint16k.dat", load_fixture("Vint16k"))
 PY
 cd /tmp
-for g in 8 1; do I2_GPUS=$g timeout 600 "$GRAFT_REPO_ROOT/integrator2_b200/host/integrator2test3D" -f /tmp/Vint16k.dat -r 0 -c > "$GRAFT_REPO_ROOT/gpurun_out/e_cli_gpus$g.txt" 2>&1; done
+for g in 8; do I2_GPUS=$g timeout 600 "$GRAFT_REPO_ROOT/integrator2_b200/host/integrator2test3D" -f /tmp/Vint16k.dat -r 0 -c > "$GRAFT_REPO_ROOT/gpurun_out/e_cli_gpus$g.txt" 2>&1; done
 cd "$GRAFT_REPO_ROOT"
-grep -E "Time for|Symmetry" gpurun_out/e_cli_gpus8.txt gpurun_out/e_cli_gpus1.txt
-for f in gpurun_out/e_bench_n1.json gpurun_out/e_bench_n4.json gpurun_out/e_bench_n8.json gpurun_out/e_bench_s5m2_ad_n1.json gpurun_out/e_bench_s5m2_ad_n8.json; do python - "$f" <<'PY'
+grep -E "Time for|Symmetry" gpurun_out/e_cli_gpus8.txt
+for f in gpurun_out/e_bench_n4.json gpurun_out/e_bench_n8.json gpurun_out/e_bench_s5m2_ad_n8.json; do python - "$f" <<'PY'
 import json, sys
 try:
     d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
