@@ -177,7 +177,7 @@ int i2_set_quadrature(i2_context *c, const double *xy, const double *w, int n, i
         packed4[4 * g + 2] = 1.0 - xy[2 * g] - xy[2 * g + 1];  // as NumericalIntegrator3D's ctor (src/NumericalIntegrator3d.cu:202-206)
         packed4[4 * g + 3] = w[g];
     }
-    I2_CUDA(upload_quadrature(packed4, n, (double)(1 << order), c->stream));
+    I2_CUDA(upload_quadrature(packed4, n, (double)(1 << order), c->stream, &c->ruleShape13));
     I2_CUDA(cudaStreamSynchronize(c->stream));  // packed4 lives on this stack frame
     c->haveQuad = true;
     return 0;
@@ -300,7 +300,8 @@ int enqueue_rounds(i2_context *c, int cls, const int *tasks, long long n, long l
         if (profile) I2_CUDA(cudaEventRecord(c->prof[0], s));
         // regular pairs with the grouped kernel: the final assembly is fused into the integrate kernel
         *fusedOut = (cls == 2 && c->mathMode == I2_MATH_FAST);
-        launch_integrate(cls, c->mathMode, pm, tasks, nullptr, nullptr, n, half, level, integrals, *fusedOut ? results : nullptr, c->numSMs, s, kernelFlags);
+        launch_integrate(cls, c->mathMode, pm, tasks, nullptr, nullptr, n, half, level, integrals, *fusedOut ? results : nullptr, c->numSMs, s,
+                         kernelFlags | (c->ruleShape13 ? 2 : 0));
         if (profile) I2_CUDA(cudaEventRecord(c->prof[1], s));
     } else {
         int rc = ensure(&sc.bufB, &sc.bufBCap, (size_t)4 * n);
@@ -319,7 +320,7 @@ int enqueue_rounds(i2_context *c, int cls, const int *tasks, long long n, long l
         I2_CUDA(cudaMemsetAsync(sc.cellFlag, 0, c->nc, s));
 
         // round 0: every task on the original control panel; every control panel present in the list is marked
-        launch_integrate(cls, c->mathMode, pm, tasks, nullptr, nullptr, n, half, 0, integrals, nullptr, c->numSMs, s);
+        launch_integrate(cls, c->mathMode, pm, tasks, nullptr, nullptr, n, half, 0, integrals, nullptr, c->numSMs, s, c->ruleShape13 ? 2 : 0);
         launch_flag_cells(tasks, n, sc.cellFlag, s);
         launch_bump(sc.cellFlag, refinements, c->nc, s);
         // rounds 1..5 are enqueued unconditionally; a round whose device-side task count is 0 does nothing.
@@ -328,7 +329,7 @@ int enqueue_rounds(i2_context *c, int cls, const int *tasks, long long n, long l
             const double *prev = (m & 1) ? integrals : sc.bufB;
             const int *listIn = m == 1 ? nullptr : sc.rest[0];
             const int *countIn = m == 1 ? nullptr : &sc.qs->count[m - 1];
-            launch_integrate(cls, c->mathMode, pm, tasks, listIn, countIn, n, m == 1 ? half : 0, m, cur, nullptr, c->numSMs, s);
+            launch_integrate(cls, c->mathMode, pm, tasks, listIn, countIn, n, m == 1 ? half : 0, m, cur, nullptr, c->numSMs, s, c->ruleShape13 ? 2 : 0);
             launch_compare(cur, prev, tasks, listIn, countIn, n, sc.rest[1], sc.blockCnt, sc.rest[0], &sc.qs->count[m], sc.cellFlag, converged, sc.qs, m,
                            c->numSMs, s);
             launch_bump(sc.cellFlag, refinements, c->nc, s);

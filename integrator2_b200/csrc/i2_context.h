@@ -13,6 +13,7 @@ struct i2_context {
     bool ownStream = false;
     int mathMode = I2_MATH_FAST;
     bool haveQuad = false;
+    bool ruleShape13 = false;   // the rule has the 1 + 3 + 3 + 6 equal-weight structure of Cowper's 13-point rule (straight-line kernel variant)
 
     // borrowed mesh arrays + owned SoA pack
     const double *verts = nullptr;

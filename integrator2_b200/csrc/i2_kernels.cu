@@ -35,7 +35,7 @@ cudaError_t upload_math_tables(cudaStream_t s) {
     return cudaMemcpyToSymbolAsync(c_mathTable, h_mathTable, sizeof(double) * I2_MATH_TABLE_SIZE, 0, cudaMemcpyHostToDevice, s);
 }
 
-cudaError_t upload_quadrature(const double *Lxyzw, int n, double pow2p, cudaStream_t s) {
+cudaError_t upload_quadrature(const double *Lxyzw, int n, double pow2p, cudaStream_t s, bool *shape13) {
     cudaError_t e = cudaMemcpyToSymbolAsync(c_gauss, Lxyzw, sizeof(double) * 4 * n, 0, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbolAsync(c_ngauss, &n, sizeof(int), 0, cudaMemcpyHostToDevice, s);
@@ -51,6 +51,7 @@ cudaError_t upload_quadrature(const double *Lxyzw, int n, double pow2p, cudaStre
         groupEnd[g] = last ? 1 : 0;
         if (last) { run = 0; groupStart[++ngroups] = g + 1; }
     }
+    if (shape13) *shape13 = n == 13 && ngroups == 4 && groupStart[1] == 1 && groupStart[2] == 4 && groupStart[3] == 7 && groupStart[4] == 13;
     e = cudaMemcpyToSymbolAsync(c_groupEnd, groupEnd, sizeof(int) * n, 0, cudaMemcpyHostToDevice, s);
     if (e != cudaSuccess) return e;
     e = cudaMemcpyToSymbolAsync(c_groupStart, groupStart, sizeof(int) * (ngroups + 1), 0, cudaMemcpyHostToDevice, s);
@@ -352,16 +353,16 @@ static __device__ __forceinline__ int raise_flag(int flagged, const PointTerms &
 // vmask = the lanes that decide together (the whole warp, or the 16 lanes of one task in the list-driven round 2 of the
 // adaptive queue, where the two tasks that share a warp depend on which other tasks are still unconverged: a task's
 // result must not depend on its warp-mate, or it would change with the partition of the list over GPUs)
-template <bool EDGELEN, bool RESID, bool DERIVE = false, bool PROJ = false, int MS = kThreads, int UNR = kPointUnroll>
+// FIX = 13: the rule has the group structure of Cowper's 13-point rule (runs of equal weights 1 + 3 + 3 + 6, checked on the host when
+// the rule is uploaded): the four groups and their points become straight-line code — no loop counters, no constant-bank loads of
+// the group table, the weights as immediate constant operands — and the compiler may overlap the loads / seeds of one point with
+// the arithmetic of the previous one.  Same operations in the same order: results are bit-identical to the generic loop.
+template <bool EDGELEN, bool RESID, bool DERIVE = false, bool PROJ = false, int MS = kThreads, int UNR = kPointUnroll, int FIX = 0>
 static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, const TriJ &T, double &a1, double &a2, double &a3, double &a4,
                                                     const unsigned vmask = 0xffffffffu) {
     a1 = 0.0; a2 = 0.0; a3 = 0.0; a4 = 0.0;
-    const int ngroups = c_ngroups;
-    int g = 0;
-#pragma unroll 1
-    for (int grp = 0; grp < ngroups; ++grp) {
-        const int gStart = g, gEnd = c_groupStart[grp + 1];
-        const double *pM = myM + 3 * MS * gStart, *const pEnd = myM + 3 * MS * gEnd;
+    auto do_group = [&](const int gStart, const int gEnd) {
+        const double *pM = myM + 3 * MS * gStart;
         double sq[3];
         auto point = [&]() -> PointTerms {
             const d3 M = {pM[0], pM[MS], pM[2 * MS]};
@@ -372,8 +373,7 @@ static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, c
         PointTerms t = point();
         double pn1 = t.N1, pd1 = t.D1, pn2 = t.N2, pd2 = t.D2, pn3 = t.N3, pd3 = t.D3, zr = t.den, zi = t.num;
         int flagged = raise_flag<PROJ>(0, t, T, sq);
-#pragma unroll UNR
-        while (pM != pEnd) {
+        auto next_point = [&]() {
             t = point();
             flagged = raise_flag<PROJ>(flagged, t, T, sq);
             pn1 *= t.N1; pd1 *= t.D1; pn2 *= t.N2; pd2 *= t.D2; pn3 *= t.N3; pd3 *= t.D3;
@@ -381,8 +381,14 @@ static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, c
             zi = zi * t.den;
             zi = fma(zr, t.num, zi);
             zr = fma(zr, t.den, -zin);
+        };
+        if (FIX) {
+#pragma unroll
+            for (int p = gStart + 1; p < gEnd; ++p) next_point();
+        } else {
+#pragma unroll UNR
+            for (int p = gStart + 1; p < gEnd; ++p) next_point();
         }
-        g = gEnd;
         const double w = c_gauss[4 * gStart + 3], w2 = w + w;
         double th;
         if (__all_sync(vmask, !flagged)) {
@@ -394,6 +400,7 @@ static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, c
             // careful form for the whole warp: epsilon fallback applied, angles added one by one
             pn1 = pd1 = pn2 = pd2 = pn3 = pd3 = 1.0;
             th = 0.0;
+#pragma unroll 1
             for (int h = gStart; h < gEnd; ++h) {
                 const d3 Mh = {myM[(3 * h + 0) * MS], myM[(3 * h + 1) * MS], myM[(3 * h + 2) * MS]};
                 PointTerms u = point_terms_raw<EDGELEN, DERIVE>(Mh, T);
@@ -423,6 +430,18 @@ static __device__ __forceinline__ void grouped_eval(const double *myM, int ng, c
             a3 = fma(w, log_ratio<RESID>(pn3, pd3), a3);
         }
         a4 = fma(w2, th, a4);
+    };
+    if (FIX == 13) {
+        do_group(0, 1); do_group(1, 4); do_group(4, 7); do_group(7, 13);
+    } else {
+        const int ngroups = c_ngroups;
+        int g = 0;
+#pragma unroll 1
+        for (int grp = 0; grp < ngroups; ++grp) {
+            const int gEnd = c_groupStart[grp + 1];
+            do_group(g, gEnd);
+            g = gEnd;
+        }
     }
 }
 
@@ -448,6 +467,7 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
     constexpr bool EDGELEN = (VAR & 1) != 0, RESID = (VAR & 2) == 0, LEVEL0 = (VAR & 4) != 0, DERIVE = (VAR & 8) != 0 && EDGELEN;
     constexpr bool PROJ = (VAR & 16) != 0 && DERIVE;
     constexpr int UNR = (VAR & 32) ? 1 : kPointUnroll;
+    constexpr int FIX = (VAR & 64) ? 13 : 0;
     if (LEVEL0) level = 0;
     const LaneLayout lay(level);
     const int G = lay.G, perLane = lay.perLane;
@@ -487,7 +507,7 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
                 iStaged = perLane > 1 ? -1 : i;
             }
             double a1, a2, a3, a4;
-            grouped_eval<EDGELEN, RESID, DERIVE, PROJ, kThreads, UNR>(myM, ng, T, a1, a2, a3, a4, vmask);
+            grouped_eval<EDGELEN, RESID, DERIVE, PROJ, kThreads, UNR, FIX>(myM, ng, T, a1, a2, a3, a4, vmask);
             if (LEVEL0) { s1 = Si * a1; s2 = Si * a2; s3 = Si * a3; s4 = Si * a4; }
             else { s1 = fma(Si, a1, s1); s2 = fma(Si, a2, s2); s3 = fma(Si, a3, s3); s4 = fma(Si, a4, s4); }
         }
@@ -977,6 +997,9 @@ static int g_minBlocks = [] { const char *e = getenv("I2_MINBLOCKS"); return e ?
 // strided 8-byte stores when the results stay in local HBM (L2 merges the partial sectors anyway), so the host asks for them only
 // when the results go to another GPU over NVLink (launch_integrate flags); env I2_VEC_STORES=1 forces them on (A/B knob)
 static int g_kernelFlags = [] { const char *e = getenv("I2_VEC_STORES"); return (e && atoi(e) != 0) ? 1 : 0; }();
+// the straight-line variant for rules with the group structure of Cowper's 13-point rule (launch flag bit 1, set by the context when
+// upload_quadrature recognised the shape; env I2_FIX13=0 turns it off: A/B knob)
+static int g_fix13 = [] { const char *e = getenv("I2_FIX13"); return (e && atoi(e) == 0) ? 0 : 1; }();
 static int g_variant = [] { const char *e = getenv("I2_VARIANT"); return e ? atoi(e) : 27; }();
 
 void launch_integrate(int cls, int mathMode, const PackedMesh &pm, const int *tasks, const int *list, const int *countDev,
@@ -1002,14 +1025,15 @@ void launch_integrate(int cls, int mathMode, const PackedMesh &pm, const int *ta
         // bit3 derive d_b, d_c from d_a instead of reading B and C, bit4 projection form of the lengths/dots, bit5 point loop not
         // unrolled; default 27 = bits 0,1,3,4);
         // the LEVEL0 specialisation (bit 2) is chosen automatically
-        const int var = (g_variant & 3) | (level == 0 ? 4 : 0) | (g_variant & 56);
+        const int var = (g_variant & 3) | (level == 0 ? 4 : 0) | (g_variant & 56) | ((g_fix13 && (flags & 2)) ? 64 : 0);
         ++g_launchCount;
-#define I2_LAUNCH_GROUPED(MB, V) k_regular_grouped<MB, V><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, half, level, flags | g_kernelFlags, out4, fusedResults3)
+#define I2_LAUNCH_GROUPED(MB, V) k_regular_grouped<MB, V><<<gb, kThreads, 0, s>>>(pm, tasks, list, countDev, countHost, half, level, (flags & 1) | g_kernelFlags, out4, fusedResults3)
 #define I2_PICK_VAR(MB)                                                                                              \
         switch (var) {                                                                                           \
         case 7: I2_LAUNCH_GROUPED(MB, 7); break; case 15: I2_LAUNCH_GROUPED(MB, 15); break;                     \
         case 27: I2_LAUNCH_GROUPED(MB, 27); break; case 31: I2_LAUNCH_GROUPED(MB, 31); break;                   \
         case 59: I2_LAUNCH_GROUPED(MB, 59); break; case 63: I2_LAUNCH_GROUPED(MB, 63); break;                   \
+        case 91: I2_LAUNCH_GROUPED(MB, 91); break; case 95: I2_LAUNCH_GROUPED(MB, 95); break;                   \
         default: if (level == 0) I2_LAUNCH_GROUPED(MB, 31); else I2_LAUNCH_GROUPED(MB, 27); break;                       \
         }
         if (g_minBlocks == 3) { I2_PICK_VAR(3) }

@@ -100,7 +100,7 @@ void launch_take_rows(const unsigned char *perCell, int rowLo, int rows, unsigne
 void launch_selftest_math(int op, const double *a, const double *b, long long n, double *out, cudaStream_t s);
 cudaError_t upload_math_tables(cudaStream_t s);
 cudaError_t preload_kernels();
-cudaError_t upload_quadrature(const double *Lxyzw, int n, double pow2p, cudaStream_t s);
+cudaError_t upload_quadrature(const double *Lxyzw, int n, double pow2p, cudaStream_t s, bool *shape13 = nullptr);
 // FP64-pipe / MUFU peak micro-benchmarks: returns elapsed ms for `iters` dependent-chain iterations
 void launch_peak_dfma(double *sink, int iters, int blocks, cudaStream_t s);
 void launch_peak_dfma3(double *sink, const double *seed, int iters, int blocks, cudaStream_t s);

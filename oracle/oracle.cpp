@@ -779,6 +779,37 @@ void orc_symmetry_error(const double *results, long long n, double *errors) {
     }
 }
 
+// TEST TOLERANCE MODEL (not part of the reference): first-order bound of the rounding noise of thetaPsi
+// (src/evaluators/evaluatorJ3DK.cu:266-313) integrated over control panel i with the current rule, level 0 — the C twin of
+// tests/helpers.py::_noise_bound_panels, here because the sampled-row parity tests of the 1e5-triangle meshes need it for 1e7 pairs.
+void orc_noise_bound(void *h, const int *tasks, long long n, double *out) {
+    const Mesh &m = *static_cast<const Mesh *>(h);
+    const double u = std::ldexp(1.0, -53);
+#pragma omp parallel for schedule(static)
+    for (long long t = 0; t < n; ++t) {
+        const Tri ci = m.cells[tasks[3 * t]], cj = m.cells[tasks[3 * t + 1]];
+        const V3 I0 = vert(m, ci.a), I1 = vert(m, ci.b), I2 = vert(m, ci.c);
+        const V3 A = vert(m, cj.a), B = vert(m, cj.b), C = vert(m, cj.c);
+        const double Si = 0.5 * len(cross(sub(I1, I0), sub(I2, I0)));
+        const V3 ta = unit(sub(C, B)), tb = unit(sub(A, C)), tc = unit(sub(B, A));
+        double acc = 0.0;
+        for (int g = 0; g < g_qf.n; ++g) {
+            const V3 L = g_qf.L[g];
+            const V3 M = add(add(mul(L.x, I0), mul(L.y, I1)), mul(L.z, I2));
+            const V3 oa = unit(sub(M, A)), ob = unit(sub(M, B)), oc = unit(sub(M, C));
+            auto term = [](V3 o1, V3 o2, V3 tt) {
+                return 2.0 / std::max(1.0 + dot(o1, tt), 1e-300) + 2.0 / std::max(1.0 + dot(o2, tt), 1e-300) + 4.0;
+            };
+            const double terms = term(oa, ob, tc) + term(ob, oc, ta) + term(oc, oa, tb);
+            const double y = dot(cross(oa, ob), oc);
+            const double x = 1.0 + dot(oa, ob) + dot(ob, oc) + dot(oc, oa);
+            const double dtheta = 8.0 * (std::fabs(x) + std::fabs(y)) / std::max(x * x + y * y, 1e-300);
+            acc += std::fabs(g_qf.w[g]) * (terms + dtheta);
+        }
+        out[t] = u * acc * Si * 0.079577471545947667884;
+    }
+}
+
 int orc_num_threads() {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -61,6 +61,7 @@ def lib():
         L.orc_run_class.argtypes = [vp, C.c_int, ip, ll, C.c_int, dp, dp, C.POINTER(C.c_ubyte), C.POINTER(ll)]
         L.orc_run_class.restype = C.c_int
         L.orc_symmetry_error.argtypes = [dp, ll, dp]
+        L.orc_noise_bound.argtypes = [vp, ip, ll, dp]
         L.orc_num_threads.restype = C.c_int
         _LIB = L
         set_quadrature(QF13_XY, QF13_W, QF13_ORDER)
@@ -165,6 +166,14 @@ class OracleMesh:
         tasks = np.ascontiguousarray(tasks, dtype=np.int32)
         out = np.empty((tasks.shape[0], 3))
         lib().orc_regular_results_quad(self._h, _ip(tasks), tasks.shape[0], int(level), _dp(out))
+        return out
+
+    def noise_bound(self, tasks):
+        """first-order rounding-noise bound of the reference formula per regular task, level 0 (the tolerance model of
+        tests/helpers.py::reference_noise_bound, evaluated in C/OpenMP for large task sets)"""
+        tasks = np.ascontiguousarray(tasks, dtype=np.int32)
+        out = np.empty(tasks.shape[0])
+        lib().orc_noise_bound(self._h, _ip(tasks), tasks.shape[0], _dp(out))
         return out
 
     def run_class(self, cls, tasks, level=0):

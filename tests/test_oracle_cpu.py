@@ -118,3 +118,14 @@ def test_subdivide_matches_child_enumeration(oracle):
         tt = np.stack([4 * t[:, 0] + k, t[:, 1] + sub.n_cells, t[:, 2]], axis=1).astype(np.int32)
         acc += mixed.regular_integrals(2, tt, 0)
     assert np.abs(acc - I1).max() <= 1e-13 * np.abs(I1).max()
+
+
+def test_noise_bound_c_twin_matches_the_numpy_model(oracle):
+    """orc_noise_bound (C/OpenMP, used for the 1e7-pair blocks of the largest-mesh parity tests) == helpers.reference_noise_bound"""
+    from helpers import reference_noise_bound
+    from integrator2_b200.meshio import load_fixture
+    m = load_fixture("s5m", 0.0005)
+    om = oracle.OracleMesh(m.vertices, m.cells)
+    t = om.tasks(2)[::97]
+    a, b = reference_noise_bound(m.vertices, m.cells, t), om.noise_bound(t)
+    assert np.allclose(a, b, rtol=1e-6, atol=0)
