@@ -240,6 +240,8 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    per_rank_ms = []     # device time of every rank for the last timed_steps call (the step time is their maximum)
+
     def timed_steps(fn, steps, warm):
         with torch.cuda.stream(stream):
             for _ in range(warm):
@@ -254,9 +256,11 @@ def main():
         barrier()
         ms = e0.elapsed_time(e1)
         if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+            every = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+            dist.all_gather(every, torch.tensor([ms], dtype=torch.float64, device=dev))
+            per_rank_ms.clear()
+            per_rank_ms.extend(float(x.item()) / steps for x in every)
+            ms = max(float(x.item()) for x in every)
         return ms / steps
 
     with torch.cuda.stream(stream):
@@ -270,6 +274,7 @@ def main():
     launches0 = abi.launch_count()
     ms_step = timed_steps(step, args.steps, 0)
     launches = abi.launch_count() - launches0
+    step_per_rank_ms = list(per_rank_ms)
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         lt = torch.tensor([launches], dtype=torch.int64, device=dev)
@@ -463,7 +468,8 @@ def main():
                            "sharding": f"{world} shards per class through i2_mgpu_* (pairs with forward slots [lo, hi), multiples of 32, in both orders; "
                                        "results row-striped per rank; error control: NCCL all-reduce of last rounds and refinement counters in the step)",
                            "l2": "inputs+outputs per step (task lists 12 B/pair, results 56 B/pair) are far larger than L2; no flush needed"},
-                "clocks": clocks, "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
+                "clocks": clocks, "gpu_launches": launches, "per_rank_ms_per_step": step_per_rank_ms or None, "e2e": e2e, "roofline": roof,
+                "cpu_baseline": cpu,
                 "with_gather_to_rank0": gather_info, "with_peer_store_to_rank0": peer_info, "nvlink_ingest": ingest,
                 "largest_mesh": largest, "checksum_sum_abs_J": checksum}
         print(json.dumps(line), flush=True)

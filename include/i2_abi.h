@@ -211,6 +211,9 @@ int i2_host_row_costs(i2_context *ctx, int upper_only, double *h_cost, unsigned 
  * (element-wise maximum; i2_host_refinements gets / sets unsigned char[3][nc]); i2_host_run_finalize adds the closed-form
  * singular parts, assembles J and, with check != 0, computes the (i,j)/(j,i) defects; i2_host_fetch copies a class of the shard
  * (tasks, results, defects; any may be NULL) to the host.  i2_mgpu_run is exactly this sequence with NCCL in the middle.     */
+/* allocates the scratch the next run of this level needs (work queue, second result buffer, defect arrays): keeps cudaMalloc out
+ * of a caller's timed region (the reference allocates its buffers before its timers start, src/evaluators/evaluator3d.cu:122-154) */
+int i2_host_reserve(i2_context *ctx, int level, int check);
 int i2_host_run_rounds(i2_context *ctx, int level);
 int i2_host_last_rounds(i2_context *ctx, int h_last[3], int set);
 int i2_host_refinements(i2_context *ctx, unsigned char *h_refinements, int set);
@@ -253,6 +256,7 @@ int i2_mgpu_synchronize(i2_mgpu *mg);
 int i2_mgpu_prepare(i2_mgpu *mg, const double *h_vertices, int nv, const int *h_cells, int nc, int level, long long h_task_counts[3]);
 int i2_mgpu_shard(i2_mgpu *mg, int rank, long long h_first[3], long long h_count[3]);
 int i2_mgpu_set_results_target(i2_mgpu *mg, int local_index, double *const d_results[3]);
+int i2_mgpu_reserve(i2_mgpu *mg, int level, int check);   /* i2_host_reserve on every local GPU */
 int i2_mgpu_run(i2_mgpu *mg, int level, int check, i2_stats h_stats[3]);
 int i2_mgpu_checksums(i2_mgpu *mg, double h_sums[12]);
 int i2_mgpu_gather(i2_mgpu *mg, int cls, int what, int root, void *d_dst);

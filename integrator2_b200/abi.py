@@ -49,7 +49,7 @@ EXPORTS = [
     "i2_set_quadrature", "i2_mesh_geometry", "i2_set_mesh", "i2_classify_count", "i2_classify_fill",
     "i2_add_reversed_pairs", "i2_integrate_class", "i2_integrate_pairs", "i2_integrate_all", "i2_symmetry_error", "i2_host_prepare", "i2_host_run",
     "i2_host_device_views", "i2_host_checksums", "i2_peer_alloc", "i2_peer_open", "i2_peer_close", "i2_peer_free", "i2_host_set_shard", "i2_host_shard", "i2_peak_rates", "i2_peak_dfma_three_operand", "i2_peak_dfma_with_integer", "i2_refine_mesh_once", "i2_launch_count", "i2_set_profiling", "i2_profile_last", "i2_selftest_math", "i2_apply_regular", "i2_apply_regular_adaptive",
-    "i2_error_summary", "i2_host_row_costs", "i2_host_run_rounds", "i2_host_last_rounds", "i2_host_refinements", "i2_host_run_finalize", "i2_host_fetch", "i2_mgpu_unique_id", "i2_mgpu_create_rank", "i2_mgpu_create_local", "i2_mgpu_destroy", "i2_mgpu_info", "i2_mgpu_context",
+    "i2_error_summary", "i2_host_reserve", "i2_mgpu_reserve", "i2_host_row_costs", "i2_host_run_rounds", "i2_host_last_rounds", "i2_host_refinements", "i2_host_run_finalize", "i2_host_fetch", "i2_mgpu_unique_id", "i2_mgpu_create_rank", "i2_mgpu_create_local", "i2_mgpu_destroy", "i2_mgpu_info", "i2_mgpu_context",
     "i2_mgpu_set_quadrature", "i2_mgpu_set_math_mode", "i2_mgpu_synchronize", "i2_mgpu_prepare", "i2_mgpu_shard", "i2_mgpu_set_results_target",
     "i2_mgpu_run", "i2_mgpu_checksums", "i2_mgpu_gather", "i2_mgpu_fetch", "i2_mgpu_refinements", "i2_mgpu_error_summary",
     "i2_mgpu_apply_prepare", "i2_mgpu_apply", "i2_mgpu_apply_result", "i2_apply_prepare", "i2_apply", "i2_apply_rounds", "i2_apply_last_rounds", "i2_apply_finish",
@@ -110,6 +110,8 @@ def load_library():
     L.i2_peer_close.argtypes = [vp, vp]
     L.i2_peer_free.argtypes = [vp, vp]
     L.i2_error_summary.argtypes = [vp, vp, ll, C.POINTER(C.c_double)]
+    L.i2_host_reserve.argtypes = [vp, i32, i32]
+    L.i2_mgpu_reserve.argtypes = [vp, i32, i32]
     L.i2_host_row_costs.argtypes = [vp, i32, vp, vp]
     L.i2_host_run_rounds.argtypes = [vp, i32]
     L.i2_host_last_rounds.argtypes = [vp, C.POINTER(i32), i32]

@@ -942,6 +942,35 @@ extern "C++" int i2::host_run_finalize(i2_context *c, int level, bool wantErrors
     return 0;
 }
 
+// Allocates what the next i2_host_run / i2_mgpu_run of this level will need (work-queue scratch, second result buffer, defect
+// arrays), so that a caller who times the run — the drop-in classes print "Time for ... integration" like the reference, whose
+// buffers are allocated before its timers start (src/evaluators/evaluator3d.cu:122-154) — does not time cudaMalloc.
+int i2_host_reserve(i2_context *c, int level, int check) {
+    if (!c) return I2_E_BADARG;
+    if (!c->hPrepared) return I2_E_NOMESH;
+    I2_CUDA(cudaSetDevice(c->device));
+    for (int k = 0; k < 3; ++k) {
+        const long long n = c->hN[k];
+        if (n == 0) continue;
+        int rc = 0;
+        if (check) rc = ensure(&c->hErrors[k], &c->capErrors[k], (size_t)n);
+        if (!rc && level < 0) {
+            i2_context::ClassScratch &sc = c->scr[k];
+            rc = ensure(&sc.bufB, &sc.bufBCap, (size_t)4 * n);
+            if (!rc && (size_t)n > sc.restCap) {
+                size_t cap0 = sc.restCap, cap1 = sc.restCap;
+                rc = ensure(&sc.rest[0], &cap0, (size_t)n);
+                if (!rc) rc = ensure(&sc.rest[1], &cap1, (size_t)n);
+                if (!rc) sc.restCap = (size_t)n;
+            }
+            if (!rc) rc = ensure(&sc.cellFlag, &sc.cellFlagCap, (size_t)c->nc);
+            if (!rc) rc = ensure(&sc.blockCnt, &sc.blockCntCap, (size_t)kCompareMaxBlocks);
+        }
+        if (rc) return rc;
+    }
+    return 0;
+}
+
 // "bring your own communicator": the two halves of i2_host_run with access to what has to be agreed between the shards
 int i2_host_run_rounds(i2_context *c, int level) { return i2::host_run_rounds(c, level); }
 int i2_host_run_finalize(i2_context *c, int level, int check) { return i2::host_run_finalize(c, level, check != 0); }

@@ -351,6 +351,12 @@ int i2_mgpu_set_results_target(i2_mgpu *mg, int local_index, double *const d_res
     return 0;
 }
 
+int i2_mgpu_reserve(i2_mgpu *mg, int level, int check) {
+    if (!mg) return I2_E_BADARG;
+    if (!mg->prepared) return I2_E_NOMESH;
+    return for_local(mg, [&](int k) { return i2_host_reserve(mg->ctx[k], level, check); });
+}
+
 // One pass of the hot path over every shard.  Nothing is synchronised unless h_stats is given.
 int i2_mgpu_run(i2_mgpu *mg, int level, int check, i2_stats h_stats[3]) {
     if (!mg) return I2_E_BADARG;

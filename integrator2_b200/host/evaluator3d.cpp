@@ -147,6 +147,8 @@ void Evaluator3D::runAllPairsMultiGpu(bool checkCorrectness) {
     printf("\nIntegrating over simple neighbors (%lld pairs), attached neighbors (%lld pairs) and not neighbors (%lld pairs) on %d GPUs...\n",
            counts[0], counts[1], counts[2], lastGpus);
 
+    checkI2Errors(i2_mgpu_reserve(mg, lastLevel, checkCorrectness ? 1 : 0));   // buffers before the timer, like the reference
+    checkI2Errors(i2_mgpu_synchronize(mg));
     i2_stats st[3];
     nvtxRangePushA("all classes integration (multi-GPU)");
     const auto t0 = std::chrono::steady_clock::now();
