@@ -1053,6 +1053,18 @@ cudaError_t preload_kernels() {
     cudaFuncAttributes a;
     cudaError_t e = preload_rest();
     if (e != cudaSuccess) return e;
+    // Looking a kernel up is not enough: the first LAUNCH on a device still pays for loading the image (milliseconds for the large
+    // integrate kernels, and the loads of several devices of one process serialise on a runtime lock: 8 GPUs driven by one
+    // process spent 24 of the 28 ms of their first timed run there).  One empty launch of the hot kernels per context, here.
+    {
+        PackedMesh none{nullptr, nullptr, 0, 0};
+        k_regular_grouped<4, 31><<<1, kThreads>>>(none, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr, nullptr);
+        k_regular_grouped<4, 27><<<1, kThreads>>>(none, nullptr, nullptr, nullptr, 0, 0, 1, 0, nullptr, nullptr);
+        k_integrate<0, MATH_STRICT, 3><<<1, kThreads>>>(none, nullptr, nullptr, nullptr, 0, 0, nullptr);
+        k_integrate<1, MATH_STRICT, 3><<<1, kThreads>>>(none, nullptr, nullptr, nullptr, 0, 0, nullptr);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
 #define I2_TOUCH(...) do { e = cudaFuncGetAttributes(&a, (const void *)(__VA_ARGS__)); if (e != cudaSuccess) return e; } while (0)
     I2_TOUCH(k_integrate<0, MATH_STRICT, 3>);
     I2_TOUCH(k_integrate<1, MATH_STRICT, 3>);
@@ -1061,6 +1073,8 @@ cudaError_t preload_kernels() {
     I2_TOUCH(k_apply_regular<4>);
     I2_TOUCH(k_apply_regular_adaptive<3>);
 #undef I2_TOUCH
+    e = cudaDeviceSynchronize();    // the empty launches above ran on the default stream
+    if (e != cudaSuccess) return e;
     // function attributes are per device: opt in to > 48 KB of dynamic shared memory on the device of the calling context
     return cudaFuncSetAttribute(k_apply_regular_adaptive<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAdaptiveSmemBytes);
 }
@@ -1181,6 +1195,7 @@ template <int CLS>
 __global__ void __launch_bounds__(128)
 k_finalize(PackedMesh pm, const double *__restrict__ verts, const int *__restrict__ tasks, long long n, double *bufA,
            const double *__restrict__ bufB, const QueueState *__restrict__ qs, double *__restrict__ results, QueueState *qsMut) {
+    if (n <= 0) return;       // (the warm-up launch of preload_kernels)
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = t < n;
     if (!active) t = n - 1;   // tail lanes redo the last task without storing: the warp votes inside the closed forms stay full-mask
@@ -1353,6 +1368,12 @@ void launch_selftest_math(int op, const double *a, const double *b, long long n,
 cudaError_t preload_rest() {
     cudaFuncAttributes a;
     cudaError_t e;
+    k_finalize<0><<<1, 128>>>(PackedMesh{nullptr, nullptr, 0, 0}, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+    k_finalize<1><<<1, 128>>>(PackedMesh{nullptr, nullptr, 0, 0}, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+    k_finalize<2><<<1, 128>>>(PackedMesh{nullptr, nullptr, 0, 0}, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr);
+    k_symmetry_error<<<1, 32>>>(nullptr, 0, nullptr);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
 #define I2_TOUCH(...) do { e = cudaFuncGetAttributes(&a, (const void *)(__VA_ARGS__)); if (e != cudaSuccess) return e; } while (0)
     I2_TOUCH(k_finalize<0>);
     I2_TOUCH(k_finalize<1>);
