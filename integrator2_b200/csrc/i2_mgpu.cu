@@ -293,7 +293,8 @@ int i2_mgpu_prepare(i2_mgpu *mg, const double *hv, int nv, const int *hc, int nc
             mg->lo[c][r] = r == 0 ? 0 : align32(pairs[c] * r / W);
             mg->hi[c][r] = r == W - 1 ? pairs[c] : align32(pairs[c] * (r + 1) / W);
         }
-    if (level < 0 && W > 1 && pairs[2] > 0) {
+    static const bool equalCuts = [] { const char *e = getenv("I2_MGPU_EQUAL_CUTS"); return e && atoi(e) != 0; }();   // A/B knob
+    if (level < 0 && W > 1 && pairs[2] > 0 && !equalCuts) {
         std::vector<double> cost(nc);
         std::vector<unsigned long long> first((size_t)nc + 1);
         rc = i2_host_row_costs(mg->ctx[0], 1, cost.data(), first.data());
