@@ -3,6 +3,8 @@
 #include "i2_context.h"
 
 #include <climits>
+#include <cstdint>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -132,6 +134,7 @@ int i2_destroy(i2_context *c) {
     if (c->clsScratch) cudaFree(c->clsScratch);
     if (c->partial) cudaFree(c->partial);
     if (c->depthBuf) cudaFree(c->depthBuf);
+    if (c->roundsGraph) cudaGraphExecDestroy(c->roundsGraph);
     if (c->ap.scratch2) cudaFree(c->ap.scratch2);
     if (c->ap.refCells) cudaFree(c->ap.refCells);
     if (c->ap.regular) cudaFree(c->ap.regular);
@@ -892,12 +895,63 @@ int i2_host_device_views(i2_context *c, const int *tasks[3], const double *resul
 // kernels) on the side streams, the regular class on the context's stream, joined at the end.  At a fixed level the classes are
 // complete afterwards (finalize on the same streams); under error control the finalize step is separate (host_run_finalize),
 // so that a multi-GPU caller can agree on the last round first.
+namespace {
+int host_run_rounds_enqueue(i2_context *c, int level);
+const bool g_useGraphs = [] { const char *e = getenv("I2_GRAPHS"); return !(e && atoi(e) == 0); }();
+}
+
 extern "C++" int i2::host_run_rounds(i2_context *c, int level) {
     if (!c) return I2_E_BADARG;
     if (!c->hPrepared) return I2_E_NOMESH;
     if (!c->haveQuad) return I2_E_NOQUAD;
     if (level > 12) return I2_E_LEVEL;
     I2_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    // Error control = a fixed chain of ~70 small dependent launches (23 per class) whose task counts live on the device: capture it
+    // once per prepared shard and replay it (env I2_GRAPHS=0 turns this off).  Not on the legacy default stream (capture is not
+    // allowed there: the drop-in classes) and not while profiling events are wanted.
+    if (level < 0 && g_useGraphs && s != nullptr && !c->profiling) {
+        int rc = i2_host_reserve(c, level, 0);      // every allocation the chain needs, before the capture (and before the key)
+        if (rc) return rc;
+        // a captured chain stays valid as long as every pointer and count it was recorded with is unchanged (a re-prepare of the same
+        // mesh reuses the buffers): FNV-1a over all of them
+        unsigned long long key = 1469598103934665603ull;
+        auto mix = [&](unsigned long long v) { key = (key ^ v) * 1099511628211ull; };
+        mix((unsigned long long)(level + 7)); mix((unsigned long long)c->mathMode); mix(c->ruleShape13 ? 1 : 0); mix((unsigned long long)c->nc);
+        mix((unsigned long long)c->stride); mix((uintptr_t)c->tri); mix((uintptr_t)c->cells); mix((uintptr_t)c->verts); mix((uintptr_t)c->hRefAll);
+        for (int k = 0; k < 3; ++k) {
+            const i2_context::ClassScratch &sc = c->scr[k];
+            mix((uintptr_t)c->hTasks[k]); mix((uintptr_t)c->hIntegrals[k]); mix((uintptr_t)results_of(c, k)); mix((unsigned long long)c->hN[k]);
+            mix((unsigned long long)c->hHalf[k]); mix((uintptr_t)sc.bufB); mix((uintptr_t)sc.rest[0]); mix((uintptr_t)sc.rest[1]);
+            mix((uintptr_t)sc.cellFlag); mix((uintptr_t)sc.blockCnt); mix((uintptr_t)sc.qs);
+        }
+        if (!c->roundsGraph || c->roundsGraphKey != key) {
+            if (c->roundsGraph) { cudaGraphExecDestroy(c->roundsGraph); c->roundsGraph = nullptr; }
+            const long long before = g_launchCount;
+            I2_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            rc = host_run_rounds_enqueue(c, level);
+            cudaGraph_t graph = nullptr;
+            const cudaError_t e = cudaStreamEndCapture(s, &graph);
+            c->roundsGraphLaunches = g_launchCount - before;
+            g_launchCount -= c->roundsGraphLaunches;     // captured, not launched: the replays count
+            if (rc || e != cudaSuccess) {
+                if (graph) cudaGraphDestroy(graph);
+                return rc ? rc : (int)e;
+            }
+            const cudaError_t ei = cudaGraphInstantiate(&c->roundsGraph, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ei != cudaSuccess) { c->roundsGraph = nullptr; return (int)ei; }
+            c->roundsGraphKey = key;
+        }
+        I2_CUDA(cudaGraphLaunch(c->roundsGraph, s));
+        g_launchCount += c->roundsGraphLaunches;
+        return 0;
+    }
+    return host_run_rounds_enqueue(c, level);
+}
+
+namespace {
+int host_run_rounds_enqueue(i2_context *c, int level) {
     cudaStream_t s = c->stream;
     if (level < 0) I2_CUDA(cudaMemsetAsync(c->hRefAll, 0, (size_t)3 * c->nc, s));
     I2_CUDA(cudaEventRecord(c->forkEv, s));
@@ -919,6 +973,7 @@ extern "C++" int i2::host_run_rounds(i2_context *c, int level) {
     for (int k = 0; k < 2; ++k) I2_CUDA(cudaStreamWaitEvent(s, c->sideDone[k], 0));   // join
     return 0;
 }
+}  // namespace
 
 extern "C++" int i2::host_run_finalize(i2_context *c, int level, bool wantErrors) {
     if (!c) return I2_E_BADARG;

@@ -82,6 +82,11 @@ struct i2_context {
     int *adjFull[2] = {nullptr, nullptr};   // whole ordered lists of the two adjacent classes (shards are copied out of them)
     size_t capAdjFull[2] = {0, 0};
     bool runFused = false;                  // last host_run_rounds fused the regular class's assembly
+    // the ~70 dependent launches of the three classes' error-control chains, captured once per prepared shard and replayed
+    // (CUDA graph): the counts live on the device and the sequence is fixed, only the launch latency is at stake
+    cudaGraphExec_t roundsGraph = nullptr;
+    unsigned long long roundsGraphKey = 0;
+    long long roundsGraphLaunches = 0;      // kernels per replay (for i2_launch_count)
     size_t capVerts = 0, capCells = 0, capNormals = 0, capMeasures = 0, capTasks[3] = {0, 0, 0}, capIntegrals[3] = {0, 0, 0},
            capResults[3] = {0, 0, 0}, capErrors[3] = {0, 0, 0};
     bool incidenceValid = false;            // incScratch / rowOff describe the mesh currently set
