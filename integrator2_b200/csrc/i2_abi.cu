@@ -96,7 +96,15 @@ int i2_create(i2_context **out, int device) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking);
     for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&c->chunkDone[k], cudaEventDisableTiming);
     for (int k = 0; k < 3 && e == cudaSuccess; ++k) e = cudaMalloc((void **)&c->scr[k].qs, sizeof(QueueState));
-    for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaStreamCreateWithFlags(&c->side[k], cudaStreamNonBlocking);
+    // The side streams carry the two adjacent classes: short chains of small dependent kernels next to the regular class's big grids.
+    // At equal priority the block scheduler serves the grid that was launched first, so a small kernel waits until the big one has
+    // dispatched ALL its CTAs and the chains crawl behind the regular class instead of hiding under it; at a higher priority
+    // their CTAs take the next SM slot that frees (env I2_SIDE_PRIORITY=0 restores equal priorities: A/B knob).
+    int prioLeast = 0, prioGreatest = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prioLeast, &prioGreatest);
+    const char *pe = getenv("I2_SIDE_PRIORITY");
+    const int sidePrio = (pe && atoi(pe) == 0) ? prioLeast : prioGreatest;
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaStreamCreateWithPriority(&c->side[k], cudaStreamNonBlocking, sidePrio);
     for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&c->sideDone[k], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->forkEv, cudaEventDisableTiming);
     if (e == cudaSuccess) e = upload_math_tables(c->stream);
