@@ -550,7 +550,9 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
         // A warp walks a contiguous chunk of kChunkIters x (32/G) tasks: lists are sorted by control panel i, so a lane meets
         // the same i (and the same child) in consecutive iterations and its staged Gauss points are reused (13 x 9 FP64 per
         // task saved); chunks are dealt round-robin to the warps of the grid.
-        constexpr int kChunkIters = 16;
+        // (list-driven rounds of the work queue have few tasks and no sorted control panels to reuse: one iteration per chunk, so
+        // that the tasks spread over all warps of the grid instead of queueing 16 deep behind a few of them)
+        const int kChunkIters = list ? 1 : 16;
         const int groupsPerWarp = 32 / G, sub = lane & (G - 1);
         // 32-bit index arithmetic throughout (task counts fit an int: the reference's int3 slots); unsigned for the padded positions
         const unsigned warpId = (blockIdx.x * kThreads + threadIdx.x) >> 5, warpStride = (gridDim.x * kThreads) >> 5;
