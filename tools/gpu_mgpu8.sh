@@ -4,9 +4,8 @@ cd "$GRAFT_REPO_ROOT"
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/e_gpus.txt
 TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1 --master-port 29512"
-for eq in 0 1; do
-I2_MGPU_EQUAL_CUTS=$eq timeout 300 $TR --nproc-per-node 8 bench.py --gpus 8 --mesh s5m2 --scale 0.0005 --level -1 --no-cpu --no-largest --no-e2e > gpurun_out/h_bench_s5m2_ad_n8_eq$eq.json 2> gpurun_out/h_bench_s5m2_ad_n8_eq$eq.err
-done
+timeout 400 $TR --nproc-per-node 8 bench.py --gpus 8 --no-cpu > gpurun_out/e_bench_n8.json 2> gpurun_out/e_bench_n8.err
+timeout 300 $TR --nproc-per-node 8 bench.py --gpus 8 --mesh s5m2 --scale 0.0005 --level -1 --no-cpu --no-largest > gpurun_out/e_bench_s5m2_ad_n8.json 2> gpurun_out/e_bench_s5m2_ad_n8.err
 # the drop-in CLI on 8 GPUs vs 1 (its own wall-clock line)
 python - <<'PY'
 import sys
@@ -18,7 +17,7 @@ cd /tmp
 for g in 8; do I2_GPUS=$g timeout 600 "$GRAFT_REPO_ROOT/integrator2_b200/host/integrator2test3D" -f /tmp/Vint16k.dat -r 0 -c > "$GRAFT_REPO_ROOT/gpurun_out/e_cli_gpus$g.txt" 2>&1; done
 cd "$GRAFT_REPO_ROOT"
 grep -E "Time for|Symmetry" gpurun_out/e_cli_gpus8.txt
-for f in gpurun_out/h_bench_s5m2_ad_n8_eq0.json gpurun_out/h_bench_s5m2_ad_n8_eq1.json; do python - "$f" <<'PY'
+for f in gpurun_out/e_bench_n8.json gpurun_out/e_bench_s5m2_ad_n8.json; do python - "$f" <<'PY'
 import json, sys
 try:
     d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
