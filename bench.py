@@ -501,32 +501,40 @@ def load_kernel_profile():
 
 
 def run_largest_mesh(mg, rank, world, dev, stream, timed_steps):
+    """The two largest configurations of BASELINE.json through i2_mgpu_apply (the whole operator by row blocks, all classes):
+    configs[3] s5m2 refined twice under error control, and (key `sphere`) configs[4] the G1 sphere refined five times at level 0."""
     import numpy as np
     import torch
     from integrator2_b200.meshio import load_fixture, subdivide
-    mesh = subdivide(load_fixture("s5m2", 0.0005), 2)
-    n = mesh.n_cells
-    va, ea, reg = class_pair_counts(mesh)
-    cuts = mg.apply_prepare(mesh.vertices, mesh.cells, -1)
-    state = {}
 
-    def step():
-        state["stats"] = None
-        mg.apply(-1, want_out=False)
+    def one(mesh, level, what, sharding):
+        n = mesh.n_cells
+        va, ea, reg = class_pair_counts(mesh)
+        cuts = mg.apply_prepare(mesh.vertices, mesh.cells, level)
+        ms = timed_steps(lambda: mg.apply(level, want_out=False), 1, 1)
+        out, stats = mg.apply(level, want_out=True, want_stats=True)        # untimed: the result vector and the counts, for the record
+        if rank != 0:
+            return None
+        return {"workload": what.format(n=n, va=va, ea=ea, reg=reg, tot=va + ea + reg),
+                "value": (va + ea + reg) / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": 1, "warmup": 1, "n_gpus": world,
+                "row_cuts": cuts, "sharding": sharding,
+                "rounds": {c: {"last_round": stats[k]["last_round"], "integrated": stats[k]["integrated"], "unconverged": stats[k]["unconverged"]}
+                           for k, c in enumerate(("vertex_adjacent", "edge_adjacent", "regular"))} if level < 0 else None,
+                "checksum_sum_abs": float(np.abs(out).sum()), "checksum_sum": [float(x) for x in out.sum(0)]}
 
-    ms = timed_steps(step, 1, 1)
-    out, stats = mg.apply(-1, want_out=True, want_stats=True)        # untimed: the result vector and the counts, for the record
-    if rank != 0:
-        return None
-    return {"workload": f"s5m2.dat scale 0.0005 refined 2x by midpoint subdivision: {n} triangles, {va} vertex-adjacent + {ea} edge-adjacent + {reg} "
-                        f"regular = {va + ea + reg} ordered pairs, automatic error control (Runge rule, <= 5 rounds), row sums sum_j J(K_i,K_j) over "
-                        "ALL classes (BASELINE.json configs[3] at full size; the reference cannot enumerate N > 46 340)",
-            "value": (va + ea + reg) / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": 1, "warmup": 1, "n_gpus": world,
-            "row_cuts": cuts, "sharding": "row blocks cut by predicted adaptive cost (k_row_cost), multiples of 32 rows; "
-                                          "one NCCL all-reduce of Point3[n] leaves the full vector on every GPU",
-            "rounds": {c: {"last_round": stats[k]["last_round"], "integrated": stats[k]["integrated"], "unconverged": stats[k]["unconverged"]}
-                       for k, c in enumerate(("vertex_adjacent", "edge_adjacent", "regular"))},
-            "checksum_sum_abs": float(np.abs(out).sum()), "checksum_sum": [float(x) for x in out.sum(0)]}
+    big = one(subdivide(load_fixture("s5m2", 0.0005), 2), -1,
+              "s5m2.dat scale 0.0005 refined 2x by midpoint subdivision: {n} triangles, {va} vertex-adjacent + {ea} edge-adjacent + {reg} "
+              "regular = {tot} ordered pairs, automatic error control (Runge rule, <= 5 rounds), row sums sum_j J(K_i,K_j) over "
+              "ALL classes (BASELINE.json configs[3] at full size; the reference cannot enumerate N > 46 340)",
+              "row blocks cut by predicted adaptive cost (k_row_cost), multiples of 32 rows; one NCCL all-reduce of Point3[n] leaves the "
+              "full vector on every GPU")
+    sphere = one(subdivide(load_fixture("G1", 1.0), 5), 0,
+                 "G1.dat sphere refined 5x by midpoint subdivision: {n} triangles, {va} vertex-adjacent + {ea} edge-adjacent + {reg} regular = "
+                 "{tot} ordered pairs, level 0, row sums over ALL classes (BASELINE.json configs[4]: the sharding sweep)",
+                 "equal row blocks (multiples of 32 rows); one NCCL all-reduce of Point3[n]")
+    if big is not None:
+        big["sphere"] = sphere
+    return big
 
 
 def class_pair_counts(mesh):
