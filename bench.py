@@ -328,67 +328,71 @@ def main():
     # ---- N > 1: export to ONE GPU, two ways, timed separately (the default step is row-striped: no rank ingests more than it
     # computed).  Both are bound by rank 0's NVLink ingest, measured by `nvlink_ingest` with plain copies.
     gather_info = peer_info = ingest = None
+    export_error = None
     if world > 1:
-        n_all = [c for c in counts]
-        # (a) NCCL send/recv inside the library (i2_mgpu_gather), after the step's kernels
-        gathered = [torch.empty((n, 3), dtype=torch.float64, device=dev) for n in n_all] if rank == 0 else [None] * 3
+        try:
+            n_all = [c for c in counts]
+            # (a) NCCL send/recv inside the library (i2_mgpu_gather), after the step's kernels
+            gathered = [torch.empty((n, 3), dtype=torch.float64, device=dev) for n in n_all] if rank == 0 else [None] * 3
 
-        def step_gather():
-            mg.run(args.level)
-            for cls in (2, 0, 1):
-                mg.gather(cls, 0, 0, gathered[cls])
+            def step_gather():
+                mg.run(args.level)
+                for cls in (2, 0, 1):
+                    mg.gather(cls, 0, 0, gathered[cls])
 
-        ms_g = timed_steps(step_gather, args.steps, 2)
-        chk_g = [float(g.abs().sum()) for g in gathered] if rank == 0 else None
-        into0 = int(sum(counts) * 24 - sum(my_counts) * 24) if rank == 0 else 0
-        gather_info = {"value": total_pairs / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g, "bytes_into_rank0_per_step": into0,
-                       "checksum_sum_abs_J_on_rank0": chk_g,
-                       "what": "step + i2_mgpu_gather: every result shard sent to rank 0 with ncclSend/ncclRecv by the library"}
-        del gathered
-        torch.cuda.empty_cache()
-        # (b) compute and gather in ONE kernel: rank 0's export arrays are mapped into every process (CUDA IPC) and the
-        # kernels' 16-byte coalesced result stores go straight into them over NVLink (i2_mgpu_set_results_target)
-        from integrator2_b200.multigpu import PeerExport
-        bounds = [[(2 * mg.shard(r)[0][k], 2 * mg.shard(r)[0][k] + mg.shard(r)[1][k]) for r in range(world)] for k in range(3)]
-        exports = [PeerExport(ctx, counts[k], bounds[k], rank, world) for k in range(3)]
-        mg.set_results_target(0, [e.results_arg() for e in exports])
-        ms_p = timed_steps(step, args.steps, 2)
-        chk_peer = [float(e.full.abs().sum()) for e in exports] if rank == 0 else None
-        peer_info = {"value": total_pairs / (ms_p * 1e-3), "unit": UNIT, "ms_per_step": ms_p, "bytes_into_rank0_per_step": into0,
-                     "checksum_sum_abs_J_on_rank0": chk_peer,
-                     "what": "step with compute and gather fused: every rank's kernels store their per-pair Point3 results directly into "
-                             "rank 0's export arrays over NVLink peer mappings (i2_peer_*, i2_mgpu_set_results_target); no NCCL call, no staging copy"}
-        # (c) the ceiling both are measured against: all other ranks copy a buffer of the same size into rank 0 at once
-        nbytes = exports[2].bounds[rank][1] * 24 - exports[2].bounds[rank][0] * 24
-        src = torch.empty((max(nbytes // 8, 1),), dtype=torch.float64, device=dev).normal_()
-        dst = torch.as_tensor(abi._RawCudaBuffer(exports[2].results_arg(), (max(nbytes // 8, 1),), "<f8"), device=dev)
+            ms_g = timed_steps(step_gather, args.steps, 2)
+            chk_g = [float(g.abs().sum()) for g in gathered] if rank == 0 else None
+            into0 = int(sum(counts) * 24 - sum(my_counts) * 24) if rank == 0 else 0
+            gather_info = {"value": total_pairs / (ms_g * 1e-3), "unit": UNIT, "ms_per_step": ms_g, "bytes_into_rank0_per_step": into0,
+                           "checksum_sum_abs_J_on_rank0": chk_g,
+                           "what": "step + i2_mgpu_gather: every result shard sent to rank 0 with ncclSend/ncclRecv by the library"}
+            del gathered
+            torch.cuda.empty_cache()
+            # (b) compute and gather in ONE kernel: rank 0's export arrays are mapped into every process (CUDA IPC) and the
+            # kernels' 16-byte coalesced result stores go straight into them over NVLink (i2_mgpu_set_results_target)
+            from integrator2_b200.multigpu import PeerExport
+            bounds = [[(2 * mg.shard(r)[0][k], 2 * mg.shard(r)[0][k] + mg.shard(r)[1][k]) for r in range(world)] for k in range(3)]
+            exports = [PeerExport(ctx, counts[k], bounds[k], rank, world) for k in range(3)]
+            mg.set_results_target(0, [e.results_arg() for e in exports])
+            ms_p = timed_steps(step, args.steps, 2)
+            chk_peer = [float(e.full.abs().sum()) for e in exports] if rank == 0 else None
+            peer_info = {"value": total_pairs / (ms_p * 1e-3), "unit": UNIT, "ms_per_step": ms_p, "bytes_into_rank0_per_step": into0,
+                         "checksum_sum_abs_J_on_rank0": chk_peer,
+                         "what": "step with compute and gather fused: every rank's kernels store their per-pair Point3 results directly into "
+                                 "rank 0's export arrays over NVLink peer mappings (i2_peer_*, i2_mgpu_set_results_target); no NCCL call, no staging copy"}
+            # (c) the ceiling both are measured against: all other ranks copy a buffer of the same size into rank 0 at once
+            nbytes = exports[2].bounds[rank][1] * 24 - exports[2].bounds[rank][0] * 24
+            src = torch.empty((max(nbytes // 8, 1),), dtype=torch.float64, device=dev).normal_()
+            dst = torch.as_tensor(abi._RawCudaBuffer(exports[2].results_arg(), (max(nbytes // 8, 1),), "<f8"), device=dev)
 
-        def copy_in():
-            if rank != 0:
-                dst.copy_(src)
+            def copy_in():
+                if rank != 0:
+                    dst.copy_(src)
 
-        ms_c = timed_steps(copy_in, 5, 2)
-        moved = counts[2] * 24 - my_counts[2] * 24 if rank == 0 else 0
-        mv = torch.tensor([moved], dtype=torch.float64, device=dev)
-        dist.all_reduce(mv, op=dist.ReduceOp.MAX)
-        ingest = {"gb_per_s": float(mv.item()) / (ms_c * 1e-3) / 1e9, "bytes": int(mv.item()), "ms": ms_c,
-                  "what": f"{world - 1} ranks copy their regular-class result shard (torch copy_ = cudaMemcpy-class kernel) into rank 0's "
-                          "peer-mapped array simultaneously: the NVLink ingest ceiling of one GPU on this box"}
-        if rank == 0:
-            floor_ms = into0 / 1e9 / ingest["gb_per_s"] * 1e3      # the bytes alone at the copy ceiling, nothing else running
-            for info in (gather_info, peer_info):
-                info["extra_ms_over_resident_step"] = info["ms_per_step"] - ms_step
-                info["ingest_gb_per_s"] = info["bytes_into_rank0_per_step"] / (info["ms_per_step"] * 1e-3) / 1e9
-                # lower bound of an export step: the slower of the resident step and the ingest of rank 0 at the copy ceiling
-                info["bound_ms"] = max(ms_step, floor_ms)
-                info["frac_of_bound"] = info["bound_ms"] / info["ms_per_step"]
-            ingest["ms_for_this_export_at_ceiling"] = floor_ms
-        barrier()
-        mg.set_results_target(0, None)
-        del dst, src
-        for e in exports:
-            e.close()
-        barrier()
+            ms_c = timed_steps(copy_in, 5, 2)
+            moved = counts[2] * 24 - my_counts[2] * 24 if rank == 0 else 0
+            mv = torch.tensor([moved], dtype=torch.float64, device=dev)
+            dist.all_reduce(mv, op=dist.ReduceOp.MAX)
+            ingest = {"gb_per_s": float(mv.item()) / (ms_c * 1e-3) / 1e9, "bytes": int(mv.item()), "ms": ms_c,
+                      "what": f"{world - 1} ranks copy their regular-class result shard (torch copy_ = cudaMemcpy-class kernel) into rank 0's "
+                              "peer-mapped array simultaneously: the NVLink ingest ceiling of one GPU on this box"}
+            if rank == 0:
+                floor_ms = into0 / 1e9 / ingest["gb_per_s"] * 1e3      # the bytes alone at the copy ceiling, nothing else running
+                for info in (gather_info, peer_info):
+                    info["extra_ms_over_resident_step"] = info["ms_per_step"] - ms_step
+                    info["ingest_gb_per_s"] = info["bytes_into_rank0_per_step"] / (info["ms_per_step"] * 1e-3) / 1e9
+                    # lower bound of an export step: the slower of the resident step and the ingest of rank 0 at the copy ceiling
+                    info["bound_ms"] = max(ms_step, floor_ms)
+                    info["frac_of_bound"] = info["bound_ms"] / info["ms_per_step"]
+                ingest["ms_for_this_export_at_ceiling"] = floor_ms
+            barrier()
+            mg.set_results_target(0, None)
+            del dst, src
+            for e in exports:
+                e.close()
+            barrier()
+        except Exception as e:  # noqa: BLE001  (the export variants are side measurements: never lose the headline line over them)
+            export_error = repr(e)
 
     # ---- end to end through the host-buffer C ABI: host mesh in -> sharded prepare (H2D, geometry, classification by
     # vertex incidence, this rank's task lists) -> three classes -> checksums over all ranks (NCCL) read back.
@@ -470,7 +474,7 @@ def main():
                            "l2": "inputs+outputs per step (task lists 12 B/pair, results 56 B/pair) are far larger than L2; no flush needed"},
                 "clocks": clocks, "gpu_launches": launches, "per_rank_ms_per_step": step_per_rank_ms or None, "e2e": e2e, "roofline": roof,
                 "cpu_baseline": cpu,
-                "with_gather_to_rank0": gather_info, "with_peer_store_to_rank0": peer_info, "nvlink_ingest": ingest,
+                "with_gather_to_rank0": gather_info, "with_peer_store_to_rank0": peer_info, "nvlink_ingest": ingest, "export_variants_error": export_error,
                 "largest_mesh": largest, "checksum_sum_abs_J": checksum}
         print(json.dumps(line), flush=True)
     mg.close()

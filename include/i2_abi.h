@@ -235,6 +235,9 @@ int i2_host_device_views(i2_context *ctx, const int *d_tasks[3], const double *d
  *                     assembly (the value of a converged pair depends on the parity of the GLOBAL last round) and
  *                     of the per-cell refinement counters.  Asynchronous unless h_stats (per-round counts summed over all
  *                     shards) is given.
+ *                     With one process per GPU every call that returns job-wide numbers is COLLECTIVE — i2_mgpu_run with h_stats,
+ *                     i2_mgpu_checksums, i2_mgpu_error_summary, i2_mgpu_apply with h_stats, and i2_mgpu_run / i2_mgpu_apply under
+ *                     error control in any case: all ranks make the same calls in the same order.
  *   i2_mgpu_checksums per class (sum J_x, J_y, J_z, sum |J|_1) over ALL shards (all-reduce), the step's small metric
  *   i2_mgpu_shard     forward-slot range of any rank: first slot and task count 2 (hi - lo) per class
  *   i2_mgpu_fetch     row-striped export: one local GPU's shard (tasks, results, defects; shard order) to host arrays

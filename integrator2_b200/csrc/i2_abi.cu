@@ -975,6 +975,10 @@ int host_run_rounds_enqueue(i2_context *c, int level) {
             if (!rc && level >= 0 && !fused) rc = enqueue_finalize(c, k, c->hTasks[k], c->hN[k], c->hIntegrals[k], results_of(c, k), st);
             if (rc) return rc;
             if (prof) I2_CUDA(cudaEventRecord(c->prof[2], st));
+        } else {
+            // an empty shard of this class (more GPUs than 32-task groups): its last round must still read 0, a multi-GPU
+            // caller takes the maximum over the shards next
+            I2_CUDA(cudaMemsetAsync(c->scr[k].qs, 0, sizeof(QueueState), st));
         }
         if (k < 2) I2_CUDA(cudaEventRecord(c->sideDone[k], st));
     }

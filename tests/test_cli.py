@@ -22,6 +22,7 @@ def test_cli_argument_handling_without_gpu(tmp_path):
     assert os.path.exists(CLI), "build with make -C integrator2_b200/host"
     r = _run([], tmp_path)
     assert r.returncode == 0 and "USAGE: integrator2test3D [options]" in r.stdout and "--exporttocsv" in r.stdout
+    assert "--exportbinary" in r.stdout and "I2_GPUS" in r.stdout      # round-2 additions: binary export, multi-GPU environment
     assert _run(["--help"], tmp_path).returncode == 0
     r = _run(["-c"], tmp_path)
     assert r.returncode != 0 and "No input file with mesh specified. Exiting" in r.stdout
