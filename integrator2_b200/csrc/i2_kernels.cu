@@ -468,7 +468,9 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
     constexpr bool PROJ = (VAR & 16) != 0 && DERIVE;
     constexpr int UNR = (VAR & 32) ? 1 : kPointUnroll;
     constexpr int FIX = (VAR & 64) ? 13 : 0;
+    constexpr bool LEVEL1 = (VAR & 128) != 0 && !LEVEL0;   // round 1 of the work queue: 4 lanes per task, one child each
     if (LEVEL0) level = 0;
+    if (LEVEL1) level = 1;
     const LaneLayout lay(level);
     const int G = lay.G, perLane = lay.perLane;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -508,7 +510,7 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
             }
             double a1, a2, a3, a4;
             grouped_eval<EDGELEN, RESID, DERIVE, PROJ, kThreads, UNR, FIX>(myM, ng, T, a1, a2, a3, a4, vmask);
-            if (LEVEL0) { s1 = Si * a1; s2 = Si * a2; s3 = Si * a3; s4 = Si * a4; }
+            if (LEVEL0 || LEVEL1) { s1 = Si * a1; s2 = Si * a2; s3 = Si * a3; s4 = Si * a4; }
             else { s1 = fma(Si, a1, s1); s2 = fma(Si, a2, s2); s3 = fma(Si, a3, s3); s4 = fma(Si, a4, s4); }
         }
         return vec4(s1 * T.tc + s2 * T.ta + s3 * T.tb, s4);
@@ -1039,7 +1041,9 @@ void launch_integrate(int cls, int mathMode, const PackedMesh &pm, const int *ta
         case 59: I2_LAUNCH_GROUPED(MB, 59); break; case 63: I2_LAUNCH_GROUPED(MB, 63); break;                   \
         default: if (level == 0) I2_LAUNCH_GROUPED(MB, 31); else I2_LAUNCH_GROUPED(MB, 27); break;                       \
         }
+        static const int useLevel1 = [] { const char *e = getenv("I2_LEVEL1"); return (e && atoi(e) == 0) ? 0 : 1; }();   // A/B knob
         if (var & 64) { if (level == 0) I2_LAUNCH_GROUPED(4, 95); else I2_LAUNCH_GROUPED(4, 91); }
+        else if (level == 1 && !list && useLevel1 && g_minBlocks == 4 && var == 27) I2_LAUNCH_GROUPED(4, 155);   // 27 | 128
         else if (g_minBlocks == 3) { I2_PICK_VAR(3) }
         else if (g_minBlocks == 5) { I2_PICK_VAR(5) }
         else { I2_PICK_VAR(4) }
