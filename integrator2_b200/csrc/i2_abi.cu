@@ -107,6 +107,7 @@ int i2_create(i2_context **out, int device) {
     for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaStreamCreateWithPriority(&c->side[k], cudaStreamNonBlocking, sidePrio);
     for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&c->sideDone[k], cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->forkEv, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->sumScratch, sizeof(double) * 16);
     if (e == cudaSuccess) e = upload_math_tables(c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     if (e == cudaSuccess) e = preload_kernels();
@@ -130,6 +131,7 @@ int i2_destroy(i2_context *c) {
         if (c->chunkDone[k]) cudaEventDestroy(c->chunkDone[k]);
     }
     if (c->forkEv) cudaEventDestroy(c->forkEv);
+    if (c->sumScratch) cudaFree(c->sumScratch);
     for (auto &sc : c->scr) {
         if (sc.bufB) cudaFree(sc.bufB);
         for (int k = 0; k < 2; ++k) if (sc.rest[k]) cudaFree(sc.rest[k]);
@@ -700,13 +702,11 @@ int i2_error_summary(i2_context *c, const double *errors, long long n, double ou
     out[0] = out[1] = 0.0;
     if (n == 0) return 0;
     I2_CUDA(cudaSetDevice(c->device));
-    double *d = nullptr;
-    I2_CUDA(cudaMalloc((void **)&d, sizeof(double) * 2));
+    double *d = c->sumScratch + 12;
     I2_CUDA(cudaMemsetAsync(d, 0, sizeof(double) * 2, c->stream));
     launch_error_summary(errors, n, d, c->numSMs, c->stream);
     I2_CUDA(cudaMemcpyAsync(out, d, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
     I2_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(d);
     out[1] /= (double)n;
     return 0;
 }
@@ -810,7 +810,7 @@ extern "C++" int i2::host_prepare_lists(i2_context *c) {
     launch_regular_fill(c->hCells, nc, c->rowOff, (unsigned long long)lo[2], (unsigned long long)hi[2], c->hTasks[2],
                         c->hTasks[2] + 3 * (hi[2] - lo[2]), c->numSMs, s);
     I2_CUDA(cudaGetLastError());
-    I2_CUDA(cudaStreamSynchronize(s));
+    // no synchronisation here: everything that consumes the lists is enqueued on the same stream
     for (int k = 0; k < 3; ++k) {
         c->hLo[k] = lo[k];
         c->hHalf[k] = hi[k] - lo[k];
@@ -880,13 +880,11 @@ int i2_host_checksums(i2_context *c, double sums[12]) {
     if (!c || !sums) return I2_E_BADARG;
     if (!c->hPrepared) return I2_E_NOMESH;
     I2_CUDA(cudaSetDevice(c->device));
-    double *d = nullptr;
-    I2_CUDA(cudaMalloc((void **)&d, sizeof(double) * 12));
+    double *d = c->sumScratch;
     I2_CUDA(cudaMemsetAsync(d, 0, sizeof(double) * 12, c->stream));
     for (int k = 0; k < 3; ++k) launch_checksum(results_of(c, k), c->hN[k], d + 4 * k, c->numSMs, c->stream);
     I2_CUDA(cudaMemcpyAsync(sums, d, sizeof(double) * 12, cudaMemcpyDeviceToHost, c->stream));
     I2_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(d);
     return 0;
 }
 

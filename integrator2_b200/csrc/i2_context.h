@@ -89,6 +89,7 @@ struct i2_context {
     long long roundsGraphLaunches = 0;      // kernels per replay (for i2_launch_count)
     size_t capVerts = 0, capCells = 0, capNormals = 0, capMeasures = 0, capTasks[3] = {0, 0, 0}, capIntegrals[3] = {0, 0, 0},
            capResults[3] = {0, 0, 0}, capErrors[3] = {0, 0, 0};
+    double *sumScratch = nullptr;           // 16 doubles: checksums / summaries without a cudaMalloc per call
     bool incidenceValid = false;            // incScratch / rowOff describe the mesh currently set
     // operator apply (i2_apply_*): row block, row-major adjacent lists of the block, their buffers
     struct ApplyState {

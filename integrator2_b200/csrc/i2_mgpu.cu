@@ -588,21 +588,27 @@ int i2_mgpu_checksums(i2_mgpu *mg, double sums[12]) {
     if (!mg || !sums) return I2_E_BADARG;
     if (!mg->prepared) return I2_E_NOMESH;
     for (int e = 0; e < 12; ++e) sums[e] = 0.0;
+    if (mg->world > mg->nLocal) {
+        // one process per GPU: checksum kernels, all-reduce on the device, ONE copy back and one synchronisation
+        NcclApi *api = nccl_api();
+        if (!api) return I2_E_NCCL;
+        i2_context *c = mg->ctx[0];
+        I2_CUDA(cudaSetDevice(c->device));
+        double *d = mg->scratch[0];
+        I2_CUDA(cudaMemsetAsync(d, 0, sizeof(double) * 12, c->stream));
+        for (int k = 0; k < 3; ++k)
+            launch_checksum(c->hResultsTarget[k] ? c->hResultsTarget[k] : c->hResults[k], c->hN[k], d + 4 * k, c->numSMs, c->stream);
+        I2_CUDA(cudaGetLastError());
+        I2_NCCL(api->AllReduce(d, d, 12, ncclFloat64, ncclSum, mg->comm[0], c->stream));
+        I2_CUDA(cudaMemcpyAsync(sums, d, sizeof(double) * 12, cudaMemcpyDeviceToHost, c->stream));
+        I2_CUDA(cudaStreamSynchronize(c->stream));
+        return 0;
+    }
     for (int k = 0; k < mg->nLocal; ++k) {
         double part[12];
         const int rc = i2_host_checksums(mg->ctx[k], part);
         if (rc) return rc;
         for (int e = 0; e < 12; ++e) sums[e] += part[e];
-    }
-    if (mg->world > mg->nLocal) {
-        NcclApi *api = nccl_api();
-        if (!api) return I2_E_NCCL;
-        i2_context *c = mg->ctx[0];
-        I2_CUDA(cudaSetDevice(c->device));
-        I2_CUDA(cudaMemcpyAsync(mg->scratch[0], sums, sizeof(double) * 12, cudaMemcpyHostToDevice, c->stream));
-        I2_NCCL(api->AllReduce(mg->scratch[0], mg->scratch[0], 12, ncclFloat64, ncclSum, mg->comm[0], c->stream));
-        I2_CUDA(cudaMemcpyAsync(sums, mg->scratch[0], sizeof(double) * 12, cudaMemcpyDeviceToHost, c->stream));
-        I2_CUDA(cudaStreamSynchronize(c->stream));
     }
     return 0;
 }
