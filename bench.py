@@ -154,7 +154,7 @@ def run_reference(args, mesh, n_pairs_total):
                                      "sample": "whole workload; the reference is CUDA-only (no CPU path): its unmodified sources compiled for sm_100, "
                                                "1 host thread + this B200, time window = its own three 'Time for ... integration' lines"},
                     "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-            print(json.dumps(line), flush=True)
+            emit(line)
             return
     # fallback: CPU oracle port on all host cores, bounded sample
     from oracle import oracle_py as O
@@ -165,10 +165,32 @@ def run_reference(args, mesh, n_pairs_total):
             "data": f"reference example mesh (tests/golden/meshes.npz, parsed from {args.mesh}.dat); no random data", "config": cfg,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": c, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything native libraries print to fd 1 while we run (NCCL announces its version there on the first communicator) goes
+    to stderr; emit() writes the ONE JSON line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+    else:
+        emit(line)
 
 
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -476,7 +498,7 @@ def main():
                 "cpu_baseline": cpu,
                 "with_gather_to_rank0": gather_info, "with_peer_store_to_rank0": peer_info, "nvlink_ingest": ingest, "export_variants_error": export_error,
                 "largest_mesh": largest, "checksum_sum_abs_J": checksum}
-        print(json.dumps(line), flush=True)
+        emit(line)
     mg.close()
     if world > 1:
         dist.destroy_process_group()
@@ -661,7 +683,7 @@ def run_matrix_free(args):
         chk = float((full if world > 1 else out).abs().sum())
         if adaptive:
             hist = torch.bincount(last["refinements"].int()).tolist()
-            print(json.dumps({"metric": METRIC, "value": pairs / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            emit({"metric": METRIC, "value": pairs / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                               "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                               "data": f"synthetic: {args.mf_mesh} (scale {args.scale}) refined {args.sphere_level}x by midpoint subdivision (deterministic, no RNG)",
                               "config": {"workload": f"matrix-free regular class under automatic error control (Runge rule, <= 5 rounds per pair): {n} triangles, "
@@ -669,11 +691,11 @@ def run_matrix_free(args):
                                          "sharding": f"{world} contiguous row blocks", "l2": "mesh SoA is L2-resident by design; no per-pair HBM traffic"},
                               "clocks": clocks, "gpu_launches": launches, "e2e": None, "roofline": None, "cpu_baseline": None,
                               "rank0_rounds": {k: last[k] for k in ("last_round", "global_last_round", "integrated", "unconverged")},
-                              "rank0_refinement_histogram": hist, "checksum_sum_abs": chk}), flush=True)
+                              "rank0_refinement_histogram": hist, "checksum_sum_abs": chk})
             if world > 1:
                 dist.destroy_process_group()
             return
-        print(json.dumps({"metric": METRIC, "value": pairs / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        emit({"metric": METRIC, "value": pairs / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                           "data": "synthetic: G1 sphere refined by midpoint subdivision (deterministic, no RNG)",
                           "config": {"workload": f"matrix-free regular class, G1 sphere refined {args.sphere_level}x: {n} triangles, {pairs} ordered regular pairs "
@@ -682,7 +704,7 @@ def run_matrix_free(args):
                           "clocks": clocks, "gpu_launches": launches, "e2e": None,
                           "roofline": {"bound": "fp64", "achieved": achieved / world, "peak": dfma_tf, "unit": "TFLOP/s", "frac": achieved / world / dfma_tf,
                                        "traffic": None, "kernel": "k_apply_regular", "note": "per GPU; same work model as the list kernel"},
-                          "cpu_baseline": None, "checksum_sum_abs": chk}), flush=True)
+                          "cpu_baseline": None, "checksum_sum_abs": chk})
     if world > 1:
         dist.destroy_process_group()
 
