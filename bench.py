@@ -186,7 +186,8 @@ def emit(line):
     if _REAL_STDOUT is not None:
         os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
     else:
-        emit(line)
+        sys.stdout.write(json.dumps(line) + "\n")
+        sys.stdout.flush()
 
 
 def main():
