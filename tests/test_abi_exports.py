@@ -67,3 +67,16 @@ def test_ctypes_binding_matches_the_header_prototypes():
         fn = getattr(L, name)
         assert fn.argtypes is not None, f"{name}: no argtypes in abi.py"
         assert len(fn.argtypes) == n, f"{name}: header has {n} parameters, abi.py declares {len(fn.argtypes)}"
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: include/i2_abi.h must compile as C99 (no C++-only constructs, no torch or CUDA types)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    assert gcc, "gcc is part of the image"
+    r = subprocess.run([gcc, "-x", "c", "-std=c99", "-fsyntax-only", "-Wall", "-pedantic", os.path.join(ROOT, "include", "i2_abi.h")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    code = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "i2_abi.h")).read(), flags=re.S)     # comments may mention torch
+    assert "torch" not in code.lower() and "cudaStream_t" not in code and "#include" not in code
