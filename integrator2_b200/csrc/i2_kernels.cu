@@ -623,10 +623,12 @@ k_regular_grouped(PackedMesh pm, const int *__restrict__ tasks, const int *__res
 constexpr int kTileJ = 32;
 constexpr int kTileStride = 29;   // 24 geometry + 3 normal + 1 weight + 1 pad(ids live in a separate int array)
 
-template <int MINB>
+// TILE = columns per shared-memory tile (32, or 16 so that five CTAs fit the SM's shared memory: MINB = 5)
+template <int MINB, int TILE = kTileJ>
 __global__ void __launch_bounds__(kThreads, MINB)
 k_apply_regular(PackedMesh pm, int rowLo, int rowHi, int colLo, int colHi, int colChunk, const double *__restrict__ weights,
                 double *__restrict__ partial) {
+    constexpr int kTileJ = TILE;   // shadows the namespace constant inside this kernel
     __shared__ double smM[MAX_GAUSS_POINTS * 3 * kThreads];
     __shared__ double smT[kTileJ * kTileStride];
     __shared__ int smId[kTileJ * 3];
@@ -716,7 +718,12 @@ void launch_apply_regular(const PackedMesh &pm, int rowLo, int rowHi, int colLo,
     const int colChunk = (cols + chunks - 1) / chunks;
     dim3 grid((rows + kThreads - 1) / kThreads, chunks);
     ++g_launchCount;
-    k_apply_regular<4><<<grid, kThreads, 0, s>>>(pm, rowLo, rowHi, colLo, colHi, colChunk, weights, partial);
+    // 94 registers without spills and 16-column tiles (44 KB of shared memory) let five CTAs share an SM: 849 ms against
+    // 886 ms with four (126 registers, 32-column tiles) on the 108 544-triangle sphere, same bits
+    // (profiles/r02_ab_apply_minb.log).  env I2_APPLY_MINB=4 restores the four-CTA variant.
+    static const int minb = [] { const char *e = getenv("I2_APPLY_MINB"); return e ? atoi(e) : 5; }();
+    if (minb == 5) k_apply_regular<5, 16><<<grid, kThreads, 0, s>>>(pm, rowLo, rowHi, colLo, colHi, colChunk, weights, partial);
+    else k_apply_regular<4><<<grid, kThreads, 0, s>>>(pm, rowLo, rowHi, colLo, colHi, colChunk, weights, partial);
     ++g_launchCount;
     k_reduce_partials<<<(rows * 3 + 255) / 256, 256, 0, s>>>(partial, rows, chunks, out3);
 }
@@ -982,7 +989,11 @@ void launch_apply_regular_adaptive(const PackedMesh &pm, int rowLo, int rowHi, i
     ApplyAdaptiveOut o{partial6, depth, lastRound, counts6};
     constexpr size_t smem = kAdaptiveSmemBytes;
     ++g_launchCount;
-    k_apply_regular_adaptive<3><<<grid, kThreads, smem, s>>>(pm, rowLo, rowHi, colLo, colHi, colChunk, weights, o);
+    // four CTAs per SM at 128 registers: 441 ms against 451 ms with three (168 registers) on s5m2 refined once, same bits
+    // (profiles/r02_ab_apply_minb.log) — the extra spill traffic sits in the rare deep rounds.  env I2_APPLY_AD_MINB=3 restores.
+    static const int minb = [] { const char *e = getenv("I2_APPLY_AD_MINB"); return e ? atoi(e) : 4; }();
+    if (minb == 4) k_apply_regular_adaptive<4><<<grid, kThreads, smem, s>>>(pm, rowLo, rowHi, colLo, colHi, colChunk, weights, o);
+    else k_apply_regular_adaptive<3><<<grid, kThreads, smem, s>>>(pm, rowLo, rowHi, colLo, colHi, colChunk, weights, o);
     if (out3) launch_reduce_partials_adaptive(partial6, depth, rows, chunks, lastRound, out3, other3, refinements, s);
 }
 
@@ -1077,11 +1088,14 @@ cudaError_t preload_kernels() {
     I2_TOUCH(k_regular_grouped<4, 31>);
     I2_TOUCH(k_regular_grouped<4, 27>);
     I2_TOUCH(k_apply_regular<4>);
+    I2_TOUCH((k_apply_regular<5, 16>));
     I2_TOUCH(k_apply_regular_adaptive<3>);
 #undef I2_TOUCH
     e = cudaDeviceSynchronize();    // the empty launches above ran on the default stream
     if (e != cudaSuccess) return e;
     // function attributes are per device: opt in to > 48 KB of dynamic shared memory on the device of the calling context
+    e = cudaFuncSetAttribute(k_apply_regular_adaptive<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAdaptiveSmemBytes);
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_apply_regular_adaptive<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAdaptiveSmemBytes);
 }
 
